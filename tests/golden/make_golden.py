@@ -1,0 +1,199 @@
+"""Generate golden vectors from the UNMODIFIED reference (run in the build container only).
+
+    python tests/golden/make_golden.py            # needs /root/reference on disk
+
+The reference has no tests of its own, so parity is pinned by running its code
+in-process here and committing the outputs as small fixtures under tests/golden/.  Nothing is
+copied from the reference: the script imports it, feeds deterministic inputs/weights
+(tests/golden/detfill.py) and stores what comes out.  Harness: 1-rank gloo process
+group + ``torch.Tensor.cuda`` identity shim because ``compute_var`` hard-codes ``.cuda()`` and
+``all_reduce`` (audiossl/models/atst/byol.py:42-53).
+"""
+import os
+import sys
+from functools import partial
+
+import numpy as np
+import torch
+from torch import nn
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, "/root/reference")
+
+from tests.golden import detfill  # noqa: E402
+
+
+def harness():
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29591")
+        dist.init_process_group("gloo", rank=0, world_size=1)
+    torch.Tensor.cuda = lambda self, *a, **k: self
+
+
+def load_det(module):
+    sd = module.state_dict()
+    new = detfill.fill_state_dict(sd)
+    module.load_state_dict({k: (torch.from_numpy(new[k]) if k in new else v) for k, v in sd.items()})
+
+
+def flat(prefix, d, out):
+    for k, v in d.items():
+        out[prefix + "/" + k] = v
+
+
+def grads_summary(module, out, prefix):
+    for name, p in module.named_parameters():
+        if p.grad is None:
+            continue
+        flat(prefix + "/grad/" + name, detfill.summarize(p.grad.numpy()), out)
+
+
+# ----------------------------------------------------------------------------- mel
+def gen_mel():
+    from audiossl.methods.atst.transform import ATSTTrainTransform
+    import torchaudio
+    from audiossl.transforms.common import MinMax
+    from torchvision import transforms
+    out = {}
+    tf1024 = ATSTTrainTransform().mel_feature
+    mel640 = torchaudio.transforms.MelSpectrogram(16000, f_min=60, f_max=7800, hop_length=160,
+                                                  win_length=640, n_fft=1024, n_mels=64)
+    tf640 = transforms.Compose([mel640, torchaudio.transforms.AmplitudeToDB(stype="power", top_db=80),
+                                MinMax(min=-79.6482, max=50.6842)])
+    cases = [("noise", 16000), ("sine_silence", 16000), ("chirp", 16000), ("zeros", 16000),
+             ("impulses", 16000), ("noise", 8000), ("noise", 1600), ("noise", 40000), ("chirp", 96000),
+             ("noise", 160000), ("sine_silence", 160000)]
+    for kind, n in cases:
+        wav = torch.from_numpy(detfill.signal(kind, n))[None]
+        for win, tf in ((1024, tf1024), (640, tf640)):
+            if win == 640 and n > 40000:
+                continue
+            y = tf(wav)  # [1,64,T]
+            out["%s_%d_w%d" % (kind, n, win)] = y.numpy()
+    # batched 4-D input: per-clip top_db reference (embedding.py:57-60 relies on [B,1,n] -> [B,1,64,T])
+    wavs = torch.stack([torch.from_numpy(detfill.signal(k, 16000)) for k in ("noise", "sine_silence", "chirp")])
+    out["batch3_16000_w1024"] = tf1024(wavs[:, None]).numpy()
+    np.savez_compressed(os.path.join(HERE, "mel.npz"), **out)
+    print("mel.npz", len(out))
+
+
+# ----------------------------------------------------------------------------- encoder / loss
+def make_inputs(tag, B, widths, lens):
+    crops, lengths = [], []
+    for i, (w, l) in enumerate(zip(widths, lens)):
+        crops.append(torch.from_numpy(detfill.det_array("%s/crop%d" % (tag, i), (B, 1, 64, w), 1.0, "uniform")))
+        lengths.append(torch.tensor(l, dtype=torch.int64))
+    return crops, lengths
+
+
+class RefATSTLike(nn.Module):
+    """ATST.forward (models/atst/atst.py:24-28) over arbitrary encoder sizes, reference parts only."""
+
+    def __init__(self, embed_dim, depth, heads, ncrops, drop_path_rate=0.0):
+        super().__init__()
+        from audiossl.models.atst.byol import MultiCropWrapper, ByolLoss
+        from audiossl.models.atst.audio_transformer import AST
+        mk = lambda: AST(patch_h=64, patch_w=4, embed_dim=embed_dim, depth=depth, num_heads=heads,
+                         qkv_bias=False, norm_layer=partial(nn.LayerNorm, eps=1e-6),
+                         drop_path_rate=drop_path_rate)
+        self.student = MultiCropWrapper(mk(), embed_dim, predictor=True)
+        self.teacher = MultiCropWrapper(mk(), embed_dim, predictor=False)
+        for p in self.teacher.parameters():
+            p.requires_grad = False
+        self.loss_fn = ByolLoss(ncrops)
+
+    def forward(self, melspecs, lengths):
+        t = self.teacher(melspecs[:2], lengths[:2])
+        s = self.student(melspecs, lengths)
+        return self.loss_fn(s, t), s, t
+
+
+def run_case(model, tag, B, widths, lens, out, record_rand=False):
+    load_det(model)
+    model.train()
+    crops, lengths = make_inputs(tag, B, widths, lens)
+    rec = []
+    if record_rand:
+        orig = torch.rand
+
+        def rand(*a, **k):
+            r = orig(*a, **k)
+            rec.append(r.reshape(-1).clone())
+            return r
+        torch.rand = rand
+    try:
+        (loss, std_s, std_t), s, t = model(crops, lengths)
+    finally:
+        if record_rand:
+            torch.rand = orig
+    loss.backward()
+    out[tag + "/loss"] = np.float32(loss.item())
+    out[tag + "/std_s"] = np.float32(std_s.item())
+    out[tag + "/std_t"] = np.float32(std_t.item())
+    out[tag + "/student_out"] = s.detach().numpy()
+    out[tag + "/teacher_out"] = t.detach().numpy()
+    grads_summary(model.student, out, tag)
+    for name, b in model.named_buffers():
+        if "running" in name:
+            flat(tag + "/buf/" + name, detfill.summarize(b.numpy()), out)
+    if record_rand:
+        out[tag + "/rand"] = torch.stack(rec).numpy()  # [n_calls, rows]
+    return model
+
+
+def gen_atst():
+    harness()
+    out = {}
+    # tiny: D=128, depth 2, 2 heads (dh=64 as in every real config); full + ragged lengths
+    m = RefATSTLike(128, 2, 2, ncrops=2)
+    run_case(m, "tiny2", 3, [101, 101], [[101, 77, 50], [101, 101, 9]], out)
+    # EMA update pinned on the same module (models/atst/atst.py:29-34 semantics via ATST.update_teacher)
+    from audiossl.models.atst.atst import ATST
+    with torch.no_grad():
+        ATST.update_teacher(m, 0.99)
+    for name, p in m.teacher.named_parameters():
+        flat("tiny2/ema/" + name, detfill.summarize(p.detach().numpy()), out)
+    # multi-crop 2 global + 2 local (two encoder calls per network), ragged local lengths
+    m = RefATSTLike(128, 2, 2, ncrops=4)
+    run_case(m, "tiny4", 2, [101, 101, 41, 41], [[101, 90], [101, 101], [41, 33], [41, 41]], out)
+    # drop path active in both networks (train-mode teacher, D7): record the torch.rand stream
+    m = RefATSTLike(128, 2, 2, ncrops=2, drop_path_rate=0.5)
+    torch.manual_seed(7)
+    run_case(m, "tiny2dp", 4, [101, 101], [[101, 101, 60, 101], [101, 80, 101, 101]], out, record_rand=True)
+    # the real thing: ATST("small") as the Lightning module builds it, drop path off for parity
+    m = ATST(arch="small", drop_path_rate=0.0)
+
+    class Wrap(nn.Module):
+        def __init__(s, a):
+            super().__init__()
+            s.student, s.teacher, s.loss_fn = a.student, a.teacher, a.loss_fn
+
+        def forward(s, c, l):
+            t = s.teacher(c[:2], l[:2])
+            st = s.student(c, l)
+            return s.loss_fn(st, t), st, t
+    run_case(Wrap(m), "small2", 2, [101, 101], [[101, 64], [101, 101]], out)
+    np.savez_compressed(os.path.join(HERE, "atst.npz"), **out)
+    print("atst.npz", len(out))
+
+
+def gen_sched():
+    from audiossl.utils.common import cosine_scheduler_step, get_params_groups
+    out = {"ema": cosine_scheduler_step(0.99, 1, 1000, 0), "wd": cosine_scheduler_step(0.04, 0.4, 1000, 0),
+           "lr": cosine_scheduler_step(5e-4, 1e-6, 1000, 100)}
+    m = RefATSTLike(128, 2, 2, ncrops=2)
+    reg, noreg = get_params_groups(m.student, debug=True)
+    out["reg"] = np.array(reg)
+    out["noreg"] = np.array(noreg)
+    np.savez_compressed(os.path.join(HERE, "sched.npz"), **out)
+    print("sched.npz")
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    gen_mel()
+    gen_atst()
+    gen_sched()

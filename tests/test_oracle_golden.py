@@ -1,0 +1,108 @@
+"""CPU: the oracle restatement (oracle/atst_oracle.py) against vectors produced by the unmodified
+reference (tests/golden/make_golden.py).  This is what pins the oracle (prompt section 3)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import atst_oracle as O
+from tests.golden import detfill
+from tests import util
+
+
+MEL_CASES = [k for k in util.gold("mel.npz").files if not k.startswith("batch")]
+
+
+@pytest.mark.parametrize("key", MEL_CASES)
+def test_mel_matches_reference(key):
+    g = util.gold("mel.npz")
+    kind, n, win = key.rsplit("_", 2)
+    n, win = int(n), int(win[1:])
+    y = O.mel_feature(detfill.signal(kind, n)[None], win_length=win)
+    ref = g[key]
+    assert y.shape == ref.shape == (1, 64, n // 160 + 1)
+    # normalised log-mel units (1 unit = 65 dB): fp32 FFT-order noise floor, SURVEY section 7 "mel accuracy"
+    np.testing.assert_allclose(y, ref, rtol=0, atol=2e-4)
+    assert np.abs(y - ref).mean() < 2e-6
+
+
+def test_mel_batched_per_clip_topdb():
+    g = util.gold("mel.npz")
+    wavs = np.stack([detfill.signal(k, 16000) for k in ("noise", "sine_silence", "chirp")])[:, None]
+    y = O.mel_feature(wavs)
+    np.testing.assert_allclose(y, g["batch3_16000_w1024"], rtol=0, atol=2e-4)
+
+
+def test_mel_filterbank_sparsity():
+    fb = O.mel_filterbank()
+    assert fb.shape == (513, 64)
+    assert int((fb != 0).sum()) == 970  # SURVEY K2 [verified]
+    nz = np.nonzero(fb.sum(1))[0]
+    assert nz.min() == 4 and nz.max() == 499
+
+
+def build(case):
+    c = util.CASES[case]
+    m = O.OracleATST(ncrops=c["ncrops"], embed_dim=c["dim"], depth=c["depth"], num_heads=c["heads"])
+    util.load_det(m)
+    m.train()
+    return m, c
+
+
+@pytest.mark.parametrize("case", ["tiny2", "tiny4", "small2"])
+def test_atst_forward_backward_matches_reference(case):
+    g = util.gold("atst.npz")
+    m, c = build(case)
+    crops, lengths = util.make_inputs(case, c["B"], c["widths"], c["lens"])
+    t = m.teacher(crops[:2], lengths[:2])
+    s = m.student(crops, lengths)
+    loss, std_s, std_t = O.byol_loss(s, t, c["ncrops"])
+    loss.backward()
+    np.testing.assert_allclose(s.detach().numpy(), g[case + "/student_out"], rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(t.detach().numpy(), g[case + "/teacher_out"], rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(loss.item(), g[case + "/loss"], rtol=1e-5)
+    np.testing.assert_allclose(std_s.item(), g[case + "/std_s"], rtol=1e-4)
+    np.testing.assert_allclose(std_t.item(), g[case + "/std_t"], rtol=1e-4)
+    n = 0
+    for name, p in m.student.named_parameters():
+        key = case + "/grad/" + name
+        if key + "/idx" not in g.files:
+            assert p.grad is None or name == "encoder.mask_embed", name
+            continue
+        util.check_summary(p.grad.numpy(), g, key, rtol=2e-3, atol=2e-4)
+        n += 1
+    assert n > 20
+    for name, b in m.named_buffers():
+        if "running" in name:
+            util.check_summary(b.numpy(), g, case + "/buf/" + name, rtol=1e-4, atol=1e-6)
+
+
+def test_ema_matches_reference():
+    g = util.gold("atst.npz")
+    m, c = build("tiny2")
+    # the golden run did fwd/bwd first (BN buffers change, params do not), then update_teacher(0.99)
+    m.update_teacher(0.99)
+    for name, p in m.teacher.named_parameters():
+        util.check_summary(p.detach().numpy(), g, "tiny2/ema/" + name, rtol=1e-6, atol=1e-7)
+
+
+def test_droppath_stream_matches_reference():
+    g = util.gold("atst.npz")
+    m, c = build("tiny2dp")
+    crops, lengths = util.make_inputs("tiny2dp", c["B"], c["widths"], c["lens"])
+    keep = [1.0 - x for x in torch.linspace(0, c["drop_path"], c["depth"]).tolist()]
+    dp_t, dp_s = util.dp_scales_from_rand(g["tiny2dp/rand"], c["depth"], keep)
+    t = m.teacher(crops[:2], lengths[:2], dp_t)
+    s = m.student(crops, lengths, dp_s)
+    loss, _, _ = O.byol_loss(s, t, 2)
+    np.testing.assert_allclose(s.detach().numpy(), g["tiny2dp/student_out"], rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(loss.item(), g["tiny2dp/loss"], rtol=1e-5)
+
+
+def test_schedules_and_param_groups():
+    g = util.gold("sched.npz")
+    np.testing.assert_allclose(O.cosine_scheduler_step(0.99, 1, 1000, 0), g["ema"], rtol=0, atol=0)
+    np.testing.assert_allclose(O.cosine_scheduler_step(0.04, 0.4, 1000, 0), g["wd"], rtol=0, atol=0)
+    np.testing.assert_allclose(O.cosine_scheduler_step(5e-4, 1e-6, 1000, 100), g["lr"], rtol=0, atol=0)
+    m, _ = build("tiny2")
+    reg, noreg = O.param_groups(m.student)
+    assert reg == list(g["reg"]) and noreg == list(g["noreg"])
