@@ -1,0 +1,349 @@
+// Attention core of modules/transformer.py:107-121 with key-padding by length (K9/K10): softmax(q k^T / 8 +
+// mask) v, never materialising [S,H,N,N].  Flash-style, tf32 tensor cores (mma.sync.m16n8k8), fp32 softmax.
+//
+// One templated kernel covers forward and both halves of the backward pass.  A CTA (4 warps) owns 64
+// "row" items of one (sequence, head) and streams over 64-wide "column" blocks held in padded smem:
+//   MODE 0 forward : rows = queries, cols = keys.   S = Q K^T -> online softmax -> O = P V, LSE (log2 domain)
+//   MODE 1 dQ      : rows = queries, cols = keys.   P = exp2(S c - L_row); dP = dO V^T; dS = P (dP - delta_row)
+//                                                   dQ = scale * dS K
+//   MODE 2 dK, dV  : rows = keys,    cols = queries. P^T = exp2(S^T c - L_col); dV = P^T dO; dP^T = V dO^T;
+//                                                   dS^T = P^T (dP^T - delta_col); dK = scale * dS^T Q
+// Masked keys (index >= length) get probability exactly 0 - identical to the reference's additive -10000,
+// whose exp underflows to 0 in fp32.  q/k/v/dO arrive already rounded to tf32 by the producing GEMM epilogue.
+#include "common.cuh"
+
+namespace atst {
+
+constexpr int kAttnRows = 64;
+constexpr int kAttnCols = 64;
+constexpr int kHd = 64;
+constexpr int kLds = 68;  // padded smem row (floats): conflict-free fragment loads
+
+struct AttnParams {
+  const float* qkv;   // [S*N, 3D]  q | k | v, head h at column h*64
+  const float* o;     // [S*N, D]   forward output (read by delta kernel)
+  const float* d_o;   // [S*N, D]   gradient wrt o
+  float* out_o;       // forward: o
+  float* dqkv;        // [S*N, 3D]
+  float* lse;         // [S, H, N]  log2-domain logsumexp of scaled scores
+  const float* delta; // [S, H, N]
+  const int* lengths; // [S] number of valid keys, or null
+  int N, H, D;
+  float scale;
+};
+
+__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                         uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t tf32_bits(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+  const int sz = valid ? 16 : 0;  // src-size 0 => zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem)), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// stage rows [r0, r0+64) x 64 floats (global row stride ld) into smem [64][kLds]; rows >= nrows are zero
+__device__ __forceinline__ void stage_block(float* dst, const float* src, int ld, int r0, int nrows, int tid) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = tid + i * 128;  // 1024 16-byte chunks
+    const int r = c >> 4, ch = c & 15;
+    const bool ok = (r0 + r) < nrows;
+    const float* g = src + static_cast<size_t>(ok ? (r0 + r) : 0) * ld + ch * 4;
+    cp_async16(dst + r * kLds + ch * 4, g, ok);
+  }
+}
+
+// acc[nt] += A(16 rows of R, 64 wide) . Y^T  for the 8 column tiles of a 64-row block Y
+__device__ __forceinline__ void mma_abt(float (&acc)[8][4], const float* R, const float* Y, int g, int t) {
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    const uint32_t a0 = __float_as_uint(R[g * kLds + 8 * ks + t]);
+    const uint32_t a1 = __float_as_uint(R[(g + 8) * kLds + 8 * ks + t]);
+    const uint32_t a2 = __float_as_uint(R[g * kLds + 8 * ks + t + 4]);
+    const uint32_t a3 = __float_as_uint(R[(g + 8) * kLds + 8 * ks + t + 4]);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const uint32_t b0 = __float_as_uint(Y[(8 * nt + g) * kLds + 8 * ks + t]);
+      const uint32_t b1 = __float_as_uint(Y[(8 * nt + g) * kLds + 8 * ks + t + 4]);
+      mma_tf32(acc[nt], a0, a1, a2, a3, b0, b1);
+    }
+  }
+}
+// acc[dt] += P(16 x 64, C-fragment layout, columns = rows of Y) . Y(64 x 64)
+// C fragment columns (2t, 2t+1) of tile ks are used as k-indices (t, t+4); Y rows are permuted to match.
+__device__ __forceinline__ void mma_py(float (&acc)[8][4], const float (&P)[8][4], const float* Y, int g, int t) {
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    const uint32_t a0 = tf32_bits(P[ks][0]), a1 = tf32_bits(P[ks][2]);
+    const uint32_t a2 = tf32_bits(P[ks][1]), a3 = tf32_bits(P[ks][3]);
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {
+      const uint32_t b0 = __float_as_uint(Y[(8 * ks + 2 * t) * kLds + 8 * dt + g]);
+      const uint32_t b1 = __float_as_uint(Y[(8 * ks + 2 * t + 1) * kLds + 8 * dt + g]);
+      mma_tf32(acc[dt], a0, a1, a2, a3, b0, b1);
+    }
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128) attn_kernel(AttnParams p) {
+  extern __shared__ float sm[];
+  float* sR1 = sm;                          // [64][68] row operand 1
+  float* sR2 = sR1 + kAttnRows * kLds;      // [64][68] row operand 2 (backward only)
+  float* sY1 = sR2 + kAttnRows * kLds;      // [64][68]
+  float* sY2 = sY1 + kAttnCols * kLds;      // [64][68]
+  float* sStat = sY2 + kAttnCols * kLds;    // [2][64] column stats (MODE 2): lse, delta
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int r0 = blockIdx.x * kAttnRows;
+  const int h = blockIdx.y, s = blockIdx.z;
+  const int N = p.N, D = p.D, ld3 = 3 * D;
+  const int len = p.lengths ? p.lengths[s] : N;
+  const size_t tok0 = static_cast<size_t>(s) * N;
+  const float* qp = p.qkv + tok0 * ld3 + h * kHd;
+  const float* kp = qp + D;
+  const float* vp = qp + 2 * D;
+  const float* dop = (MODE != 0) ? p.d_o + tok0 * D + h * kHd : nullptr;
+  const float c = p.scale * 1.4426950408889634f;  // scores -> log2 domain
+
+  const float* r1p = (MODE == 2) ? kp : qp;
+  const float* r2p = (MODE == 1) ? dop : vp;
+  const int r2ld = (MODE == 1) ? D : ld3;
+  const float* y1p = (MODE == 2) ? qp : kp;
+  const float* y2p = (MODE == 2) ? dop : vp;
+  const int y2ld = (MODE == 2) ? D : ld3;
+
+  stage_block(sR1, r1p, ld3, r0, N, tid);
+  if (MODE != 0) stage_block(sR2, r2p, r2ld, r0, N, tid);
+
+  const float* R1w = sR1 + warp * 16 * kLds;
+  const float* R2w = sR2 + warp * 16 * kLds;
+  const int row_a = r0 + warp * 16 + g, row_b = row_a + 8;  // the two rows this thread's C fragments cover
+
+  float acc1[8][4], acc2[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc1[i][j] = acc2[i][j] = 0.f;
+  float m_a = -INFINITY, m_b = -INFINITY, l_a = 0.f, l_b = 0.f;  // forward running max / sum
+  float L_a = 0.f, L_b = 0.f, dl_a = 0.f, dl_b = 0.f;            // MODE 1 row stats
+  if (MODE == 1) {
+    const float* lse = p.lse + (static_cast<size_t>(s) * p.H + h) * N;
+    const float* dlt = p.delta + (static_cast<size_t>(s) * p.H + h) * N;
+    if (row_a < N) { L_a = lse[row_a]; dl_a = dlt[row_a]; }
+    if (row_b < N) { L_b = lse[row_b]; dl_b = dlt[row_b]; }
+  }
+  // keys limit for the column loop: forward / dQ only need keys < len; dK/dV loops over all queries
+  const int ncols = (MODE == 2) ? N : len;
+
+  for (int c0 = 0; c0 < ncols; c0 += kAttnCols) {
+    __syncthreads();  // previous block fully consumed
+    stage_block(sY1, y1p, ld3, c0, N, tid);
+    stage_block(sY2, y2p, y2ld, c0, N, tid);
+    if (MODE == 2 && tid < kAttnCols) {
+      const int q = c0 + tid;
+      const size_t base = (static_cast<size_t>(s) * p.H + h) * N;
+      sStat[tid] = q < N ? p.lse[base + q] : 0.f;
+      sStat[64 + tid] = q < N ? p.delta[base + q] : 0.f;
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    float sc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sc[i][j] = 0.f;
+    mma_abt(sc, R1w, sY1, g, t);
+
+    if (MODE == 0) {
+      // online softmax over this key block; thread holds cols 8nt+2t, +1 of rows g (c0,c1) and g+8 (c2,c3)
+      float mx_a = -INFINITY, mx_b = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int col = c0 + 8 * nt + 2 * t;
+        if (col < len) { mx_a = fmaxf(mx_a, sc[nt][0]); mx_b = fmaxf(mx_b, sc[nt][2]); }
+        if (col + 1 < len) { mx_a = fmaxf(mx_a, sc[nt][1]); mx_b = fmaxf(mx_b, sc[nt][3]); }
+      }
+      mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 1));
+      mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 2));
+      mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 1));
+      mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 2));
+      const float mn_a = fmaxf(m_a, mx_a), mn_b = fmaxf(m_b, mx_b);
+      const float al_a = exp2f((m_a - mn_a) * c), al_b = exp2f((m_b - mn_b) * c);
+      float sum_a = 0.f, sum_b = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int col = c0 + 8 * nt + 2 * t;
+        const float p0 = col < len ? exp2f((sc[nt][0] - mn_a) * c) : 0.f;
+        const float p1 = col + 1 < len ? exp2f((sc[nt][1] - mn_a) * c) : 0.f;
+        const float p2 = col < len ? exp2f((sc[nt][2] - mn_b) * c) : 0.f;
+        const float p3 = col + 1 < len ? exp2f((sc[nt][3] - mn_b) * c) : 0.f;
+        sc[nt][0] = p0; sc[nt][1] = p1; sc[nt][2] = p2; sc[nt][3] = p3;
+        sum_a += p0 + p1;
+        sum_b += p2 + p3;
+      }
+      sum_a += __shfl_xor_sync(0xffffffffu, sum_a, 1);
+      sum_a += __shfl_xor_sync(0xffffffffu, sum_a, 2);
+      sum_b += __shfl_xor_sync(0xffffffffu, sum_b, 1);
+      sum_b += __shfl_xor_sync(0xffffffffu, sum_b, 2);
+      l_a = l_a * al_a + sum_a;
+      l_b = l_b * al_b + sum_b;
+      m_a = mn_a;
+      m_b = mn_b;
+#pragma unroll
+      for (int dt = 0; dt < 8; ++dt) {
+        acc1[dt][0] *= al_a; acc1[dt][1] *= al_a; acc1[dt][2] *= al_b; acc1[dt][3] *= al_b;
+      }
+      mma_py(acc1, sc, sY2, g, t);
+    } else {
+      // probabilities from the saved log-sum-exp
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int col = c0 + 8 * nt + 2 * t;
+        if (MODE == 1) {
+          sc[nt][0] = col < len ? exp2f(sc[nt][0] * c - L_a) : 0.f;
+          sc[nt][1] = col + 1 < len ? exp2f(sc[nt][1] * c - L_a) : 0.f;
+          sc[nt][2] = col < len ? exp2f(sc[nt][2] * c - L_b) : 0.f;
+          sc[nt][3] = col + 1 < len ? exp2f(sc[nt][3] * c - L_b) : 0.f;
+        } else {  // rows are keys, cols are queries
+          const float l0 = sStat[8 * nt + 2 * t], l1 = sStat[8 * nt + 2 * t + 1];
+          const bool q0 = col < N, q1 = col + 1 < N;
+          sc[nt][0] = (row_a < len && q0) ? exp2f(sc[nt][0] * c - l0) : 0.f;
+          sc[nt][1] = (row_a < len && q1) ? exp2f(sc[nt][1] * c - l1) : 0.f;
+          sc[nt][2] = (row_b < len && q0) ? exp2f(sc[nt][2] * c - l0) : 0.f;
+          sc[nt][3] = (row_b < len && q1) ? exp2f(sc[nt][3] * c - l1) : 0.f;
+        }
+      }
+      if (MODE == 2) mma_py(acc2, sc, sY2, g, t);  // dV += P^T dO
+      float dp[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dp[i][j] = 0.f;
+      mma_abt(dp, R2w, sY2, g, t);  // dP = dO V^T   |   dP^T = V dO^T
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        if (MODE == 1) {
+          sc[nt][0] *= dp[nt][0] - dl_a; sc[nt][1] *= dp[nt][1] - dl_a;
+          sc[nt][2] *= dp[nt][2] - dl_b; sc[nt][3] *= dp[nt][3] - dl_b;
+        } else {
+          const float d0 = sStat[64 + 8 * nt + 2 * t], d1 = sStat[64 + 8 * nt + 2 * t + 1];
+          sc[nt][0] *= dp[nt][0] - d0; sc[nt][1] *= dp[nt][1] - d1;
+          sc[nt][2] *= dp[nt][2] - d0; sc[nt][3] *= dp[nt][3] - d1;
+        }
+      }
+      mma_py(acc1, sc, sY1, g, t);  // dQ += dS K   |   dK += dS^T Q
+    }
+  }
+
+  // ---------------------------------------------------------------- write out
+  if (MODE == 0) {
+    const float inv_a = l_a > 0.f ? 1.0f / l_a : 0.f, inv_b = l_b > 0.f ? 1.0f / l_b : 0.f;
+    float* lse = p.lse + (static_cast<size_t>(s) * p.H + h) * N;
+    if (t == 0) {
+      if (row_a < N) lse[row_a] = m_a * c + log2f(l_a);
+      if (row_b < N) lse[row_b] = m_b * c + log2f(l_b);
+    }
+    float* op = p.out_o + tok0 * D + h * kHd;
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {
+      const int col = 8 * dt + 2 * t;
+      if (row_a < N)
+        *reinterpret_cast<float2*>(op + static_cast<size_t>(row_a) * D + col) =
+            make_float2(round_tf32(acc1[dt][0] * inv_a), round_tf32(acc1[dt][1] * inv_a));
+      if (row_b < N)
+        *reinterpret_cast<float2*>(op + static_cast<size_t>(row_b) * D + col) =
+            make_float2(round_tf32(acc1[dt][2] * inv_b), round_tf32(acc1[dt][3] * inv_b));
+    }
+  } else {
+    float* d1 = p.dqkv + tok0 * ld3 + h * kHd + (MODE == 2 ? D : 0);  // dQ or dK
+    float* d2 = p.dqkv + tok0 * ld3 + h * kHd + 2 * D;                // dV
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {
+      const int col = 8 * dt + 2 * t;
+      if (row_a < N) {
+        *reinterpret_cast<float2*>(d1 + static_cast<size_t>(row_a) * ld3 + col) =
+            make_float2(round_tf32(acc1[dt][0] * p.scale), round_tf32(acc1[dt][1] * p.scale));
+        if (MODE == 2)
+          *reinterpret_cast<float2*>(d2 + static_cast<size_t>(row_a) * ld3 + col) =
+              make_float2(round_tf32(acc2[dt][0]), round_tf32(acc2[dt][1]));
+      }
+      if (row_b < N) {
+        *reinterpret_cast<float2*>(d1 + static_cast<size_t>(row_b) * ld3 + col) =
+            make_float2(round_tf32(acc1[dt][2] * p.scale), round_tf32(acc1[dt][3] * p.scale));
+        if (MODE == 2)
+          *reinterpret_cast<float2*>(d2 + static_cast<size_t>(row_b) * ld3 + col) =
+              make_float2(round_tf32(acc2[dt][2]), round_tf32(acc2[dt][3]));
+      }
+    }
+  }
+}
+
+// delta[s,h,n] = sum_d dO[tok, h*64+d] * O[tok, h*64+d]; one warp per (token, head) pair group
+__global__ void attn_delta_kernel(const float* __restrict__ o, const float* __restrict__ d_o, float* __restrict__ delta,
+                                  int S, int N, int H, int D) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // token index
+  const int lane = threadIdx.x & 31;
+  if (gw >= S * N) return;
+  const int s = gw / N, n = gw - s * N;
+  const float* po = o + static_cast<size_t>(gw) * D;
+  const float* pd = d_o + static_cast<size_t>(gw) * D;
+  for (int h = 0; h < H; ++h) {
+    const float2 a = *reinterpret_cast<const float2*>(po + h * kHd + 2 * lane);
+    const float2 b = *reinterpret_cast<const float2*>(pd + h * kHd + 2 * lane);
+    float v = a.x * b.x + a.y * b.y;
+    v = warp_sum(v);
+    if (lane == 0) delta[(static_cast<size_t>(s) * H + h) * N + n] = v;
+  }
+}
+
+constexpr int kAttnSmem = (4 * 64 * kLds + 128) * 4;
+
+template <int MODE>
+static int launch_attn(const AttnParams& p, int S, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    if (e != cudaSuccess) { atst_set_error("attn smem attr: %s", cudaGetErrorString(e)); return ATST_ERR_CUDA; }
+    configured = true;
+  }
+  dim3 grid((p.N + kAttnRows - 1) / kAttnRows, p.H, S);
+  attn_kernel<MODE><<<grid, 128, kAttnSmem, stream>>>(p);
+  return atst_check_launch("attn_kernel");
+}
+
+int attention_forward(const float* qkv, float* o, float* lse, const int* lengths, int S, int N, int H,
+                      cudaStream_t stream) {
+  ATST_REQUIRE(S > 0 && N > 0 && H > 0, "attention_forward: bad shape S=%d N=%d H=%d", S, N, H);
+  AttnParams p{};
+  p.qkv = qkv; p.out_o = o; p.lse = lse; p.lengths = lengths;
+  p.N = N; p.H = H; p.D = H * kHd; p.scale = 0.125f;
+  return launch_attn<0>(p, S, stream);
+}
+
+int attention_backward(const float* qkv, const float* o, const float* d_o, const float* lse, float* delta_ws,
+                       float* dqkv, const int* lengths, int S, int N, int H, cudaStream_t stream) {
+  ATST_REQUIRE(S > 0 && N > 0 && H > 0, "attention_backward: bad shape S=%d N=%d H=%d", S, N, H);
+  const int D = H * kHd;
+  const long long threads = static_cast<long long>(S) * N * 32;
+  attn_delta_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(o, d_o, delta_ws, S, N, H, D);
+  int rc = atst_check_launch("attn_delta_kernel");
+  if (rc) return rc;
+  AttnParams p{};
+  p.qkv = qkv; p.o = o; p.d_o = d_o; p.dqkv = dqkv; p.lse = const_cast<float*>(lse); p.delta = delta_ws;
+  p.lengths = lengths; p.N = N; p.H = H; p.D = D; p.scale = 0.125f;
+  rc = launch_attn<1>(p, S, stream);
+  if (rc) return rc;
+  return launch_attn<2>(p, S, stream);
+}
+
+}  // namespace atst

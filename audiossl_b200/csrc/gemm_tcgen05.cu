@@ -1,0 +1,427 @@
+// TF32 tcgen05 GEMM for the AST transformer.
+//
+//   NT  ("K-major"):   C[M,N] = epi( A[M,K] . B[N,K]^T )          forward (B = weight [out,in]) and
+//                                                                 dgrad   (B = transposed weight copy)
+//   TN  ("MN-major"):  C[M,N] += A[T,M]^T . B[T,N]  (split over T) wgrad: both operands are token-major
+//                                                                 activations, contraction over tokens
+//
+// Structure (one CTA per SM, persistent over output tiles):
+//   warp 0      TMA producer: cp.async.bulk.tensor -> 128B-swizzled smem ring (kStages x (A 16 KB + B 16/32 KB))
+//   warp 1      MMA issuer: one lane issues tcgen05.mma.kind::tf32 (M=128, N=BLOCK_N, K=8) into TMEM,
+//               tcgen05.commit releases smem slots / publishes the accumulator
+//   warp 2      TMEM allocator (2 accumulator stages x BLOCK_N columns)
+//   warps 4-7   epilogue: tcgen05.ld 32x32b -> registers -> per-warp smem transpose -> fused epilogue
+//               (bias / exact-erf GELU / GELU' / droppath-scaled residual / split-K atomics) ->
+//               coalesced float4 global stores.  The accumulator is double buffered so the epilogue of
+//               tile i overlaps the main loop of tile i+1.
+// fp32 containers everywhere; the tensor core reads the top 19 bits (TF32).  Producers round-to-nearest
+// (cvt.rna.tf32) the activations/weights they hand to a GEMM so operand error is unbiased.
+#include "common.cuh"
+#include "gemm.h"
+
+namespace atst {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockKBytes = 128;  // one 128B swizzle row
+constexpr int kBlockK = 32;        // tf32 elements per k-block
+constexpr int kUmmaK = 8;          // tf32 elements per tcgen05.mma
+constexpr int kThreads = 256;
+constexpr int kStagePad = 36;      // floats per staged row (16B aligned, conflict-free)
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int kABytes = kBlockM * kBlockKBytes;
+  static constexpr int kBBytes = BLOCK_N * kBlockKBytes;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int kEpiBytes = 4 * 32 * kStagePad * 4;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kEpiBytes + 256;
+  static constexpr int kTmemCols = 2 * BLOCK_N;  // 512 or 256: power of two
+};
+
+__device__ __forceinline__ float gelu_exact(float u) { return 0.5f * u * (1.0f + erff(u * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad(float u) {
+  const float cdf = 0.5f * (1.0f + erff(u * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * u * u);
+  return cdf + u * pdf;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024B alignment for the 128B swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
+  float* smem_epi = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kEpiBytes);
+  uint64_t* full_bar = bars;                     // [kStages]
+  uint64_t* empty_bar = bars + Cfg::kStages;     // [kStages]
+  uint64_t* tfull_bar = bars + 2 * Cfg::kStages; // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = (p.M + kBlockM - 1) / kBlockM;
+  const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int kb_total = (p.K + kBlockK - 1) / kBlockK;
+  const int splits = p.splits > 0 ? p.splits : 1;
+  const int kb_per_split = (kb_total + splits - 1) / splits;
+  const int total_tiles = m_tiles * n_tiles * splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int split = tile / (m_tiles * n_tiles);
+        const int rem = tile - split * (m_tiles * n_tiles);
+        const int m0 = (rem / n_tiles) * kBlockM;
+        const int n0 = (rem % n_tiles) * BLOCK_N;
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb0 + kb_per_split, kb_total);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          void* sa = smem_a + stage * Cfg::kABytes;
+          void* sb = smem_b + stage * Cfg::kBBytes;
+          // MN-major operands are [k rows, features]: box {32 features, 32 k rows, BLOCK/32 feature chunks}
+          if (A_MN) tma_load_3d(sa, &tmA, &full_bar[stage], 0, kb * kBlockK, m0 / 32);
+          else      tma_load_2d(sa, &tmA, &full_bar[stage], kb * kBlockK, m0);
+          if (B_MN) tma_load_3d(sb, &tmB, &full_bar[stage], 0, kb * kBlockK, n0 / 32);
+          else      tma_load_2d(sb, &tmB, &full_bar[stage], kb * kBlockK, n0);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = make_idesc(2u, kBlockM, BLOCK_N, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int split = tile / (m_tiles * n_tiles);
+      const int kb0 = split * kb_per_split;
+      const int kb1 = min(kb0 + kb_per_split, kb_total);
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::kABytes);
+          const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kBBytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // K-major : [rows][128 B], 8-row swizzle atoms 1024 B apart; one MMA consumes 32 B of each row
+            // MN-major: [feature chunk][32 k rows][128 B]; one MMA consumes 8 k rows = p.mn_kstep bytes
+            const uint64_t da = A_MN ? make_smem_desc(a_addr + k * p.mn_kstep, p.mn_lbo, p.mn_sbo, p.mn_layout)
+                                     : make_smem_desc(a_addr + k * 32, 16, 1024, 2);
+            const uint64_t db = B_MN ? make_smem_desc(b_addr + k * p.mn_kstep, p.mn_lbo, p.mn_sbo, p.mn_layout)
+                                     : make_smem_desc(b_addr + k * 32, 16, 1024, 2);
+            umma_tf32(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (kb1 <= kb0 && lane == 0) umma_commit(&tfull_bar[acc]);  // empty split: nothing accumulated
+      __syncwarp();
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue
+    const int ew = warp - 4;  // == warp % 4: TMEM lane quadrant
+    float* stg = smem_epi + ew * 32 * kStagePad;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int split = tile / (m_tiles * n_tiles);
+      const int rem = tile - split * (m_tiles * n_tiles);
+      const int m0 = (rem / n_tiles) * kBlockM;
+      const int n0 = (rem % n_tiles) * BLOCK_N;
+      const int kb0 = split * kb_per_split;
+      const bool empty_split = min(kb0 + kb_per_split, kb_total) <= kb0;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(ew * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c * 32, r);
+        tmem_ld_wait();
+        if (c == BLOCK_N / 32 - 1) {
+          // accumulator fully read: hand the TMEM stage back to the MMA warp before the global stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+        if (n0 + c * 32 >= p.N || empty_split) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                 __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+          *reinterpret_cast<float4*>(&stg[lane * kStagePad + 4 * j]) = v;
+        }
+        __syncwarp();
+        const int gn = n0 + c * 32 + (lane & 7) * 4;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias != nullptr && gn < p.N) bias4 = *reinterpret_cast<const float4*>(p.bias + gn);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = 4 * i + (lane >> 3);
+          const int gm = m0 + ew * 32 + row;
+          if (gm >= p.M || gn >= p.N) continue;
+          float4 v = *reinterpret_cast<const float4*>(&stg[row * kStagePad + (lane & 7) * 4]);
+          v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+          float* cptr = p.C + static_cast<size_t>(gm) * p.ldc + gn;
+          switch (p.epi) {
+            case EPI_STORE:
+              break;
+            case EPI_GELU: {  // aux <- pre-activation, C <- gelu
+              *reinterpret_cast<float4*>(p.aux + static_cast<size_t>(gm) * p.ldaux + gn) = v;
+              v.x = gelu_exact(v.x); v.y = gelu_exact(v.y); v.z = gelu_exact(v.z); v.w = gelu_exact(v.w);
+              break;
+            }
+            case EPI_DGELU: {  // C <- acc * gelu'(aux)
+              const float4 u = *reinterpret_cast<const float4*>(p.aux + static_cast<size_t>(gm) * p.ldaux + gn);
+              v.x *= gelu_grad(u.x); v.y *= gelu_grad(u.y); v.z *= gelu_grad(u.z); v.w *= gelu_grad(u.w);
+              break;
+            }
+            case EPI_RESID: {  // C <- resid + rowscale[seq] * acc
+              const float s = p.rowscale ? p.rowscale[gm / p.rows_per_seq] : 1.0f;
+              const float4 x = *reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(gm) * p.ldr + gn);
+              v.x = fmaf(s, v.x, x.x); v.y = fmaf(s, v.y, x.y); v.z = fmaf(s, v.z, x.z); v.w = fmaf(s, v.w, x.w);
+              break;
+            }
+            case EPI_SCALE: {  // C <- rowscale[seq] * acc   (dgrad through droppath)
+              const float s = p.rowscale ? p.rowscale[gm / p.rows_per_seq] : 1.0f;
+              v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+              break;
+            }
+            case EPI_RELU:
+              v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+              break;
+            default:
+              break;
+          }
+          if (p.round_out) {
+            v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+          }
+          if (p.epi == EPI_ATOMIC) {
+            atomicAdd(cptr + 0, v.x); atomicAdd(cptr + 1, v.y); atomicAdd(cptr + 2, v.z); atomicAdd(cptr + 3, v.w);
+          } else {
+            *reinterpret_cast<float4*>(cptr) = v;
+          }
+        }
+        __syncwarp();
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  __syncwarp();  // reconverge single-lane roles before the CTA-wide barrier
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// --------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || ptr == nullptr) {
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  return fn;
+}
+
+// row-major [rows, cols] fp32 with leading dimension ld (elements); box = {32 cols, box_rows}
+static int make_map_kmajor(CUtensorMap* map, const float* ptr, int rows, int cols, int ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { atst_set_error("cuTensorMapEncodeTiled entry point not available"); return ATST_ERR_CUDA; }
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
+  cuuint32_t box[2] = {32, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { atst_set_error("cuTensorMapEncodeTiled(K-major) failed: %d", (int)r); return ATST_ERR_CUDA; }
+  return ATST_OK;
+}
+
+// token-major [tokens, feats] fp32 (ld elements) viewed as {32 feats, tokens, feats/32}; box {32, 32, box_feats/32}
+static int make_map_mnmajor(CUtensorMap* map, const float* ptr, int tokens, int feats, int ld, int box_feats,
+                            int swizzle_mode) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { atst_set_error("cuTensorMapEncodeTiled entry point not available"); return ATST_ERR_CUDA; }
+  cuuint64_t dims[3] = {32, static_cast<cuuint64_t>(tokens), static_cast<cuuint64_t>((feats + 31) / 32)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 4, 128};
+  cuuint32_t box[3] = {32, 32, static_cast<cuuint32_t>(box_feats / 32)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, static_cast<CUtensorMapSwizzle>(swizzle_mode),
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { atst_set_error("cuTensorMapEncodeTiled(MN-major) failed: %d", (int)r); return ATST_ERR_CUDA; }
+  return ATST_OK;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  static bool configured = false;
+  auto kfn = gemm_tf32_kernel<BLOCK_N, A_MN, B_MN>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) { atst_set_error("cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e)); return ATST_ERR_CUDA; }
+    configured = true;
+  }
+  const int m_tiles = (p.M + kBlockM - 1) / kBlockM;
+  const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int tiles = m_tiles * n_tiles * (p.splits > 0 ? p.splits : 1);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kfn<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  return atst_check_launch("gemm_tf32_kernel");
+}
+
+int gemm_nt(const float* A, int lda, const float* B, int ldb, GemmParams p, cudaStream_t stream) {
+  ATST_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm_nt: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
+  ATST_REQUIRE(p.N % 4 == 0 && p.ldc % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && p.K % 4 == 0,
+               "gemm_nt: N, K and leading dimensions must be multiples of 4 (N=%d K=%d lda=%d ldb=%d ldc=%d)", p.N, p.K,
+               lda, ldb, p.ldc);
+  ATST_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(p.C) & 15) == 0, "gemm_nt: pointers must be 16-byte aligned");
+  const bool wide = (p.N % 256 == 0) || p.N > 1024;
+  CUtensorMap ta, tb;
+  int rc = make_map_kmajor(&ta, A, p.M, p.K, lda, kBlockM);
+  if (rc) return rc;
+  rc = make_map_kmajor(&tb, B, p.N, p.K, ldb, wide ? 256 : 128);
+  if (rc) return rc;
+  p.splits = 1;
+  return wide ? launch<256, false, false>(ta, tb, p, stream) : launch<128, false, false>(ta, tb, p, stream);
+}
+
+static void mn_defaults(GemmParams& p) {
+  if (p.mn_layout == 0 && p.mn_lbo == 0) {  // defaults: 128B swizzle with 32B atoms (the tf32 MN-major layout)
+    p.mn_layout = 1;
+    p.mn_lbo = 32 * 128;  // bytes between 32-feature chunks: 32 k rows x 128 B
+    p.mn_sbo = 4 * 128;   // bytes between 4-row k groups of the 32B-atom swizzle
+    p.mn_kstep = 8 * 128; // 8 k rows per MMA
+    p.mn_tma_swizzle = (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  }
+}
+
+int gemm_nn(const float* A, int lda, const float* B, int ldb, GemmParams p, cudaStream_t stream) {
+  // C[M,N] = epi(A[M,K] . B[K,N]); B row-major [K, N] (a Linear weight [out=K, in=N] used for dgrad)
+  ATST_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm_nn: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
+  ATST_REQUIRE(p.N % 32 == 0 && p.ldc % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && p.K % 4 == 0,
+               "gemm_nn: N must be a multiple of 32, K and leading dims multiples of 4 (N=%d K=%d)", p.N, p.K);
+  mn_defaults(p);
+  const bool wide = (p.N % 256 == 0) || p.N > 1024;
+  CUtensorMap ta, tb;
+  int rc = make_map_kmajor(&ta, A, p.M, p.K, lda, kBlockM);
+  if (rc) return rc;
+  rc = make_map_mnmajor(&tb, B, p.K, p.N, ldb, wide ? 256 : 128, p.mn_tma_swizzle);
+  if (rc) return rc;
+  p.splits = 1;
+  return wide ? launch<256, false, true>(ta, tb, p, stream) : launch<128, false, true>(ta, tb, p, stream);
+}
+
+int gemm_tn(const float* A, int lda, const float* B, int ldb, int T, GemmParams p, cudaStream_t stream) {
+  // C[M,N] (+)= A[T,M]^T B[T,N]; M, N are feature counts, T tokens.
+  ATST_REQUIRE(p.M > 0 && p.N > 0 && T > 0, "gemm_tn: empty problem");
+  ATST_REQUIRE(p.M % 32 == 0 && p.N % 32 == 0 && lda % 4 == 0 && ldb % 4 == 0 && p.ldc % 4 == 0,
+               "gemm_tn: feature dims must be multiples of 32 (M=%d N=%d)", p.M, p.N);
+  p.K = T;
+  const bool wide = (p.N % 256 == 0) || p.N > 1024;
+  const int bn = wide ? 256 : 128;
+  mn_defaults(p);
+  const int m_tiles = (p.M + kBlockM - 1) / kBlockM, n_tiles = (p.N + bn - 1) / bn;
+  const int kb_total = (T + kBlockK - 1) / kBlockK;
+  if (p.splits <= 0) {
+    // pick the split count whose work-unit count fills whole waves of SMs best (>= 8 k-blocks per unit)
+    const int t = m_tiles * n_tiles, sms = num_sms();
+    int best = 1;
+    double best_eff = 0.0;
+    for (int s = 1; s <= 64 && s * 8 <= kb_total; ++s) {
+      const int units = t * s;
+      const int waves = (units + sms - 1) / sms;
+      const double eff = static_cast<double>(units) / (static_cast<double>(waves) * sms);
+      if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+    }
+    p.splits = best;
+  }
+  // no empty splits: shrink until every split owns at least one k-block
+  while (p.splits > 1 && (p.splits - 1) * ((kb_total + p.splits - 1) / p.splits) >= kb_total) --p.splits;
+  p.epi = EPI_ATOMIC;
+  CUtensorMap ta, tb;
+  int rc = make_map_mnmajor(&ta, A, T, p.M, lda, kBlockM, p.mn_tma_swizzle);
+  if (rc) return rc;
+  rc = make_map_mnmajor(&tb, B, T, p.N, ldb, bn, p.mn_tma_swizzle);
+  if (rc) return rc;
+  return wide ? launch<256, true, true>(ta, tb, p, stream) : launch<128, true, true>(ta, tb, p, stream);
+}
+
+}  // namespace atst

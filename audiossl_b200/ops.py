@@ -1,0 +1,232 @@
+"""Torch-tensor front for the C ABI: shape checks, output allocation, current stream.
+
+PyTorch is used for device memory and streams only; every function below launches hand-written
+sm_100a kernels from libatst_b200.so.
+"""
+import torch
+
+from . import _lib
+from ._lib import check, ptr
+
+EPI_STORE, EPI_GELU, EPI_DGELU, EPI_RESID, EPI_SCALE, EPI_RELU = 0, 1, 2, 3, 4, 5
+
+
+def _f32c(t, name):
+    if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+        raise ValueError("%s must be a contiguous fp32 CUDA tensor" % name)
+    return t
+
+
+def mel_forward(wav, win_length=1024, normalize=True, out=None):
+    """wav [..., n] fp32 cuda -> normalised log-mel [..., 64, n//160+1] (reference mel_feature)."""
+    lead = wav.shape[:-1]
+    n = wav.shape[-1]
+    w2 = _f32c(wav.reshape(-1, n), "wav")
+    B = w2.shape[0]
+    T = n // 160 + 1
+    if out is None:
+        out = torch.empty((B, 64, T), device=wav.device, dtype=torch.float32)
+    ws = torch.empty((B,), device=wav.device, dtype=torch.int32)
+    check(_lib.lib().atst_mel_forward(ptr(w2), B, n, w2.stride(0), win_length, ptr(out), 64 * T, ptr(ws),
+                                      1 if normalize else 0, _lib.stream()), "atst_mel_forward")
+    return out.reshape(*lead, 64, T)
+
+
+def gemm_nt(A, B, bias=None, epi=EPI_STORE, resid=None, aux=None, rowscale=None, rows_per_seq=1, round_out=False,
+            out=None):
+    """out[M,N] = epi(A[M,K] @ B[N,K]^T + bias)."""
+    M, K = A.shape
+    N = B.shape[0]
+    assert B.shape[1] == K
+    if out is None:
+        out = torch.empty((M, N), device=A.device, dtype=torch.float32)
+    check(_lib.lib().atst_gemm_nt(ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(out), out.stride(0), M, N, K,
+                                  ptr(bias), epi, ptr(resid), resid.stride(0) if resid is not None else 0,
+                                  ptr(aux), aux.stride(0) if aux is not None else 0, ptr(rowscale), rows_per_seq,
+                                  1 if round_out else 0, _lib.stream()), "atst_gemm_nt")
+    return out
+
+
+def gemm_nn(A, W, epi=EPI_STORE, aux=None, rowscale=None, rows_per_seq=1, round_out=False, out=None):
+    """out[M,N] = epi(A[M,K] @ W[K,N])  (dgrad against a Linear weight W[out=K, in=N])."""
+    M, K = A.shape
+    N = W.shape[1]
+    assert W.shape[0] == K
+    if out is None:
+        out = torch.empty((M, N), device=A.device, dtype=torch.float32)
+    check(_lib.lib().atst_gemm_nn(ptr(A), A.stride(0), ptr(W), W.stride(0), ptr(out), out.stride(0), M, N, K, epi,
+                                  ptr(aux), aux.stride(0) if aux is not None else 0, ptr(rowscale), rows_per_seq,
+                                  1 if round_out else 0, _lib.stream()), "atst_gemm_nn")
+    return out
+
+
+def gemm_tn_acc(A, B, out):
+    """out[M,N] += A[T,M]^T @ B[T,N]  (wgrad; accumulates)."""
+    T, M = A.shape
+    N = B.shape[1]
+    assert B.shape[0] == T and tuple(out.shape) == (M, N)
+    check(_lib.lib().atst_gemm_tn(ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(out), out.stride(0), M, N, T,
+                                  _lib.stream()), "atst_gemm_tn")
+    return out
+
+
+def layernorm_fwd(x, gamma, beta, rows, D, x_stride=None, out=None, out_stride=None, eps=1e-6, round_out=True):
+    x_stride = D if x_stride is None else x_stride
+    if out is None:
+        out = torch.empty((rows, D), device=x.device, dtype=torch.float32)
+    out_stride = D if out_stride is None else out_stride
+    mean = torch.empty((rows,), device=x.device, dtype=torch.float32)
+    rstd = torch.empty((rows,), device=x.device, dtype=torch.float32)
+    check(_lib.lib().atst_layernorm_forward(ptr(x), x_stride, ptr(gamma), ptr(beta), ptr(out), out_stride, ptr(mean),
+                                            ptr(rstd), rows, D, eps, 1 if round_out else 0, _lib.stream()),
+          "atst_layernorm_forward")
+    return out, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, rows, D, dres=None, dx=None, dy_stride=None,
+                  x_stride=None, dres_stride=None, dx_stride=None):
+    dy_stride = D if dy_stride is None else dy_stride
+    x_stride = D if x_stride is None else x_stride
+    dres_stride = D if dres_stride is None else dres_stride
+    if dx is None:
+        dx = torch.empty((rows, D), device=x.device, dtype=torch.float32)
+    dx_stride = D if dx_stride is None else dx_stride
+    check(_lib.lib().atst_layernorm_backward(ptr(dy), dy_stride, ptr(x), x_stride, ptr(mean), ptr(rstd), ptr(gamma),
+                                             ptr(dres), dres_stride, ptr(dx), dx_stride, ptr(dgamma), ptr(dbeta),
+                                             rows, D, _lib.stream()), "atst_layernorm_backward")
+    return dx
+
+
+def attention_fwd(qkv, S, N, H, lengths=None, out=None, lse=None):
+    D = H * 64
+    if out is None:
+        out = torch.empty((S * N, D), device=qkv.device, dtype=torch.float32)
+    if lse is None:
+        lse = torch.empty((S, H, N), device=qkv.device, dtype=torch.float32)
+    check(_lib.lib().atst_attention_forward(ptr(qkv), ptr(out), ptr(lse), ptr(lengths), S, N, H, _lib.stream()),
+          "atst_attention_forward")
+    return out, lse
+
+
+def attention_bwd(qkv, o, d_o, lse, S, N, H, lengths=None, dqkv=None, delta_ws=None):
+    if dqkv is None:
+        dqkv = torch.empty_like(qkv)
+    if delta_ws is None:
+        delta_ws = torch.empty((S, H, N), device=qkv.device, dtype=torch.float32)
+    check(_lib.lib().atst_attention_backward(ptr(qkv), ptr(o), ptr(d_o), ptr(lse), ptr(delta_ws), ptr(dqkv),
+                                             ptr(lengths), S, N, H, _lib.stream()), "atst_attention_backward")
+    return dqkv
+
+
+def patchify(mel, out=None):
+    """mel [S,1,64,T] -> [S*(T//4), 256] (PatchEmbed_v2 rearrange, tf32-rounded)."""
+    S, _, H, T = mel.shape
+    assert H == 64 and mel.is_contiguous()
+    P = T // 4
+    if out is None:
+        out = torch.empty((S * P, 256), device=mel.device, dtype=torch.float32)
+    check(_lib.lib().atst_patchify(ptr(mel), 64 * T, S, T, ptr(out), _lib.stream()), "atst_patchify")
+    return out
+
+
+def tokens_fwd(pe, cls, pos, S, P, D, use_cls=True, mask_embed=None, mask=None, out=None):
+    N = P + (1 if use_cls else 0)
+    if out is None:
+        out = torch.empty((S * N, D), device=pe.device, dtype=torch.float32)
+    check(_lib.lib().atst_tokens_forward(ptr(pe), ptr(cls), ptr(pos), ptr(mask_embed), ptr(mask), ptr(out), S, P, D,
+                                         1 if use_cls else 0, _lib.stream()), "atst_tokens_forward")
+    return out
+
+
+def tokens_bwd(dx, dpe, dpos, dcls, S, P, D, use_cls=True, mask=None, dmask_embed=None):
+    check(_lib.lib().atst_tokens_backward(ptr(dx), ptr(mask), ptr(dpe), ptr(dpos), ptr(dcls), ptr(dmask_embed), S, P,
+                                          D, 1 if use_cls else 0, _lib.stream()), "atst_tokens_backward")
+
+
+def colsum_acc(X, out, rows=None, cols=None, ld=None):
+    rows = X.shape[0] if rows is None else rows
+    cols = X.shape[1] if cols is None else cols
+    ld = X.stride(0) if ld is None else ld
+    check(_lib.lib().atst_colsum_accumulate(ptr(X), ld, rows, cols, ptr(out), _lib.stream()), "atst_colsum")
+
+
+def bn_stats(X):
+    rows, cols = X.shape
+    mean = torch.empty((cols,), device=X.device, dtype=torch.float32)
+    m2 = torch.empty((cols,), device=X.device, dtype=torch.float32)
+    check(_lib.lib().atst_bn_stats(ptr(X), rows, cols, ptr(mean), ptr(m2), _lib.stream()), "atst_bn_stats")
+    return mean, m2
+
+
+def bn_finalize(mean, m2, count, running_mean=None, running_var=None, eps=1e-5, momentum=0.1):
+    rstd = torch.empty_like(mean)
+    check(_lib.lib().atst_bn_finalize(ptr(mean), ptr(m2), float(count), eps, momentum, ptr(rstd), ptr(running_mean),
+                                      ptr(running_var), mean.numel(), _lib.stream()), "atst_bn_finalize")
+    return rstd
+
+
+def bn_relu_fwd(X, mean, rstd, gamma, beta, out=None):
+    rows, cols = X.shape
+    if out is None:
+        out = torch.empty_like(X)
+    check(_lib.lib().atst_bn_relu_forward(ptr(X), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ptr(out), rows, cols,
+                                          _lib.stream()), "atst_bn_relu_forward")
+    return out
+
+
+def bn_relu_bwd_stats(dY, X, mean, rstd, gamma, beta):
+    rows, cols = X.shape
+    s1 = torch.empty((cols,), device=X.device, dtype=torch.float32)
+    s2 = torch.empty((cols,), device=X.device, dtype=torch.float32)
+    check(_lib.lib().atst_bn_relu_backward_stats(ptr(dY), ptr(X), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), rows,
+                                                 cols, ptr(s1), ptr(s2), _lib.stream()), "atst_bn_relu_backward_stats")
+    return s1, s2
+
+
+def bn_relu_bwd_apply(dY, X, mean, rstd, gamma, beta, s1, s2, count, out=None):
+    rows, cols = X.shape
+    if out is None:
+        out = torch.empty_like(X)
+    check(_lib.lib().atst_bn_relu_backward_apply(ptr(dY), ptr(X), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta),
+                                                 ptr(s1), ptr(s2), float(count), ptr(out), rows, cols,
+                                                 _lib.stream()), "atst_bn_relu_backward_apply")
+    return out
+
+
+def byol_loss(student, teacher, ncrops, B, dstudent=None, acc=None):
+    if dstudent is None:
+        dstudent = torch.empty_like(student)
+    if acc is None:
+        acc = torch.empty((1 + 4 * 256,), device=student.device, dtype=torch.float32)
+    check(_lib.lib().atst_byol_loss(ptr(student), ptr(teacher), ncrops, B, ptr(dstudent), ptr(acc), _lib.stream()),
+          "atst_byol_loss")
+    return dstudent, acc
+
+
+def byol_finalize(acc, n_student_rows, n_teacher_rows, ncrops, B, out=None):
+    if out is None:
+        out = torch.empty((3,), device=acc.device, dtype=torch.float32)
+    check(_lib.lib().atst_byol_finalize(ptr(acc), float(n_student_rows), float(n_teacher_rows), ncrops, B, ptr(out),
+                                        _lib.stream()), "atst_byol_finalize")
+    return out
+
+
+def ema_update(k, q, m):
+    assert k.numel() == q.numel()
+    check(_lib.lib().atst_ema_update(ptr(k), ptr(q), float(m), k.numel(), _lib.stream()), "atst_ema_update")
+
+
+def adamw_step(p, g, m, v, step, lr, wd, beta1=0.9, beta2=0.999, eps=1e-6, grad_scale=1.0):
+    check(_lib.lib().atst_adamw_step(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), int(step), float(lr), float(wd),
+                                     beta1, beta2, eps, float(grad_scale), _lib.stream()), "atst_adamw_step")
+
+
+def round_tf32(src, dst=None):
+    if dst is None:
+        dst = torch.empty_like(src)
+    check(_lib.lib().atst_round_tf32(ptr(src), ptr(dst), src.numel(), _lib.stream()), "atst_round_tf32")
+    return dst
+
+
+def axpy(y, x, a):
+    check(_lib.lib().atst_axpy(ptr(y), ptr(x), float(a), y.numel(), _lib.stream()), "atst_axpy")
