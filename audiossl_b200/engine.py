@@ -1,0 +1,242 @@
+"""Explicit forward / backward drivers for the AST encoder and the projector / predictor heads.
+
+No torch autograd inside: every step is a launch of a hand-written sm_100a kernel through the C ABI
+(audiossl_b200.ops).  Activations needed by the backward pass are kept in a shape-keyed workspace that is
+reused from step to step, so a training step performs no device allocation after the first one.
+
+Reference semantics (file:line under /root/reference):
+  encoder forward  audiossl/models/atst/audio_transformer.py:153-210 (prepare_tokens, block loop, norm, CLS)
+  block            audiossl/modules/transformer.py:136-150 (pre-LN, DropPath on both branches)
+  frame encoder    audiossl/methods/atstframe/audio_transformer.py:161-207
+  heads            audiossl/models/atst/byol.py:6-22 (Linear -> BatchNorm1d -> ReLU -> Linear, no biases)
+"""
+import torch
+
+from . import ops
+
+
+class Workspace:
+    """shape-keyed cache of device tensors (activations, gradients, scratch)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs = {}
+
+    def get(self, tag, shape, dtype=torch.float32):
+        key = (tag, tuple(shape), dtype)
+        t = self.bufs.get(key)
+        if t is None:
+            t = torch.empty(shape, device=self.device, dtype=dtype)
+            self.bufs[key] = t
+        return t
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in self.bufs.values())
+
+
+def droppath_scales(depth, drop_path_rate, S, device, generator=None):
+    """per-block (attn, mlp) DropPath scales floor(keep + U[0,1)) / keep for S sequences
+    (modules/transformer.py:48-57; rates linspace(0, rate, depth), audio_transformer.py:107).
+    Blocks with rate 0 get None (nn.Identity in the reference: no random draw)."""
+    out = []
+    rates = torch.linspace(0, drop_path_rate, depth).tolist()
+    for r in rates:
+        if r == 0.0:
+            out.append(None)
+            continue
+        keep = 1.0 - r
+        u = torch.rand((2, S), device=device, generator=generator)
+        s = torch.floor(keep + u) / keep
+        out.append((s[0].contiguous(), s[1].contiguous()))
+    return out
+
+
+class EncoderEngine:
+    def __init__(self, embed_dim, depth, num_heads, use_cls=True, norm_name="norm", prefix="encoder.",
+                 patch_w=4, max_frames=1001):
+        assert embed_dim == num_heads * 64, "head_dim must be 64 (all reference configs)"
+        self.D, self.depth, self.H = embed_dim, depth, num_heads
+        self.use_cls, self.norm_name, self.px = use_cls, norm_name, prefix
+        self.patch_w, self.max_frames = patch_w, max_frames
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, fp, ws, mel, lengths, dp=None, save=True, tag="s", mask=None, mask_input=True):
+        """mel [S,1,64,T] fp32 cuda contiguous; lengths [S] (valid frames) or None.
+        Returns (out [S,D] tf32-rounded final-norm CLS rows, ctx) for the clip model, or
+        (x_norm [S*N, D], ctx) for the frame model (row selection is done by the caller)."""
+        px, D, H = self.px, self.D, self.H
+        S, _, Hm, T = mel.shape
+        if T > self.max_frames:
+            raise ValueError("clip of %d frames exceeds the positional-embedding capacity %d "
+                             "(reference: 10 s max, chunk longer audio)" % (T, self.max_frames))
+        P = T // self.patch_w
+        N = P + (1 if self.use_cls else 0)
+        M = S * N
+        key_len = None
+        if lengths is not None:
+            plen = (lengths - lengths % self.patch_w) // self.patch_w
+            key_len = (plen + (1 if self.use_cls else 0)).to(torch.int32).contiguous()
+        t = (lambda name, shape: ws.get(tag + "/" + name, shape))
+        patches = ops.patchify(mel, out=t("patches", (S * P, 256)))
+        pe = ops.gemm_nt(patches, fp.c(px + "patch_embed.patch_embed.weight"),
+                         bias=fp.p(px + "patch_embed.patch_embed.bias"), out=t("pe", (S * P, D)))
+        m8 = None
+        if mask is not None:
+            m8 = mask.to(torch.uint8).contiguous()
+        x = ops.tokens_fwd(pe, fp.p(px + "cls_token") if self.use_cls else None, fp.p(px + "pos_embed"), S, P, D,
+                           use_cls=self.use_cls, mask_embed=fp.p(px + "mask_embed") if (m8 is not None and mask_input) else None,
+                           mask=m8 if mask_input else None, out=t("x0", (M, D)))
+        ctx = {"S": S, "P": P, "N": N, "M": M, "key_len": key_len, "dp": dp, "tag": tag, "layers": [],
+               "patches": patches, "mask": m8 if mask_input else None}
+        for i in range(self.depth):
+            b = "%sblocks.%d." % (px, i)
+            lt = (lambda name, shape, i=i: ws.get("%s/L%d/%s" % (tag, i if save else 0, name), shape))
+            h, mean1, rstd1 = self._ln(x, fp.p(b + "norm1.weight"), fp.p(b + "norm1.bias"), M, lt("h", (M, D)),
+                                       lt("mean1", (M,)), lt("rstd1", (M,)))
+            qkv = ops.gemm_nt(h, fp.c(b + "attn.qkv.weight"), round_out=True, out=lt("qkv", (M, 3 * D)))
+            o, lse = ops.attention_fwd(qkv, S, N, H, key_len, out=lt("o", (M, D)), lse=lt("lse", (S, H, N)))
+            s_attn = s_mlp = None
+            if dp is not None and dp[i] is not None:
+                s_attn, s_mlp = dp[i]
+            x1 = ops.gemm_nt(o, fp.c(b + "attn.proj.weight"), bias=fp.p(b + "attn.proj.bias"), epi=ops.EPI_RESID,
+                             resid=x, rowscale=s_attn, rows_per_seq=N, out=lt("x1", (M, D)))
+            h2, mean2, rstd2 = self._ln(x1, fp.p(b + "norm2.weight"), fp.p(b + "norm2.bias"), M, lt("h2", (M, D)),
+                                        lt("mean2", (M,)), lt("rstd2", (M,)))
+            u = lt("u", (M, 4 * D))
+            g = ops.gemm_nt(h2, fp.c(b + "mlp.fc1.weight"), bias=fp.p(b + "mlp.fc1.bias"), epi=ops.EPI_GELU, aux=u,
+                            round_out=True, out=lt("g", (M, 4 * D)))
+            x2 = ops.gemm_nt(g, fp.c(b + "mlp.fc2.weight"), bias=fp.p(b + "mlp.fc2.bias"), epi=ops.EPI_RESID,
+                             resid=x1, rowscale=s_mlp, rows_per_seq=N, out=lt("x2", (M, D)))
+            if save:
+                ctx["layers"].append(dict(x=x, h=h, mean1=mean1, rstd1=rstd1, qkv=qkv, o=o, lse=lse, x1=x1, h2=h2,
+                                          mean2=mean2, rstd2=rstd2, u=u, g=g))
+            x = x2
+        ctx["x_final"] = x
+        nm = px + self.norm_name
+        if self.use_cls:
+            out = t("cls_out", (S, D))
+            mean = t("meanf", (S,))
+            rstd = t("rstdf", (S,))
+            ops.layernorm_fwd(x, fp.p(nm + ".weight"), fp.p(nm + ".bias"), S, D, x_stride=N * D, out=out, mean=mean,
+                              rstd=rstd)
+        else:
+            out = t("xn", (M, D))
+            mean = t("meanf", (M,))
+            rstd = t("rstdf", (M,))
+            self._ln(x, fp.p(nm + ".weight"), fp.p(nm + ".bias"), M, out, mean, rstd)
+        ctx["meanf"], ctx["rstdf"] = mean, rstd
+        return out, ctx
+
+    def _ln(self, x, g, b, rows, out, mean, rstd):
+        return ops.layernorm_fwd(x, g, b, rows, self.D, out=out, mean=mean, rstd=rstd)
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, fp, ws, ctx, d_out):
+        """d_out: gradient wrt forward()'s output ([S,D] clip model / [S*N,D] frame model).
+        Accumulates parameter gradients into fp.grad."""
+        px, D, H = self.px, self.D, self.H
+        S, P, N, M, tag = ctx["S"], ctx["P"], ctx["N"], ctx["M"], ctx["tag"]
+        t = (lambda name, shape: ws.get(tag + "/bwd/" + name, shape))
+        nm = px + self.norm_name
+        dxa, dxb = t("dxa", (M, D)), t("dxb", (M, D))
+        if self.use_cls:
+            dxa.zero_()
+            ops.layernorm_bwd(d_out, ctx["x_final"], ctx["meanf"], ctx["rstdf"], fp.p(nm + ".weight"),
+                              fp.g(nm + ".weight"), fp.g(nm + ".bias"), S, D, dx=dxa, x_stride=N * D, dx_stride=N * D)
+        else:
+            ops.layernorm_bwd(d_out, ctx["x_final"], ctx["meanf"], ctx["rstdf"], fp.p(nm + ".weight"),
+                              fp.g(nm + ".weight"), fp.g(nm + ".bias"), M, D, dx=dxa)
+        dx = dxa
+        other = dxb
+        dp = ctx["dp"]
+        for i in reversed(range(self.depth)):
+            b = "%sblocks.%d." % (px, i)
+            L = ctx["layers"][i]
+            s_attn = s_mlp = None
+            if dp is not None and dp[i] is not None:
+                s_attn, s_mlp = dp[i]
+            # ---- MLP branch: x2 = x1 + s * (g W2^T + b2)
+            dys = self._scaled(dx, s_mlp, N, t("dys", (M, D)))
+            ops.colsum_acc(dys, fp.g(b + "mlp.fc2.bias"))
+            ops.gemm_tn_acc(dys, L["g"], fp.g(b + "mlp.fc2.weight"))
+            du = ops.gemm_nn(dys, fp.c(b + "mlp.fc2.weight"), epi=ops.EPI_DGELU, aux=L["u"], round_out=True,
+                             out=t("du", (M, 4 * D)))
+            ops.colsum_acc(du, fp.g(b + "mlp.fc1.bias"))
+            ops.gemm_tn_acc(du, L["h2"], fp.g(b + "mlp.fc1.weight"))
+            dh2 = ops.gemm_nn(du, fp.c(b + "mlp.fc1.weight"), out=t("dh", (M, D)))
+            dx1 = ops.layernorm_bwd(dh2, L["x1"], L["mean2"], L["rstd2"], fp.p(b + "norm2.weight"),
+                                    fp.g(b + "norm2.weight"), fp.g(b + "norm2.bias"), M, D, dres=dx, dx=other)
+            # ---- attention branch: x1 = x + s * (o Wp^T + bp)
+            dys = self._scaled(dx1, s_attn, N, t("dys", (M, D)))
+            ops.colsum_acc(dys, fp.g(b + "attn.proj.bias"))
+            ops.gemm_tn_acc(dys, L["o"], fp.g(b + "attn.proj.weight"))
+            d_o = ops.gemm_nn(dys, fp.c(b + "attn.proj.weight"), round_out=True, out=t("d_o", (M, D)))
+            dqkv = ops.attention_bwd(L["qkv"], L["o"], d_o, L["lse"], S, N, H, ctx["key_len"],
+                                     dqkv=t("dqkv", (M, 3 * D)), delta_ws=t("delta", (S, H, N)))
+            ops.gemm_tn_acc(dqkv, L["h"], fp.g(b + "attn.qkv.weight"))
+            dh = ops.gemm_nn(dqkv, fp.c(b + "attn.qkv.weight"), out=t("dh", (M, D)))
+            ops.layernorm_bwd(dh, L["x"], L["mean1"], L["rstd1"], fp.p(b + "norm1.weight"), fp.g(b + "norm1.weight"),
+                              fp.g(b + "norm1.bias"), M, D, dres=dx1, dx=dx)
+            # dx now holds the gradient wrt the block input; `other` is free again
+        dpe = t("dpe", (S * P, D))
+        ops.tokens_bwd(dx, dpe, fp.g(px + "pos_embed"), fp.g(px + "cls_token") if self.use_cls else None, S, P, D,
+                       use_cls=self.use_cls, mask=ctx["mask"],
+                       dmask_embed=fp.g(px + "mask_embed") if ctx["mask"] is not None else None)
+        ops.colsum_acc(dpe, fp.g(px + "patch_embed.patch_embed.bias"))
+        ops.gemm_tn_acc(dpe, ctx["patches"], fp.g(px + "patch_embed.patch_embed.weight"))
+
+    def _scaled(self, dy, scale, rows_per_seq, buf):
+        """s[row // rows_per_seq] * dy (DropPath backward); identity when the path is never dropped."""
+        if scale is None:
+            return dy
+        M, D = dy.shape
+        torch.mul(dy.view(-1, rows_per_seq, D), scale.view(-1, 1, 1), out=buf.view(-1, rows_per_seq, D))
+        return buf
+
+
+class HeadEngine:
+    """Linear(in,4096,no bias) -> BatchNorm1d(4096, train) -> ReLU -> Linear(4096,256,no bias)."""
+
+    def __init__(self, prefix, in_dim, hidden=4096, out_dim=256):
+        self.px, self.in_dim, self.hidden, self.out_dim = prefix, in_dim, hidden, out_dim
+
+    def forward(self, fp, ws, x, bn_buffers, tag, round_out, stats_sync=None, momentum=0.1, eps=1e-5):
+        """x [R, in] (tf32-rounded).  bn_buffers: (running_mean, running_var, num_batches_tracked) or None.
+        stats_sync(mean, m2, n) -> (mean, m2, n_total): SyncBatchNorm statistics exchange (DDP)."""
+        px = self.px
+        R = x.shape[0]
+        t = (lambda name, shape: ws.get(tag + "/" + px + name, shape))
+        z1 = ops.gemm_nt(x, fp.c(px + "0.weight"), out=t("z1", (R, self.hidden)))
+        mean, m2 = ops.bn_stats(z1)
+        n = float(R)
+        if stats_sync is not None:
+            mean, m2, n = stats_sync(mean, m2, n)
+        rm = rv = None
+        if bn_buffers is not None:
+            rm, rv, nbt = bn_buffers
+            nbt += 1
+        rstd = ops.bn_finalize(mean, m2, n, rm, rv, eps=eps, momentum=momentum)
+        a1 = ops.bn_relu_fwd(z1, mean, rstd, fp.p(px + "1.weight"), fp.p(px + "1.bias"), out=t("a1", (R, self.hidden)))
+        z2 = ops.gemm_nt(a1, fp.c(px + "3.weight"), round_out=round_out, out=t("z2", (R, self.out_dim)))
+        ctx = dict(x=x, z1=z1, mean=mean, rstd=rstd, a1=a1, n=n, R=R, tag=tag)
+        return z2, ctx
+
+    def backward(self, fp, ws, ctx, dz2, need_dx=True, sums_sync=None):
+        """dz2 [R,256] tf32-rounded.  sums_sync(s1, s2) -> all-reduced (SyncBatchNorm backward)."""
+        px = self.px
+        R, tag = ctx["R"], ctx["tag"]
+        t = (lambda name, shape: ws.get(tag + "/bwd/" + px + name, shape))
+        ops.gemm_tn_acc(dz2, ctx["a1"], fp.g(px + "3.weight"))
+        da1 = ops.gemm_nn(dz2, fp.c(px + "3.weight"), out=t("da1", (R, self.hidden)))
+        gamma, beta = fp.p(px + "1.weight"), fp.p(px + "1.bias")
+        s1, s2 = ops.bn_relu_bwd_stats(da1, ctx["z1"], ctx["mean"], ctx["rstd"], gamma, beta)
+        fp.g(px + "1.bias").add_(s1)
+        fp.g(px + "1.weight").add_(s2)
+        if sums_sync is not None:
+            s1, s2 = sums_sync(s1, s2)
+        dz1 = ops.bn_relu_bwd_apply(da1, ctx["z1"], ctx["mean"], ctx["rstd"], gamma, beta, s1, s2, ctx["n"],
+                                    out=t("dz1", (R, self.hidden)))
+        ops.gemm_tn_acc(dz1, ctx["x"], fp.g(px + "0.weight"))
+        if not need_dx:
+            return None
+        return ops.gemm_nn(dz1, fp.c(px + "0.weight"), round_out=False, out=t("dx", (R, self.in_dim)))

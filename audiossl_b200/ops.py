@@ -10,6 +10,35 @@ from ._lib import check, ptr
 
 EPI_STORE, EPI_GELU, EPI_DGELU, EPI_RESID, EPI_SCALE, EPI_RELU = 0, 1, 2, 3, 4, 5
 
+# launch accounting for bench.py: kernels launched through the C ABI, algorithmic GEMM flops, and (optionally)
+# a CUDA-event pair around every GEMM launch to measure the dominant kernel in place
+STATS = {"launches": 0, "gemm_flops": 0.0, "gemm_launches": 0, "time_gemms": False, "gemm_events": []}
+
+
+def reset_stats():
+    STATS.update(launches=0, gemm_flops=0.0, gemm_launches=0, gemm_events=[])
+
+
+class _GemmTimer:
+    def __init__(self, flops):
+        self.flops = flops
+        STATS["launches"] += 1
+        STATS["gemm_launches"] += 1
+        STATS["gemm_flops"] += flops
+        self.ev = None
+        if STATS["time_gemms"]:
+            self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.ev[0].record()
+
+    def done(self):
+        if self.ev is not None:
+            self.ev[1].record()
+            STATS["gemm_events"].append((self.ev[0], self.ev[1], self.flops))
+
+
+def _count(n):
+    STATS["launches"] += n
+
 
 def _f32c(t, name):
     if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
@@ -29,6 +58,7 @@ def mel_forward(wav, win_length=1024, normalize=True, out=None):
     ws = torch.empty((B,), device=wav.device, dtype=torch.int32)
     check(_lib.lib().atst_mel_forward(ptr(w2), B, n, w2.stride(0), win_length, ptr(out), 64 * T, ptr(ws),
                                       1 if normalize else 0, _lib.stream()), "atst_mel_forward")
+    _count(3)
     return out.reshape(*lead, 64, T)
 
 
@@ -40,10 +70,12 @@ def gemm_nt(A, B, bias=None, epi=EPI_STORE, resid=None, aux=None, rowscale=None,
     assert B.shape[1] == K
     if out is None:
         out = torch.empty((M, N), device=A.device, dtype=torch.float32)
+    _t = _GemmTimer(2.0 * M * N * K)
     check(_lib.lib().atst_gemm_nt(ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(out), out.stride(0), M, N, K,
                                   ptr(bias), epi, ptr(resid), resid.stride(0) if resid is not None else 0,
                                   ptr(aux), aux.stride(0) if aux is not None else 0, ptr(rowscale), rows_per_seq,
                                   1 if round_out else 0, _lib.stream()), "atst_gemm_nt")
+    _t.done()
     return out
 
 
@@ -54,9 +86,11 @@ def gemm_nn(A, W, epi=EPI_STORE, aux=None, rowscale=None, rows_per_seq=1, round_
     assert W.shape[0] == K
     if out is None:
         out = torch.empty((M, N), device=A.device, dtype=torch.float32)
+    _t = _GemmTimer(2.0 * M * N * K)
     check(_lib.lib().atst_gemm_nn(ptr(A), A.stride(0), ptr(W), W.stride(0), ptr(out), out.stride(0), M, N, K, epi,
                                   ptr(aux), aux.stride(0) if aux is not None else 0, ptr(rowscale), rows_per_seq,
                                   1 if round_out else 0, _lib.stream()), "atst_gemm_nn")
+    _t.done()
     return out
 
 
@@ -65,21 +99,27 @@ def gemm_tn_acc(A, B, out):
     T, M = A.shape
     N = B.shape[1]
     assert B.shape[0] == T and tuple(out.shape) == (M, N)
+    _t = _GemmTimer(2.0 * M * N * T)
     check(_lib.lib().atst_gemm_tn(ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(out), out.stride(0), M, N, T,
                                   _lib.stream()), "atst_gemm_tn")
+    _t.done()
     return out
 
 
-def layernorm_fwd(x, gamma, beta, rows, D, x_stride=None, out=None, out_stride=None, eps=1e-6, round_out=True):
+def layernorm_fwd(x, gamma, beta, rows, D, x_stride=None, out=None, out_stride=None, eps=1e-6, round_out=True,
+                  mean=None, rstd=None):
     x_stride = D if x_stride is None else x_stride
     if out is None:
         out = torch.empty((rows, D), device=x.device, dtype=torch.float32)
     out_stride = D if out_stride is None else out_stride
-    mean = torch.empty((rows,), device=x.device, dtype=torch.float32)
-    rstd = torch.empty((rows,), device=x.device, dtype=torch.float32)
+    if mean is None:
+        mean = torch.empty((rows,), device=x.device, dtype=torch.float32)
+    if rstd is None:
+        rstd = torch.empty((rows,), device=x.device, dtype=torch.float32)
     check(_lib.lib().atst_layernorm_forward(ptr(x), x_stride, ptr(gamma), ptr(beta), ptr(out), out_stride, ptr(mean),
                                             ptr(rstd), rows, D, eps, 1 if round_out else 0, _lib.stream()),
           "atst_layernorm_forward")
+    _count(1)
     return out, mean, rstd
 
 
@@ -94,6 +134,7 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, rows, D, dres=None, d
     check(_lib.lib().atst_layernorm_backward(ptr(dy), dy_stride, ptr(x), x_stride, ptr(mean), ptr(rstd), ptr(gamma),
                                              ptr(dres), dres_stride, ptr(dx), dx_stride, ptr(dgamma), ptr(dbeta),
                                              rows, D, _lib.stream()), "atst_layernorm_backward")
+    _count(1)
     return dx
 
 
@@ -105,6 +146,7 @@ def attention_fwd(qkv, S, N, H, lengths=None, out=None, lse=None):
         lse = torch.empty((S, H, N), device=qkv.device, dtype=torch.float32)
     check(_lib.lib().atst_attention_forward(ptr(qkv), ptr(out), ptr(lse), ptr(lengths), S, N, H, _lib.stream()),
           "atst_attention_forward")
+    _count(1)
     return out, lse
 
 
@@ -115,6 +157,7 @@ def attention_bwd(qkv, o, d_o, lse, S, N, H, lengths=None, dqkv=None, delta_ws=N
         delta_ws = torch.empty((S, H, N), device=qkv.device, dtype=torch.float32)
     check(_lib.lib().atst_attention_backward(ptr(qkv), ptr(o), ptr(d_o), ptr(lse), ptr(delta_ws), ptr(dqkv),
                                              ptr(lengths), S, N, H, _lib.stream()), "atst_attention_backward")
+    _count(3)
     return dqkv
 
 
@@ -126,6 +169,7 @@ def patchify(mel, out=None):
     if out is None:
         out = torch.empty((S * P, 256), device=mel.device, dtype=torch.float32)
     check(_lib.lib().atst_patchify(ptr(mel), 64 * T, S, T, ptr(out), _lib.stream()), "atst_patchify")
+    _count(1)
     return out
 
 
@@ -135,12 +179,14 @@ def tokens_fwd(pe, cls, pos, S, P, D, use_cls=True, mask_embed=None, mask=None, 
         out = torch.empty((S * N, D), device=pe.device, dtype=torch.float32)
     check(_lib.lib().atst_tokens_forward(ptr(pe), ptr(cls), ptr(pos), ptr(mask_embed), ptr(mask), ptr(out), S, P, D,
                                          1 if use_cls else 0, _lib.stream()), "atst_tokens_forward")
+    _count(1)
     return out
 
 
 def tokens_bwd(dx, dpe, dpos, dcls, S, P, D, use_cls=True, mask=None, dmask_embed=None):
     check(_lib.lib().atst_tokens_backward(ptr(dx), ptr(mask), ptr(dpe), ptr(dpos), ptr(dcls), ptr(dmask_embed), S, P,
                                           D, 1 if use_cls else 0, _lib.stream()), "atst_tokens_backward")
+    _count(1)
 
 
 def colsum_acc(X, out, rows=None, cols=None, ld=None):
@@ -148,6 +194,7 @@ def colsum_acc(X, out, rows=None, cols=None, ld=None):
     cols = X.shape[1] if cols is None else cols
     ld = X.stride(0) if ld is None else ld
     check(_lib.lib().atst_colsum_accumulate(ptr(X), ld, rows, cols, ptr(out), _lib.stream()), "atst_colsum")
+    _count(1)
 
 
 def bn_stats(X):
@@ -155,6 +202,7 @@ def bn_stats(X):
     mean = torch.empty((cols,), device=X.device, dtype=torch.float32)
     m2 = torch.empty((cols,), device=X.device, dtype=torch.float32)
     check(_lib.lib().atst_bn_stats(ptr(X), rows, cols, ptr(mean), ptr(m2), _lib.stream()), "atst_bn_stats")
+    _count(1)
     return mean, m2
 
 
@@ -162,6 +210,7 @@ def bn_finalize(mean, m2, count, running_mean=None, running_var=None, eps=1e-5, 
     rstd = torch.empty_like(mean)
     check(_lib.lib().atst_bn_finalize(ptr(mean), ptr(m2), float(count), eps, momentum, ptr(rstd), ptr(running_mean),
                                       ptr(running_var), mean.numel(), _lib.stream()), "atst_bn_finalize")
+    _count(1)
     return rstd
 
 
@@ -171,6 +220,7 @@ def bn_relu_fwd(X, mean, rstd, gamma, beta, out=None):
         out = torch.empty_like(X)
     check(_lib.lib().atst_bn_relu_forward(ptr(X), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ptr(out), rows, cols,
                                           _lib.stream()), "atst_bn_relu_forward")
+    _count(1)
     return out
 
 
@@ -180,6 +230,7 @@ def bn_relu_bwd_stats(dY, X, mean, rstd, gamma, beta):
     s2 = torch.empty((cols,), device=X.device, dtype=torch.float32)
     check(_lib.lib().atst_bn_relu_backward_stats(ptr(dY), ptr(X), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), rows,
                                                  cols, ptr(s1), ptr(s2), _lib.stream()), "atst_bn_relu_backward_stats")
+    _count(1)
     return s1, s2
 
 
@@ -190,6 +241,7 @@ def bn_relu_bwd_apply(dY, X, mean, rstd, gamma, beta, s1, s2, count, out=None):
     check(_lib.lib().atst_bn_relu_backward_apply(ptr(dY), ptr(X), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta),
                                                  ptr(s1), ptr(s2), float(count), ptr(out), rows, cols,
                                                  _lib.stream()), "atst_bn_relu_backward_apply")
+    _count(1)
     return out
 
 
@@ -200,6 +252,7 @@ def byol_loss(student, teacher, ncrops, B, dstudent=None, acc=None):
         acc = torch.empty((1 + 4 * 256,), device=student.device, dtype=torch.float32)
     check(_lib.lib().atst_byol_loss(ptr(student), ptr(teacher), ncrops, B, ptr(dstudent), ptr(acc), _lib.stream()),
           "atst_byol_loss")
+    _count(1)
     return dstudent, acc
 
 
@@ -208,25 +261,30 @@ def byol_finalize(acc, n_student_rows, n_teacher_rows, ncrops, B, out=None):
         out = torch.empty((3,), device=acc.device, dtype=torch.float32)
     check(_lib.lib().atst_byol_finalize(ptr(acc), float(n_student_rows), float(n_teacher_rows), ncrops, B, ptr(out),
                                         _lib.stream()), "atst_byol_finalize")
+    _count(1)
     return out
 
 
 def ema_update(k, q, m):
     assert k.numel() == q.numel()
     check(_lib.lib().atst_ema_update(ptr(k), ptr(q), float(m), k.numel(), _lib.stream()), "atst_ema_update")
+    _count(1)
 
 
 def adamw_step(p, g, m, v, step, lr, wd, beta1=0.9, beta2=0.999, eps=1e-6, grad_scale=1.0):
     check(_lib.lib().atst_adamw_step(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), int(step), float(lr), float(wd),
                                      beta1, beta2, eps, float(grad_scale), _lib.stream()), "atst_adamw_step")
+    _count(1)
 
 
 def round_tf32(src, dst=None):
     if dst is None:
         dst = torch.empty_like(src)
     check(_lib.lib().atst_round_tf32(ptr(src), ptr(dst), src.numel(), _lib.stream()), "atst_round_tf32")
+    _count(1)
     return dst
 
 
 def axpy(y, x, a):
     check(_lib.lib().atst_axpy(ptr(y), ptr(x), float(a), y.numel(), _lib.stream()), "atst_axpy")
+    _count(1)

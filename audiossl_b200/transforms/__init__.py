@@ -1,0 +1,6 @@
+from .common import (CentralCrop, GaussianNoise, Identity, MinMax, Normalize, PadToSize, RandomCrop, ToSizeN, div)
+from .byol_a import MixGaussianNoise, Mixup, RandomResizeCrop, log_mixup_exp
+from .mel import LogMelSpectrogram
+
+__all__ = ["CentralCrop", "GaussianNoise", "Identity", "MinMax", "Normalize", "PadToSize", "RandomCrop", "ToSizeN",
+           "div", "MixGaussianNoise", "Mixup", "RandomResizeCrop", "log_mixup_exp", "LogMelSpectrogram"]

@@ -1,0 +1,294 @@
+"""ATST pre-training step throughput (BASELINE.json metric) on N B200s of one node, or the CPU reference arm.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3                 # our arm, one JSON line on stdout
+    torchrun --nproc-per-node N ... bench.py --gpus N ...          # one rank per GPU (NCCL), weak scaling
+    python bench.py --impl reference --steps 3 --warmup 1          # the reference's algorithm on the host cores
+
+One "step" = one pass of the hot path over one synthetic batch: fused log-mel of both views (raw 16 kHz
+waveforms already in HBM) -> EMA-teacher forward + student forward (AST-base, 251 tokens) -> BYOL loss ->
+student backward -> gradient all-reduce (N > 1) -> HF-AdamW -> teacher EMA.  Workload at N = 1 is BASELINE
+config 2: ATST-base, 10 s clips, 64 mels, 256 clips per GPU, DropPath 0.1 as in the recipe.
+`e2e` repeats the measurement through the public Lightning-style API with HOST (pinned) waveforms: the
+host->device copy of both views and the device->host read of the loss are inside the timed region.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CLIP_SECONDS = 10.0
+SR = 16000
+STEP_GFLOP_PER_CLIP = 360.5  # BASELINE.md section 4, config 2 (teacher fwd + student fwd + student bwd)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "src": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi style clock / throttle-reason sampling during the timed region (pynvml, 200 ms)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_step_fn(batch, threads=None):
+    """The reference's algorithm on the host: oracle mel_feature x2 views + teacher fwd + student fwd + loss +
+    backward + EMA on ATST-base / 10 s clips (oracle/atst_oracle.py, pinned against the reference's outputs)."""
+    import numpy as np
+    import torch
+    from oracle import atst_oracle as O
+    if threads:
+        torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    model = O.OracleATST("base")
+    model.train()
+    g = torch.Generator().manual_seed(1234)
+    wav = (torch.randn(2, batch, 1, int(CLIP_SECONDS * SR), generator=g) * 0.1).numpy()
+    depth = 12
+    rates = torch.linspace(0, 0.1, depth).tolist()
+
+    def dp(S):
+        out = []
+        for r in rates:
+            if r == 0:
+                out.append(None)
+                continue
+            keep = 1 - r
+            out.append((torch.floor(keep + torch.rand(S)) / keep, torch.floor(keep + torch.rand(S)) / keep))
+        return [out]
+
+    def step():
+        crops = [torch.from_numpy(O.mel_feature(wav[v])) for v in range(2)]
+        lengths = [torch.full((batch,), crops[0].shape[-1], dtype=torch.int64)] * 2
+        for p in model.student.parameters():
+            p.grad = None
+        loss, _, _ = model(crops, lengths, dp_student=dp(2 * batch), dp_teacher=dp(2 * batch))
+        loss.backward()
+        model.update_teacher(0.9995)
+        return float(loss.detach())
+
+    return step
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 4
+    cores = os.cpu_count() or 1
+    step = cpu_reference_step_fn(batch, cores)
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = batch / dt
+    line = {"impl": "reference", "metric": "ATST-base clips/sec (student+teacher fwd + bwd)", "value": val,
+            "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "ATST-base, 10 s 16 kHz clips, 64 mel, 2 views, DropPath 0.1; CPU sample of %d clips/step"
+                                   % batch},
+            "cpu_baseline": {"value": val, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": "%d steps of %d clips (oracle port of the reference algorithm, torch CPU fp32)"
+                                       % (args.steps, batch)},
+            "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from audiossl_b200 import ops
+    from audiossl_b200.methods.atst.model import ATSTLightningModule
+    from audiossl_b200.transforms import LogMelSpectrogram
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    n = int(CLIP_SECONDS * SR)
+    torch.manual_seed(0)
+    lm = ATSTLightningModule(arch=args.arch, learning_rate=2e-4, warmup_steps=10, max_steps=100000, ema=0.9995)
+    lm.cuda().train()
+    opt = lm.configure_optimizers()[0]
+    lm.trainer.optimizers = [opt]
+    mel = LogMelSpectrogram()
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    wav_dev = torch.randn(2, B, 1, n, device=dev, generator=g) * 0.1
+    wav_host = wav_dev.cpu().pin_memory()
+    lengths = [torch.full((B,), n // 160 + 1, device=dev, dtype=torch.int64)] * 2
+    stage = torch.empty_like(wav_dev)
+
+    def step(i, from_host):
+        if from_host:
+            stage.copy_(wav_host, non_blocking=True)
+            src = stage
+        else:
+            src = wav_dev
+        crops = [mel(src[0]), mel(src[1])]
+        lm.global_step = i
+        loss = lm.training_step(((crops, lengths), None), i)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        lm.on_train_batch_end(None, None, i)
+        if from_host:
+            return loss.item()  # device -> host read of the step's result
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(from_host, steps, start_i):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step(start_i + i, from_host)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for i in range(args.warmup):
+        step(i, False)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ops.reset_stats()
+    ms = timed(False, args.steps, args.warmup)
+    launches = ops.STATS["launches"]
+    gemm_flops_step = ops.STATS["gemm_flops"] / args.steps
+    ms_e2e = timed(True, args.steps, args.warmup + args.steps)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    # dominant kernel (gemm_tf32_kernel) measured in place: one extra step with an event pair around every launch
+    ops.STATS["time_gemms"] = True
+    ops.reset_stats()
+    torch.cuda.synchronize()
+    step(args.warmup + 2 * args.steps, False)
+    torch.cuda.synchronize()
+    ops.STATS["time_gemms"] = False
+    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in ops.STATS["gemm_events"])
+    gemm_fl = sum(f for _, _, f in ops.STATS["gemm_events"])
+    n_gemm = len(ops.STATS["gemm_events"])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    ms_step = ms / args.steps
+    value = B * world / (ms_step / 1e3)
+    e2e_val = B * world / (ms_e2e / args.steps / 1e3)
+    achieved = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    line = {
+        "metric": "ATST-base clips/sec (student+teacher fwd + bwd)", "value": value, "unit": "clips/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
+        "data": "synthetic",
+        "config": {"workload": "ATST-%s, 10 s 16 kHz clips, 64 mel, 2 views, %d clips/GPU, DropPath 0.1, "
+                               "mel+teacher fwd+student fwd+loss+bwd+AdamW+EMA" % (args.arch, B),
+                   "parallelism": "dp%d" % world, "l2": "inputs_exceed_l2 (>=80 GB of activations per step)",
+                   "step_gflop_per_clip_algorithmic": STEP_GFLOP_PER_CLIP},
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e_val, "unit": "clips/s", "h2d_bytes_per_step": wav_host.numel() * 4,
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "kernel": "gemm_tf32_kernel (tcgen05 kind::tf32)", "achieved": achieved,
+                     "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None,
+                     "peak_source": pk["src"] + " bf16 cuBLAS sustained; TF32 tensor rate is half of bf16",
+                     "launches_per_step": n_gemm, "gemm_ms_per_step": gemm_ms,
+                     "gemm_share_of_step": gemm_ms / ms_step,
+                     "algorithmic_gemm_tflop_per_step": gemm_flops_step / 1e12,
+                     "model_flops_utilisation_of_step": STEP_GFLOP_PER_CLIP * 1e9 * B / (ms_step / 1e3) / 1e12 / pk["tflops"]},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        cstep = cpu_reference_step_fn(4, cores)
+        cstep()
+        t0 = time.perf_counter()
+        k = 0
+        while k < 2 or (time.perf_counter() - t0 < 10.0 and k < 8):
+            cstep()
+            k += 1
+        dt = (time.perf_counter() - t0) / k
+        line["cpu_baseline"] = {"value": 4 / dt, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": "%d steps of 4 clips of the same workload (oracle port, torch CPU fp32)" % k}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="clips per GPU")
+    ap.add_argument("--arch", default="base")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.warmup < 3 and a.impl == "ours":
+        a.warmup = 3
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

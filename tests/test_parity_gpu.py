@@ -1,0 +1,238 @@
+"""GPU parity tests: the CUDA path (through the public API / C ABI) against the CPU oracle and the golden
+vectors generated from the unmodified reference.  Tolerances: the GEMMs use TF32 operands (10-bit mantissa,
+fp32 accumulate) so forward outputs/loss are held to 1e-3 relative (north_star), gradients to 2e-2 of the
+gradient RMS; everything that is not a GEMM (mel, LayerNorm, loss, EMA, AdamW) is fp32 and held tighter."""
+import numpy as np
+import pytest
+import torch
+
+from tests import util
+from tests.golden import detfill
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+# --------------------------------------------------------------------------- mel (bit-exact shape / index)
+MEL_KEYS = [k for k in util.gold("mel.npz").files if not k.startswith("batch")]
+
+
+@pytest.mark.parametrize("key", MEL_KEYS)
+def test_mel_golden(key):
+    from audiossl_b200.transforms import LogMelSpectrogram
+    g = util.gold("mel.npz")
+    kind, n, win = key.rsplit("_", 2)
+    n, win = int(n), int(win[1:])
+    wav = torch.from_numpy(detfill.signal(kind, n))[None].cuda()
+    y = LogMelSpectrogram(win_length=win)(wav).cpu().numpy()
+    assert y.shape == g[key].shape == (1, 64, n // 160 + 1)
+    np.testing.assert_allclose(y, g[key], rtol=0, atol=2e-4)
+    assert np.abs(y - g[key]).mean() < 5e-6
+
+
+def test_mel_batched_matches_per_clip_and_golden():
+    from audiossl_b200.transforms import LogMelSpectrogram
+    g = util.gold("mel.npz")
+    wavs = torch.stack([torch.from_numpy(detfill.signal(k, 16000)) for k in ("noise", "sine_silence", "chirp")])
+    y = LogMelSpectrogram()(wavs[:, None].cuda()).cpu().numpy()
+    assert y.shape == (3, 1, 64, 101)
+    np.testing.assert_allclose(y, g["batch3_16000_w1024"], rtol=0, atol=2e-4)
+
+
+def test_mel_full_size_properties():
+    """BASELINE config-2 shape (10 s clips): oracle on a sample of clips + clip independence + silence floor."""
+    from audiossl_b200 import ops
+    from oracle import atst_oracle as O
+    gen = torch.Generator().manual_seed(1234)
+    wav = torch.randn(32, 1, 160000, generator=gen) * 0.1
+    wav[5] = 0.0  # all-zero clip: amin floor, everything clamps to the same value
+    y = ops.mel_forward(wav.cuda()).cpu()
+    assert y.shape == (32, 1, 64, 1001)
+    ref = O.mel_feature(wav[:3].numpy())
+    np.testing.assert_allclose(y[:3].numpy(), ref, rtol=0, atol=2e-4)
+    assert torch.all(y[5] == y[5, 0, 0, 0])
+    y2 = ops.mel_forward(wav[7:9].cuda()).cpu()  # a clip's output does not depend on its batch neighbours
+    assert torch.equal(y2, y[7:9])
+
+
+def test_mel_rejects_bad_input():
+    from audiossl_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.mel_forward(torch.zeros(1, 300, device="cuda"))  # shorter than the reflect pad
+    with pytest.raises(RuntimeError):
+        ops.mel_forward(torch.zeros(1, 16000, device="cuda"), win_length=512)
+
+
+# --------------------------------------------------------------------------- kernels vs torch fp32
+@pytest.mark.parametrize("M,N,K", [(156, 384, 128), (300, 128, 256), (1004, 2304, 768), (70, 4096, 128), (512, 256, 4096)])
+def test_gemm_nt_exact_on_tf32_inputs(M, N, K):
+    from audiossl_b200 import ops
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    A = ops.round_tf32(torch.randn(M, K, device="cuda"))
+    B = ops.round_tf32(torch.randn(N, K, device="cuda") * 0.05)
+    bias = torch.randn(N, device="cuda")
+    assert rel(ops.gemm_nt(A, B, bias=bias), A @ B.t() + bias) < 2e-5
+
+
+@pytest.mark.parametrize("T,M,N", [(96, 128, 128), (1000, 256, 384), (4000, 768, 2304), (130, 4096, 256)])
+def test_gemm_wgrad_dgrad(T, M, N):
+    from audiossl_b200 import ops
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(1)
+    A = ops.round_tf32(torch.randn(T, M, device="cuda") * 0.1)
+    B = ops.round_tf32(torch.randn(T, N, device="cuda") * 0.1)
+    C = torch.ones(M, N, device="cuda")
+    ops.gemm_tn_acc(A, B, C)
+    assert rel(C, 1.0 + A.t() @ B) < 2e-5  # accumulates into the existing gradient
+    W = ops.round_tf32(torch.randn(M, N, device="cuda") * 0.1)
+    assert rel(ops.gemm_nn(A, W), A @ W) < 2e-5
+
+
+def test_attention_matches_reference_formula():
+    from audiossl_b200 import ops
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    S, N, H = 3, 151, 6
+    D = H * 64
+    qkv = ops.round_tf32(torch.randn(S * N, 3 * D, device="cuda"))
+    lengths = torch.tensor([N, 77, 1], dtype=torch.int32, device="cuda")
+    q = qkv.clone().requires_grad_(True)
+    t = q.reshape(S, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+    att = (t[0] @ t[1].transpose(-2, -1)) * 0.125
+    att = att + ((torch.arange(N, device="cuda")[None] >= lengths[:, None]) * -10000.0)[:, None, None, :]
+    o_ref = (att.softmax(-1) @ t[2]).transpose(1, 2).reshape(S * N, D)
+    d_o = ops.round_tf32(torch.randn(S * N, D, device="cuda"))
+    o_ref.backward(d_o)
+    o, lse = ops.attention_fwd(qkv, S, N, H, lengths)
+    dqkv = ops.attention_bwd(qkv, o, d_o, lse, S, N, H, lengths)
+    assert rel(o, o_ref) < 1e-3
+    assert rel(dqkv, q.grad) < 1e-3
+
+
+# --------------------------------------------------------------------------- full model vs oracle / golden
+def build_cuda_model(case):
+    from audiossl_b200.models.atst import ATST
+    c = util.CASES[case]
+    m = ATST(arch=dict(embed_dim=c["dim"], depth=c["depth"], num_heads=c["heads"]), ncrops=c["ncrops"],
+             drop_path_rate=c.get("drop_path", 0.0))
+    util.load_det(m.student)
+    util.load_det(m.teacher)
+    m.cuda().train()
+    return m, c
+
+
+def run_case(case, dp=None):
+    m, c = build_cuda_model(case)
+    crops, lengths = util.make_inputs(case, c["B"], c["widths"], c["lens"])
+    crops = [x.cuda() for x in crops]
+    lengths = [x.cuda() for x in lengths]
+    kw = {}
+    if dp is not None:
+        kw = dict(dp_teacher=dp[0], dp_student=dp[1])
+    loss, std_s, std_t = m(crops, lengths, **kw)
+    loss.backward()
+    return m, c, loss, std_s, std_t
+
+
+@pytest.mark.parametrize("case", ["tiny2", "tiny4", "small2"])
+def test_atst_step_matches_reference_golden(case):
+    g = util.gold("atst.npz")
+    m, c, loss, std_s, std_t = run_case(case)
+    s_out, t_out = m._rt.last_outputs
+    # north_star: forward / loss within 1e-3 relative of the fp32 reference
+    assert rel(s_out, g[case + "/student_out"]) < 1e-3
+    assert rel(t_out, g[case + "/teacher_out"]) < 1e-3
+    np.testing.assert_allclose(loss.item(), g[case + "/loss"], rtol=1e-3)
+    np.testing.assert_allclose(std_s.item(), g[case + "/std_s"], rtol=1e-3)
+    np.testing.assert_allclose(std_t.item(), g[case + "/std_t"], rtol=1e-3)
+    n = 0
+    for name, p in m.student.named_parameters():
+        key = case + "/grad/" + name
+        if key + "/idx" not in g.files:
+            continue
+        assert p.grad is not None, name
+        util.check_summary(p.grad.cpu().numpy(), g, key, rtol=2e-2, atol=2e-2)
+        n += 1
+    assert n > 20
+    for name, b in m.named_buffers():
+        if "running" in name:
+            util.check_summary(b.cpu().numpy(), g, case + "/buf/" + name, rtol=2e-3, atol=2e-3)
+
+
+def test_atst_droppath_matches_reference_golden():
+    g = util.gold("atst.npz")
+    c = util.CASES["tiny2dp"]
+    keep = [1.0 - x for x in torch.linspace(0, c["drop_path"], c["depth"]).tolist()]
+    dp_t, dp_s = util.dp_scales_from_rand(g["tiny2dp/rand"], c["depth"], keep)
+    to_cuda = lambda groups: [[None if b is None else (b[0].cuda(), b[1].cuda()) for b in blocks] for blocks in groups]
+    m, c, loss, _, _ = run_case("tiny2dp", dp=(to_cuda(dp_t), to_cuda(dp_s)))
+    assert rel(m._rt.last_outputs[0], g["tiny2dp/student_out"]) < 1e-3
+    np.testing.assert_allclose(loss.item(), g["tiny2dp/loss"], rtol=1e-3)
+    for name, p in m.student.named_parameters():
+        key = "tiny2dp/grad/" + name
+        if key + "/idx" in g.files:
+            util.check_summary(p.grad.cpu().numpy(), g, key, rtol=2e-2, atol=2e-2)
+
+
+def test_ema_matches_reference_golden():
+    g = util.gold("atst.npz")
+    m, c = build_cuda_model("tiny2")
+    m.update_teacher(0.99)
+    for name, p in m.teacher.named_parameters():
+        util.check_summary(p.detach().cpu().numpy(), g, "tiny2/ema/" + name, rtol=1e-6, atol=1e-7)
+
+
+def test_three_training_steps_follow_the_oracle():
+    """Lightning-surface loop (schedule -> step -> backward -> AdamW -> EMA) against the oracle doing the
+    same with its own restated HF AdamW; drop path off.  Loss trajectory within 1e-3 relative."""
+    from audiossl_b200.methods.atst.model import ATSTLightningModule
+    from oracle import atst_oracle as O
+    torch.manual_seed(0)
+    lm = ATSTLightningModule(arch="small", learning_rate=5e-4, warmup_steps=2, max_steps=10, ema=0.99,
+                             drop_path_rate=0.0)
+    util.load_det(lm.model.student)
+    util.load_det(lm.model.teacher)
+    lm.cuda().train()
+    opt = lm.configure_optimizers()[0]
+    lm.trainer.optimizers = [opt]
+    ref = O.OracleATST("small")
+    util.load_det(ref)
+    ref.train()
+    reg, noreg = O.param_groups(ref.student)
+    sp = dict(ref.student.named_parameters())
+    state = {n: (torch.zeros_like(p), torch.zeros_like(p)) for n, p in sp.items()}
+    crops, lengths = util.make_inputs("loop", 4, [101, 101], [[101, 90, 101, 50], [101, 101, 70, 101]])
+    for step in range(3):
+        lm.global_step = step
+        loss = lm.training_step(((([c.cuda() for c in crops]), [l.cuda() for l in lengths]), None), step)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        lm.on_train_batch_end(None, None, step)
+        # oracle
+        for p in ref.student.parameters():
+            p.grad = None
+        rl, _, _ = ref(crops, lengths)
+        rl.backward()
+        lr, wd = lm.mylr_scheduler[step], lm.wd_scheduler[step]
+        for n, p in sp.items():
+            if p.grad is None:
+                continue
+            O.hf_adamw_step(p.data, p.grad, state[n][0], state[n][1], step + 1, lr, wd if n in reg else 0.0)
+        ref.update_teacher(lm.ema_scheduler[step])
+        np.testing.assert_allclose(loss.item(), rl.item(), rtol=1e-3)
+    w = lm.model.teacher.encoder.blocks[3].mlp.fc1.weight.detach().cpu()
+    assert rel(w, ref.teacher.encoder.blocks[3].mlp.fc1.weight.detach()) < 1e-3
+
+
+def test_too_long_clip_is_rejected():
+    from audiossl_b200.models.atst import ATST
+    m = ATST(arch=dict(embed_dim=128, depth=1, num_heads=2)).cuda()
+    x = [torch.zeros(2, 1, 64, 1101, device="cuda")] * 2
+    with pytest.raises(ValueError):
+        m(x, [torch.full((2,), 1101, device="cuda")] * 2)
