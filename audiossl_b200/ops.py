@@ -20,8 +20,9 @@ def reset_stats():
 
 
 class _GemmTimer:
-    def __init__(self, flops):
+    def __init__(self, flops, tag=""):
         self.flops = flops
+        self.tag = tag
         STATS["launches"] += 1
         STATS["gemm_launches"] += 1
         STATS["gemm_flops"] += flops
@@ -33,7 +34,7 @@ class _GemmTimer:
     def done(self):
         if self.ev is not None:
             self.ev[1].record()
-            STATS["gemm_events"].append((self.ev[0], self.ev[1], self.flops))
+            STATS["gemm_events"].append((self.ev[0], self.ev[1], self.flops, self.tag))
 
 
 def _count(n):
@@ -70,7 +71,7 @@ def gemm_nt(A, B, bias=None, epi=EPI_STORE, resid=None, aux=None, rowscale=None,
     assert B.shape[1] == K
     if out is None:
         out = torch.empty((M, N), device=A.device, dtype=torch.float32)
-    _t = _GemmTimer(2.0 * M * N * K)
+    _t = _GemmTimer(2.0 * M * N * K, "nt %dx%dx%d e%d" % (M, N, K, epi))
     check(_lib.lib().atst_gemm_nt(ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(out), out.stride(0), M, N, K,
                                   ptr(bias), epi, ptr(resid), resid.stride(0) if resid is not None else 0,
                                   ptr(aux), aux.stride(0) if aux is not None else 0, ptr(rowscale), rows_per_seq,
@@ -86,7 +87,7 @@ def gemm_nn(A, W, epi=EPI_STORE, aux=None, rowscale=None, rows_per_seq=1, round_
     assert W.shape[0] == K
     if out is None:
         out = torch.empty((M, N), device=A.device, dtype=torch.float32)
-    _t = _GemmTimer(2.0 * M * N * K)
+    _t = _GemmTimer(2.0 * M * N * K, "nn %dx%dx%d e%d" % (M, N, K, epi))
     check(_lib.lib().atst_gemm_nn(ptr(A), A.stride(0), ptr(W), W.stride(0), ptr(out), out.stride(0), M, N, K, epi,
                                   ptr(aux), aux.stride(0) if aux is not None else 0, ptr(rowscale), rows_per_seq,
                                   1 if round_out else 0, _lib.stream()), "atst_gemm_nn")
@@ -99,7 +100,7 @@ def gemm_tn_acc(A, B, out):
     T, M = A.shape
     N = B.shape[1]
     assert B.shape[0] == T and tuple(out.shape) == (M, N)
-    _t = _GemmTimer(2.0 * M * N * T)
+    _t = _GemmTimer(2.0 * M * N * T, "tn %dx%dx%d" % (M, N, T))
     check(_lib.lib().atst_gemm_tn(ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(out), out.stride(0), M, N, T,
                                   _lib.stream()), "atst_gemm_tn")
     _t.done()

@@ -114,13 +114,36 @@ def cpu_reference_step_fn(batch, threads=None):
     return step
 
 
+def pick_cpu_threads():
+    """a big host (128+ hardware threads) is slower with every thread on these small per-clip GEMMs/FFTs:
+    probe a forward pass at a few thread counts and keep the fastest."""
+    import torch
+    from oracle import atst_oracle as O
+    cores = os.cpu_count() or 1
+    cands = sorted({c for c in (8, 16, 32, 64, cores) if c <= cores})
+    enc = O.OracleAST(768, 2, 12)
+    x = torch.randn(4, 1, 64, 1001)
+    ln = torch.full((4,), 1001, dtype=torch.int64)
+    best, best_t = cands[0], 1e30
+    for c in cands:
+        torch.set_num_threads(c)
+        with torch.no_grad():
+            enc(x, ln)
+            t0 = time.perf_counter()
+            enc(x, ln)
+            dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+    return best
+
+
 def run_reference(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     batch = 4
-    cores = os.cpu_count() or 1
+    cores = pick_cpu_threads()
     step = cpu_reference_step_fn(batch, cores)
     for _ in range(max(args.warmup, 1)):
         step()
@@ -209,6 +232,11 @@ def run_ours(args):
 
     for i in range(args.warmup):
         step(i, False)
+    if args.profile:  # short run for ncu: one more step, nothing else
+        torch.cuda.synchronize()
+        step(args.warmup, False)
+        torch.cuda.synchronize()
+        return
     sampler = ClockSampler(local)
     sampler.start()
     ops.reset_stats()
@@ -225,9 +253,19 @@ def run_ours(args):
     step(args.warmup + 2 * args.steps, False)
     torch.cuda.synchronize()
     ops.STATS["time_gemms"] = False
-    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in ops.STATS["gemm_events"])
-    gemm_fl = sum(f for _, _, f in ops.STATS["gemm_events"])
+    gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in ops.STATS["gemm_events"])
+    gemm_fl = sum(f for _, _, f, _ in ops.STATS["gemm_events"])
     n_gemm = len(ops.STATS["gemm_events"])
+    if rank == 0 and args.breakdown:
+        agg = {}
+        for a, b2, f, tag in ops.STATS["gemm_events"]:
+            e = agg.setdefault(tag, [0, 0.0, 0.0])
+            e[0] += 1
+            e[1] += a.elapsed_time(b2)
+            e[2] += f
+        with open(args.breakdown, "w") as fh:
+            for tag, (cnt, t_ms, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                fh.write("%-28s n=%3d  %8.3f ms  %7.1f TFLOP/s\n" % (tag, cnt, t_ms, fl / t_ms / 1e9))
 
     if rank != 0:
         if world > 1:
@@ -260,7 +298,7 @@ def run_ours(args):
                      "model_flops_utilisation_of_step": STEP_GFLOP_PER_CLIP * 1e9 * B / (ms_step / 1e3) / 1e12 / pk["tflops"]},
     }
     if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+        cores = pick_cpu_threads()
         cstep = cpu_reference_step_fn(4, cores)
         cstep()
         t0 = time.perf_counter()
@@ -285,8 +323,10 @@ if __name__ == "__main__":
     ap.add_argument("--batch", type=int, default=256, help="clips per GPU")
     ap.add_argument("--arch", default="base")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="warm-up + one step only (for ncu captures)")
+    ap.add_argument("--breakdown", default="", help="write a per-GEMM-shape timing table to this file")
     a = ap.parse_args()
-    if a.warmup < 3 and a.impl == "ours":
+    if a.warmup < 3 and a.impl == "ours" and not a.profile:
         a.warmup = 3
     if a.impl == "reference":
         run_reference(a)

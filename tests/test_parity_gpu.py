@@ -120,8 +120,7 @@ def build_cuda_model(case):
     c = util.CASES[case]
     m = ATST(arch=dict(embed_dim=c["dim"], depth=c["depth"], num_heads=c["heads"]), ncrops=c["ncrops"],
              drop_path_rate=c.get("drop_path", 0.0))
-    util.load_det(m.student)
-    util.load_det(m.teacher)
+    util.load_det(m)
     m.cuda().train()
     return m, c
 
@@ -195,8 +194,7 @@ def test_three_training_steps_follow_the_oracle():
     torch.manual_seed(0)
     lm = ATSTLightningModule(arch="small", learning_rate=5e-4, warmup_steps=2, max_steps=10, ema=0.99,
                              drop_path_rate=0.0)
-    util.load_det(lm.model.student)
-    util.load_det(lm.model.teacher)
+    util.load_det(lm.model)
     lm.cuda().train()
     opt = lm.configure_optimizers()[0]
     lm.trainer.optimizers = [opt]

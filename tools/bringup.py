@@ -315,7 +315,51 @@ def sec_tokens():
                                                      rel_err(dcls, d3[:, 0].sum(0))))
 
 
-SECTIONS = {"mel": sec_mel, "gemm_nt": sec_gemm_nt, "gemm_mn": sec_gemm_mn, "ln": sec_ln, "attn": sec_attn,
+def sec_gemm_perf():
+    """isolated throughput of the three GEMM flavours at BASELINE config-2 sizes"""
+    import torch
+    from audiossl_b200 import ops
+    M = 128512
+
+    def tm(fn, flops, name):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(4):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 4
+        print("%-34s %8.3f ms  %7.1f TFLOP/s" % (name, ms, flops / ms / 1e9), flush=True)
+
+    for (N, K) in [(2304, 768), (768, 768), (3072, 768), (768, 3072)]:
+        A = torch.randn(M, K, device="cuda")
+        W = torch.randn(N, K, device="cuda")
+        C = torch.empty(M, N, device="cuda")
+        tm(lambda: ops.gemm_nt(A, W, out=C), 2.0 * M * N * K, "nt  M x %d x %d" % (N, K))
+        bias = torch.randn(N, device="cuda")
+        aux = torch.empty(M, N, device="cuda")
+        if N == 3072:
+            tm(lambda: ops.gemm_nt(A, W, bias=bias, epi=ops.EPI_GELU, aux=aux, round_out=True, out=C), 2.0 * M * N * K,
+               "nt+gelu M x %d x %d" % (N, K))
+        if N == 768:
+            tm(lambda: ops.gemm_nt(A, W, bias=bias, epi=ops.EPI_RESID, resid=aux, out=C), 2.0 * M * N * K,
+               "nt+resid M x %d x %d" % (N, K))
+        # dgrad: dX[M,K] = dY[M,N] @ W[N,K]
+        dX = torch.empty(M, K, device="cuda")
+        tm(lambda: ops.gemm_nn(C, W, out=dX), 2.0 * M * N * K, "nn  M x %d (K=%d)" % (K, N))
+        if K == 3072:
+            tm(lambda: ops.gemm_nn(C, W, epi=ops.EPI_DGELU, aux=A, round_out=True, out=dX), 2.0 * M * N * K,
+               "nn+dgelu M x %d (K=%d)" % (K, N))
+        # wgrad: dW[N,K] += dY[M,N]^T @ X[M,K]
+        dW = torch.zeros(N, K, device="cuda")
+        tm(lambda: ops.gemm_tn_acc(C, A, dW), 2.0 * M * N * K, "tn  %d x %d (T=M)" % (N, K))
+        del A, W, C, aux, dX, dW
+
+
+SECTIONS = {"gemm_perf": sec_gemm_perf, "mel": sec_mel, "gemm_nt": sec_gemm_nt, "gemm_mn": sec_gemm_mn, "ln": sec_ln, "attn": sec_attn,
             "bn": sec_bn, "loss": sec_loss, "optim": sec_optim, "tokens": sec_tokens}
 
 if __name__ == "__main__":
