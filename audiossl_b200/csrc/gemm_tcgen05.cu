@@ -39,11 +39,30 @@ struct GemmCfg {
   static constexpr int kTmemCols = 2 * BLOCK_N;  // 512 or 256: power of two
 };
 
-__device__ __forceinline__ float gelu_exact(float u) { return 0.5f * u * (1.0f + erff(u * 0.70710678118654752f)); }
+// erf by Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, far below the TF32 operand rounding of the next GEMM):
+// one MUFU.RCP + one MUFU.EX2 + 7 FMA instead of libdevice erff's ~25 instructions.  The exp(-u^2/2) factor is
+// shared between the cdf and the pdf, so gelu'(u) costs no second exponential.
+struct GeluParts { float cdf, pdf; };
+__device__ __forceinline__ GeluParts gelu_parts(float u) {
+  const float x = u * 0.70710678118654752f;
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float e = __expf(-ax * ax);            // exp(-u^2 / 2)
+  const float erf_abs = fmaf(-poly, e, 1.0f);  // erf(|x|)
+  GeluParts g;
+  g.cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+  g.pdf = 0.3989422804014327f * e;
+  return g;
+}
+__device__ __forceinline__ float gelu_exact(float u) { return u * gelu_parts(u).cdf; }
 __device__ __forceinline__ float gelu_grad(float u) {
-  const float cdf = 0.5f * (1.0f + erff(u * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * u * u);
-  return cdf + u * pdf;
+  const GeluParts g = gelu_parts(u);
+  return fmaf(u, g.pdf, g.cdf);
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
@@ -183,8 +202,24 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(ew * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
+      // side inputs (residual / saved pre-activation) are fetched one 32-column chunk ahead of their use so
+      // their DRAM latency overlaps the TMEM load, the smem transpose and the math of the previous chunk
+      const float* side_ptr = (p.epi == EPI_RESID) ? p.resid : ((p.epi == EPI_DGELU) ? p.aux : nullptr);
+      const int side_ld = (p.epi == EPI_RESID) ? p.ldr : p.ldaux;
+      const int gm_base = m0 + ew * 32 + (lane >> 3);
+      const int gn_lane = n0 + (lane & 7) * 4;
+      auto load_side = [&](int c, float4 (&side)[8]) {
+        if (side_ptr == nullptr) return;
+        const int gn = gn_lane + c * 32;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int gm = gm_base + 4 * i;
+          side[i] = (gm < p.M && gn < p.N)
+                        ? __ldg(reinterpret_cast<const float4*>(side_ptr + static_cast<size_t>(gm) * side_ld + gn))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      auto process = [&](int c, const float4 (&side)[8]) {
         uint32_t r[32];
         tmem_ld_32x32(taddr + c * 32, r);
         tmem_ld_wait();
@@ -194,7 +229,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
-        if (n0 + c * 32 >= p.N || empty_split) continue;
+        if (n0 + c * 32 >= p.N || empty_split) return;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
@@ -202,9 +237,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           *reinterpret_cast<float4*>(&stg[lane * kStagePad + 4 * j]) = v;
         }
         __syncwarp();
-        const int gn = n0 + c * 32 + (lane & 7) * 4;
+        const int gn = gn_lane + c * 32;
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias != nullptr && gn < p.N) bias4 = *reinterpret_cast<const float4*>(p.bias + gn);
+        if (p.bias != nullptr && gn < p.N) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + gn));
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int row = 4 * i + (lane >> 3);
@@ -214,21 +249,19 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
           float* cptr = p.C + static_cast<size_t>(gm) * p.ldc + gn;
           switch (p.epi) {
-            case EPI_STORE:
-              break;
             case EPI_GELU: {  // aux <- pre-activation, C <- gelu
               *reinterpret_cast<float4*>(p.aux + static_cast<size_t>(gm) * p.ldaux + gn) = v;
               v.x = gelu_exact(v.x); v.y = gelu_exact(v.y); v.z = gelu_exact(v.z); v.w = gelu_exact(v.w);
               break;
             }
             case EPI_DGELU: {  // C <- acc * gelu'(aux)
-              const float4 u = *reinterpret_cast<const float4*>(p.aux + static_cast<size_t>(gm) * p.ldaux + gn);
+              const float4 u = side[i];
               v.x *= gelu_grad(u.x); v.y *= gelu_grad(u.y); v.z *= gelu_grad(u.z); v.w *= gelu_grad(u.w);
               break;
             }
             case EPI_RESID: {  // C <- resid + rowscale[seq] * acc
               const float s = p.rowscale ? p.rowscale[gm / p.rows_per_seq] : 1.0f;
-              const float4 x = *reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(gm) * p.ldr + gn);
+              const float4 x = side[i];
               v.x = fmaf(s, v.x, x.x); v.y = fmaf(s, v.y, x.y); v.z = fmaf(s, v.z, x.z); v.w = fmaf(s, v.w, x.w);
               break;
             }
@@ -253,6 +286,15 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         __syncwarp();
+      };
+      float4 side_a[8], side_b[8];
+      load_side(0, side_a);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; c += 2) {
+        load_side(c + 1, side_b);
+        process(c, side_a);
+        if (c + 2 < BLOCK_N / 32) load_side(c + 2, side_a);
+        process(c + 1, side_b);
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;

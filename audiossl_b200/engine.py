@@ -58,6 +58,7 @@ class EncoderEngine:
         self.D, self.depth, self.H = embed_dim, depth, num_heads
         self.use_cls, self.norm_name, self.px = use_cls, norm_name, prefix
         self.patch_w, self.max_frames = patch_w, max_frames
+        self.debug = None  # bring-up aid: list collecting (name, layer, tensor clone) during backward
 
     # ------------------------------------------------------------------ forward
     def forward(self, fp, ws, mel, lengths, dp=None, save=True, tag="s", mask=None, mask_input=True):
@@ -149,6 +150,8 @@ class EncoderEngine:
         dx = dxa
         other = dxb
         dp = ctx["dp"]
+        dbg = (lambda name, i, t_: self.debug.append((name, i, t_.clone()))) if self.debug is not None else (lambda *a: None)
+        dbg("dx_out", self.depth, dx)
         for i in reversed(range(self.depth)):
             b = "%sblocks.%d." % (px, i)
             L = ctx["layers"][i]
@@ -161,11 +164,14 @@ class EncoderEngine:
             ops.gemm_tn_acc(dys, L["g"], fp.g(b + "mlp.fc2.weight"))
             du = ops.gemm_nn(dys, fp.c(b + "mlp.fc2.weight"), epi=ops.EPI_DGELU, aux=L["u"], round_out=True,
                              out=t("du", (M, 4 * D)))
+            dbg("du", i, du)
             ops.colsum_acc(du, fp.g(b + "mlp.fc1.bias"))
             ops.gemm_tn_acc(du, L["h2"], fp.g(b + "mlp.fc1.weight"))
             dh2 = ops.gemm_nn(du, fp.c(b + "mlp.fc1.weight"), out=t("dh", (M, D)))
             dx1 = ops.layernorm_bwd(dh2, L["x1"], L["mean2"], L["rstd2"], fp.p(b + "norm2.weight"),
                                     fp.g(b + "norm2.weight"), fp.g(b + "norm2.bias"), M, D, dres=dx, dx=other)
+            dbg("dh2", i, dh2)
+            dbg("dx1", i, dx1)
             # ---- attention branch: x1 = x + s * (o Wp^T + bp)
             dys = self._scaled(dx1, s_attn, N, t("dys", (M, D)))
             ops.colsum_acc(dys, fp.g(b + "attn.proj.bias"))
@@ -173,10 +179,13 @@ class EncoderEngine:
             d_o = ops.gemm_nn(dys, fp.c(b + "attn.proj.weight"), round_out=True, out=t("d_o", (M, D)))
             dqkv = ops.attention_bwd(L["qkv"], L["o"], d_o, L["lse"], S, N, H, ctx["key_len"],
                                      dqkv=t("dqkv", (M, 3 * D)), delta_ws=t("delta", (S, H, N)))
+            dbg("d_o", i, d_o)
+            dbg("dqkv", i, dqkv)
             ops.gemm_tn_acc(dqkv, L["h"], fp.g(b + "attn.qkv.weight"))
             dh = ops.gemm_nn(dqkv, fp.c(b + "attn.qkv.weight"), out=t("dh", (M, D)))
             ops.layernorm_bwd(dh, L["x"], L["mean1"], L["rstd1"], fp.p(b + "norm1.weight"), fp.g(b + "norm1.weight"),
                               fp.g(b + "norm1.bias"), M, D, dres=dx1, dx=dx)
+            dbg("dx_in", i, dx)
             # dx now holds the gradient wrt the block input; `other` is free again
         dpe = t("dpe", (S * P, D))
         ops.tokens_bwd(dx, dpe, fp.g(px + "pos_embed"), fp.g(px + "cls_token") if self.use_cls else None, S, P, D,
