@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "gemm.h"
 #include "ops.h"
+#include <string.h>
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 using namespace atst;
@@ -10,6 +11,12 @@ using namespace atst;
 extern "C" {
 
 int atst_version(void) { return 100; }
+
+int atst_set_option(const char* name, int value) {
+  if (name != nullptr && strcmp(name, "gemm_l2_prefetch") == 0) { gemm_set_l2_prefetch(value); return ATST_OK; }
+  atst_set_error("atst_set_option: unknown option '%s'", name ? name : "(null)");
+  return ATST_ERR_ARG;
+}
 
 int atst_init(void) {
   int dev = 0;

@@ -29,6 +29,7 @@ struct GemmParams {
   int epi = EPI_STORE;
   int round_out = 0;                // round C to tf32 (it feeds another GEMM)
   int splits = 0;                   // TN only: split-K factor (0 = auto)
+  int l2_prefetch = 1;              // producer prefetches streaming operand tiles into L2 ahead of the smem ring
   // TN (token-major operands) shared-memory descriptor fields; 0 = defaults
   uint32_t mn_lbo = 0, mn_sbo = 0, mn_kstep = 0, mn_layout = 0;
   int mn_tma_swizzle = 0;
@@ -40,5 +41,7 @@ int gemm_nt(const float* A, int lda, const float* B, int ldb, GemmParams p, cuda
 int gemm_nn(const float* A, int lda, const float* B, int ldb, GemmParams p, cudaStream_t stream);
 // C[M,N] += A[T,M]^T . B[T,N]; contraction over the T rows (tokens); p.K ignored
 int gemm_tn(const float* A, int lda, const float* B, int ldb, int T, GemmParams p, cudaStream_t stream);
+
+void gemm_set_l2_prefetch(int on);
 
 }  // namespace atst

@@ -115,17 +115,42 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
+    // A second cursor runs kPrefetchDist k-blocks ahead of the load cursor (across tile boundaries) and pulls the
+    // streaming operand tiles into L2, so a smem slot refill sees L2-hit latency instead of HBM latency: with
+    // 4 x 48 KB slots only ~1500 cycles of latency are covered by the ring itself.
     if (lane == 0) {
+      constexpr int kPrefetchDist = 12;
+      const int tiles_mn = m_tiles * n_tiles;
+      auto tile_span = [&](int tile, int& m0, int& n0, int& kb0, int& kb1) {
+        const int split = tile / tiles_mn;
+        const int rem = tile - split * tiles_mn;
+        m0 = (rem / n_tiles) * kBlockM;
+        n0 = (rem % n_tiles) * BLOCK_N;
+        kb0 = split * kb_per_split;
+        kb1 = min(kb0 + kb_per_split, kb_total);
+      };
+      int pf_tile = blockIdx.x, pf_m0 = 0, pf_n0 = 0, pf_kb = 0, pf_kb1 = 0;
+      if (pf_tile < total_tiles) tile_span(pf_tile, pf_m0, pf_n0, pf_kb, pf_kb1);
+      auto prefetch_step = [&]() {
+        while (pf_tile < total_tiles && pf_kb >= pf_kb1) {
+          pf_tile += gridDim.x;
+          if (pf_tile < total_tiles) tile_span(pf_tile, pf_m0, pf_n0, pf_kb, pf_kb1);
+        }
+        if (pf_tile >= total_tiles) return;
+        if (A_MN) tma_prefetch_3d(&tmA, 0, pf_kb * kBlockK, pf_m0 / 32);
+        else      tma_prefetch_2d(&tmA, pf_kb * kBlockK, pf_m0);
+        if (A_MN && B_MN) tma_prefetch_3d(&tmB, 0, pf_kb * kBlockK, pf_n0 / 32);  // wgrad: both operands stream
+        ++pf_kb;
+      };
+      if (p.l2_prefetch)
+        for (int i = 0; i < kPrefetchDist; ++i) prefetch_step();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int split = tile / (m_tiles * n_tiles);
-        const int rem = tile - split * (m_tiles * n_tiles);
-        const int m0 = (rem / n_tiles) * kBlockM;
-        const int n0 = (rem % n_tiles) * BLOCK_N;
-        const int kb0 = split * kb_per_split;
-        const int kb1 = min(kb0 + kb_per_split, kb_total);
+        int m0, n0, kb0, kb1;
+        tile_span(tile, m0, n0, kb0, kb1);
         for (int kb = kb0; kb < kb1; ++kb) {
+          if (p.l2_prefetch) prefetch_step();
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           void* sa = smem_a + stage * Cfg::kABytes;
@@ -359,6 +384,9 @@ static int make_map_mnmajor(CUtensorMap* map, const float* ptr, int tokens, int 
   return ATST_OK;
 }
 
+static int g_l2_prefetch = 1;
+void gemm_set_l2_prefetch(int on) { g_l2_prefetch = on; }
+
 static int g_num_sms = 0;
 static int num_sms() {
   if (g_num_sms == 0) {
@@ -384,7 +412,9 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
   const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int tiles = m_tiles * n_tiles * (p.splits > 0 ? p.splits : 1);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kfn<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  GemmParams q = p;
+  q.l2_prefetch = g_l2_prefetch;
+  kfn<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, q);
   return atst_check_launch("gemm_tf32_kernel");
 }
 

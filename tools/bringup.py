@@ -334,6 +334,16 @@ def sec_gemm_perf():
         ms = e0.elapsed_time(e1) / 4
         print("%-34s %8.3f ms  %7.1f TFLOP/s" % (name, ms, flops / ms / 1e9), flush=True)
 
+    from audiossl_b200 import _lib
+    for pf in (0, 1):
+        _lib.lib().atst_set_option(b"gemm_l2_prefetch", pf)
+        A = torch.randn(M, 768, device="cuda")
+        W = torch.randn(2304, 768, device="cuda")
+        C = torch.empty(M, 2304, device="cuda")
+        tm(lambda: ops.gemm_nt(A, W, out=C), 2.0 * M * 2304 * 768, "l2_prefetch=%d nt M x 2304 x 768" % pf)
+        dW = torch.zeros(2304, 768, device="cuda")
+        tm(lambda: ops.gemm_tn_acc(C, A, dW), 2.0 * M * 2304 * 768, "l2_prefetch=%d tn 2304 x 768" % pf)
+        del A, W, C, dW
     for (N, K) in [(2304, 768), (768, 768), (3072, 768), (768, 3072)]:
         A = torch.randn(M, K, device="cuda")
         W = torch.randn(N, K, device="cuda")
