@@ -45,7 +45,8 @@ int atst_gemm_nt(const float* A, int lda, const float* B, int ldb, float* C, int
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = bias; p.epi = epi; p.resid = resid; p.ldr = ldr;
   p.aux = aux; p.ldaux = ldaux; p.rowscale = rowscale; p.rows_per_seq = rows_per_seq > 0 ? rows_per_seq : 1;
   p.round_out = round_out;
-  ATST_REQUIRE(epi >= EPI_STORE && epi <= EPI_RELU, "atst_gemm_nt: bad epilogue %d", epi);
+  ATST_REQUIRE((epi >= EPI_STORE && epi <= EPI_RELU) || epi == EPI_DBG_NOSTORE || epi == EPI_DBG_NOLOAD,
+               "atst_gemm_nt: bad epilogue %d", epi);
   ATST_REQUIRE(!(epi == EPI_RESID && resid == nullptr), "atst_gemm_nt: EPI_RESID needs resid");
   ATST_REQUIRE(!((epi == EPI_GELU || epi == EPI_DGELU) && aux == nullptr), "atst_gemm_nt: GELU epilogues need aux");
   return gemm_nt(A, lda, B, ldb, p, ST(stream));
@@ -149,6 +150,8 @@ int atst_adamw_step(float* p, const float* g, float* m, float* v, long long n, i
                     float beta1, float beta2, float eps, float grad_scale, void* stream) {
   return adamw_step(p, g, m, v, n, step, lr, wd, beta1, beta2, eps, grad_scale, ST(stream));
 }
+int atst_gelu_forward(const float* u, float* g, long long n, void* stream) { return gelu_forward(u, g, n, ST(stream)); }
+int atst_gelu_backward(float* d, const float* u, long long n, void* stream) { return gelu_backward(d, u, n, ST(stream)); }
 int atst_round_tf32(const float* src, float* dst, long long n, void* stream) {
   return round_tf32_copy(src, dst, n, ST(stream));
 }

@@ -219,6 +219,50 @@ __global__ void bn_relu_bwd_apply_kernel(const float* __restrict__ dY, const flo
   }
 }
 
+// un-fused GELU pair (used when the GEMM epilogue would be the bottleneck): same single-exp formulation as the
+// fused epilogues in gemm_tcgen05.cu
+__device__ __forceinline__ void gelu_cdf_pdf(float u, float& cdf, float& pdf) {
+  const float x = u * 0.70710678118654752f;
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float e = __expf(-ax * ax);
+  cdf = 0.5f * (1.0f + copysignf(fmaf(-poly, e, 1.0f), x));
+  pdf = 0.3989422804014327f * e;
+}
+// g = tf32(gelu(u))
+__global__ void gelu_fwd_kernel(const float* __restrict__ u, float* __restrict__ g, long long n4) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(u) + i);
+    float c, p;
+    float4 o;
+    gelu_cdf_pdf(v.x, c, p); o.x = round_tf32(v.x * c);
+    gelu_cdf_pdf(v.y, c, p); o.y = round_tf32(v.y * c);
+    gelu_cdf_pdf(v.z, c, p); o.z = round_tf32(v.z * c);
+    gelu_cdf_pdf(v.w, c, p); o.w = round_tf32(v.w * c);
+    reinterpret_cast<float4*>(g)[i] = o;
+  }
+}
+// d = tf32(d * gelu'(u)) in place
+__global__ void gelu_bwd_kernel(float* __restrict__ d, const float* __restrict__ u, long long n4) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(u) + i);
+    float4 o = reinterpret_cast<float4*>(d)[i];
+    float c, p;
+    gelu_cdf_pdf(v.x, c, p); o.x = round_tf32(o.x * fmaf(v.x, p, c));
+    gelu_cdf_pdf(v.y, c, p); o.y = round_tf32(o.y * fmaf(v.y, p, c));
+    gelu_cdf_pdf(v.z, c, p); o.z = round_tf32(o.z * fmaf(v.z, p, c));
+    gelu_cdf_pdf(v.w, c, p); o.w = round_tf32(o.w * fmaf(v.w, p, c));
+    reinterpret_cast<float4*>(d)[i] = o;
+  }
+}
+
 __global__ void round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n4) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -302,6 +346,16 @@ int bn_relu_backward_apply(const float* dY, const float* X, const float* mean, c
   bn_relu_bwd_apply_kernel<<<grid_for(total), 256, 0, st>>>(dY, X, mean, rstd, gamma, beta, s1, s2, 1.0f / count, dX,
                                                            total, cols);
   return atst_check_launch("bn_relu_bwd_apply_kernel");
+}
+int gelu_forward(const float* u, float* g, long long n, cudaStream_t st) {
+  ATST_REQUIRE(n % 4 == 0, "gelu_forward: n %% 4 != 0");
+  gelu_fwd_kernel<<<grid_for(n / 4, 256, 148 * 32), 256, 0, st>>>(u, g, n / 4);
+  return atst_check_launch("gelu_fwd_kernel");
+}
+int gelu_backward(float* d, const float* u, long long n, cudaStream_t st) {
+  ATST_REQUIRE(n % 4 == 0, "gelu_backward: n %% 4 != 0");
+  gelu_bwd_kernel<<<grid_for(n / 4, 256, 148 * 32), 256, 0, st>>>(d, u, n / 4);
+  return atst_check_launch("gelu_bwd_kernel");
 }
 int round_tf32_copy(const float* src, float* dst, long long n, cudaStream_t st) {
   ATST_REQUIRE(n % 4 == 0, "round_tf32_copy: n %% 4 != 0");

@@ -13,6 +13,8 @@ enum GemmEpilogue : int {
   EPI_SCALE = 4,   // C = rowscale[row / rows_per_seq] * acc
   EPI_RELU = 5,    // C = max(acc + bias, 0)
   EPI_ATOMIC = 6,  // C += acc   (split-K partial sums, red.global.add)
+  EPI_DBG_NOSTORE = 8,  // profiling aid: full epilogue without the global stores
+  EPI_DBG_NOLOAD = 9,   // profiling aid: epilogue without the TMEM loads (stores zeros)
 };
 
 struct GemmParams {

@@ -246,8 +246,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       };
       auto process = [&](int c, const float4 (&side)[8]) {
         uint32_t r[32];
-        tmem_ld_32x32(taddr + c * 32, r);
-        tmem_ld_wait();
+        if (p.epi != EPI_DBG_NOLOAD) {
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
         if (c == BLOCK_N / 32 - 1) {
           // accumulator fully read: hand the TMEM stage back to the MMA warp before the global stores
           tc_fence_before();
@@ -306,7 +311,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           if (p.epi == EPI_ATOMIC) {
             atomicAdd(cptr + 0, v.x); atomicAdd(cptr + 1, v.y); atomicAdd(cptr + 2, v.z); atomicAdd(cptr + 3, v.w);
-          } else {
+          } else if (p.epi != EPI_DBG_NOSTORE || v.x == 123.456f) {
             *reinterpret_cast<float4*>(cptr) = v;
           }
         }
@@ -384,7 +389,7 @@ static int make_map_mnmajor(CUtensorMap* map, const float* ptr, int tokens, int 
   return ATST_OK;
 }
 
-static int g_l2_prefetch = 1;
+static int g_l2_prefetch = 0;  // measured: no gain (the ring is L2-bandwidth, not latency, limited)
 void gemm_set_l2_prefetch(int on) { g_l2_prefetch = on; }
 
 static int g_num_sms = 0;

@@ -12,7 +12,12 @@ Reference semantics (file:line under /root/reference):
 """
 import torch
 
+import os
+
 from . import ops
+
+# GELU / GELU' inside the GEMM epilogue (1) or as separate elementwise passes (0); see DESIGN.md "GEMM epilogues"
+FUSE_GELU = os.environ.get("ATST_FUSE_GELU", "0") == "1"
 
 
 class Workspace:
@@ -104,8 +109,12 @@ class EncoderEngine:
             h2, mean2, rstd2 = self._ln(x1, fp.p(b + "norm2.weight"), fp.p(b + "norm2.bias"), M, lt("h2", (M, D)),
                                         lt("mean2", (M,)), lt("rstd2", (M,)))
             u = lt("u", (M, 4 * D))
-            g = ops.gemm_nt(h2, fp.c(b + "mlp.fc1.weight"), bias=fp.p(b + "mlp.fc1.bias"), epi=ops.EPI_GELU, aux=u,
-                            round_out=True, out=lt("g", (M, 4 * D)))
+            if FUSE_GELU:
+                g = ops.gemm_nt(h2, fp.c(b + "mlp.fc1.weight"), bias=fp.p(b + "mlp.fc1.bias"), epi=ops.EPI_GELU,
+                                aux=u, round_out=True, out=lt("g", (M, 4 * D)))
+            else:
+                ops.gemm_nt(h2, fp.c(b + "mlp.fc1.weight"), bias=fp.p(b + "mlp.fc1.bias"), out=u)
+                g = ops.gelu_fwd(u, lt("g", (M, 4 * D)))
             x2 = ops.gemm_nt(g, fp.c(b + "mlp.fc2.weight"), bias=fp.p(b + "mlp.fc2.bias"), epi=ops.EPI_RESID,
                              resid=x1, rowscale=s_mlp, rows_per_seq=N, out=lt("x2", (M, D)))
             if save:
@@ -162,8 +171,12 @@ class EncoderEngine:
             dys = self._scaled(dx, s_mlp, N, t("dys", (M, D)))
             ops.colsum_acc(dys, fp.g(b + "mlp.fc2.bias"))
             ops.gemm_tn_acc(dys, L["g"], fp.g(b + "mlp.fc2.weight"))
-            du = ops.gemm_nn(dys, fp.c(b + "mlp.fc2.weight"), epi=ops.EPI_DGELU, aux=L["u"], round_out=True,
-                             out=t("du", (M, 4 * D)))
+            if FUSE_GELU:
+                du = ops.gemm_nn(dys, fp.c(b + "mlp.fc2.weight"), epi=ops.EPI_DGELU, aux=L["u"], round_out=True,
+                                 out=t("du", (M, 4 * D)))
+            else:
+                du = ops.gemm_nn(dys, fp.c(b + "mlp.fc2.weight"), out=t("du", (M, 4 * D)))
+                ops.gelu_bwd_(du, L["u"])
             dbg("du", i, du)
             ops.colsum_acc(du, fp.g(b + "mlp.fc1.bias"))
             ops.gemm_tn_acc(du, L["h2"], fp.g(b + "mlp.fc1.weight"))

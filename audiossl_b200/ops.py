@@ -278,6 +278,18 @@ def adamw_step(p, g, m, v, step, lr, wd, beta1=0.9, beta2=0.999, eps=1e-6, grad_
     _count(1)
 
 
+def gelu_fwd(u, out):
+    check(_lib.lib().atst_gelu_forward(ptr(u), ptr(out), u.numel(), _lib.stream()), "atst_gelu_forward")
+    _count(1)
+    return out
+
+
+def gelu_bwd_(d, u):
+    check(_lib.lib().atst_gelu_backward(ptr(d), ptr(u), d.numel(), _lib.stream()), "atst_gelu_backward")
+    _count(1)
+    return d
+
+
 def round_tf32(src, dst=None):
     if dst is None:
         dst = torch.empty_like(src)

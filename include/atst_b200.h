@@ -109,6 +109,10 @@ int atst_ema_update(float* k, const float* q, float m, long long n, void* stream
 int atst_adamw_step(float* p, const float* g, float* m, float* v, long long n, int step, float lr, float wd,
                     float beta1, float beta2, float eps, float grad_scale, void* stream);
 
+/* ---- exact-erf GELU as separate passes (audiossl/modules/transformer.py:78,88): g = gelu(u); d *= gelu'(u) */
+int atst_gelu_forward(const float* u, float* g, long long n, void* stream);
+int atst_gelu_backward(float* d, const float* u, long long n, void* stream);
+
 /* ---- misc */
 int atst_round_tf32(const float* src, float* dst, long long n, void* stream);
 int atst_axpy(float* y, const float* x, float a, long long n, void* stream);

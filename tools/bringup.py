@@ -335,7 +335,17 @@ def sec_gemm_perf():
         print("%-34s %8.3f ms  %7.1f TFLOP/s" % (name, ms, flops / ms / 1e9), flush=True)
 
     from audiossl_b200 import _lib
-    for pf in (0, 1):
+    A = torch.randn(M, 768, device="cuda")
+    W = torch.randn(2304, 768, device="cuda")
+    C = torch.empty(M, 2304, device="cuda")
+    for epi, nm in ((0, "store"), (8, "dbg no-store"), (9, "dbg no-tmem-load")):
+        tm(lambda: ops.gemm_nt(A, W, epi=epi, out=C), 2.0 * M * 2304 * 768, "nt M x 2304 x 768 epi=%s" % nm)
+    u = torch.randn(M, 3072, device="cuda")
+    gg = torch.empty_like(u)
+    tm(lambda: ops.gelu_fwd(u, gg), 1.0, "gelu_fwd elementwise [M,3072]")
+    tm(lambda: ops.gelu_bwd_(gg, u), 1.0, "gelu_bwd elementwise [M,3072]")
+    del A, W, C, u, gg
+    for pf in (0,):
         _lib.lib().atst_set_option(b"gemm_l2_prefetch", pf)
         A = torch.randn(M, 768, device="cuda")
         W = torch.randn(2304, 768, device="cuda")

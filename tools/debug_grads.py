@@ -31,7 +31,10 @@ crops, lengths = util.make_inputs(case, c["B"], c["widths"], c["lens"])
 acts = {}
 enc = ref.student.encoder
 for i, blk in enumerate(enc.blocks):
-    blk.register_forward_hook(lambda mod, inp, out, i=i: (out.retain_grad(), acts.__setitem__(("x_out", i), out)))
+    def hook(mod, inp, out, i=i):
+        out.retain_grad()
+        acts[("x_out", i)] = out
+    blk.register_forward_hook(hook)
 rl, _, _ = ref(crops, lengths)
 rl.backward()
 
