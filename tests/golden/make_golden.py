@@ -150,6 +150,10 @@ def gen_atst():
     # tiny: D=128, depth 2, 2 heads (dh=64 as in every real config); full + ragged lengths
     m = RefATSTLike(128, 2, 2, ncrops=2)
     run_case(m, "tiny2", 3, [101, 101], [[101, 77, 50], [101, 101, 9]], out)
+    # same encoder, 32 clips per crop: BatchNorm / loss statistics over 64 rows (well conditioned: used for the
+    # gradient tolerance of the TF32 CUDA path)
+    mb = RefATSTLike(128, 2, 2, ncrops=2)
+    run_case(mb, "tiny2b32", 32, [101, 101], [[101 - (i * 7) % 60 for i in range(32)], [101 - (i * 11) % 45 for i in range(32)]], out)
     # EMA update pinned on the same module (models/atst/atst.py:29-34 semantics via ATST.update_teacher)
     from audiossl.models.atst.atst import ATST
     with torch.no_grad():

@@ -48,7 +48,7 @@ def build(case):
     return m, c
 
 
-@pytest.mark.parametrize("case", ["tiny2", "tiny4", "small2"])
+@pytest.mark.parametrize("case", ["tiny2", "tiny2b32", "tiny4", "small2"])
 def test_atst_forward_backward_matches_reference(case):
     g = util.gold("atst.npz")
     m, c = build(case)

@@ -27,16 +27,30 @@ def make_inputs(tag, B, widths, lens):
     return crops, lengths
 
 
-def check_summary(arr, g, prefix, rtol, atol):
-    """compare an array with a detfill.summarize() record stored under prefix/* in npz g."""
+def summary_rms(g, prefix, size):
+    return float(np.sqrt(g[prefix + "/sq"] / max(size, 1)))
+
+
+def check_summary(arr, g, prefix, rtol, atol, scale=None):
+    """compare an array with a detfill.summarize() record stored under prefix/* in npz g.
+    atol is relative to `scale` (default: the rms of the golden array itself)."""
     a = np.asarray(arr, np.float32).ravel()
     idx = g[prefix + "/idx"]
-    scale = max(float(np.sqrt(g[prefix + "/sq"] / max(a.size, 1))), 1e-12)  # rms of the golden array
+    if scale is None:
+        scale = max(summary_rms(g, prefix, a.size), 1e-12)
     np.testing.assert_allclose(a[: g[prefix + "/head"].size], g[prefix + "/head"], rtol=rtol, atol=atol * scale,
                                err_msg=prefix + " head")
     np.testing.assert_allclose(a[idx], g[prefix + "/samp"], rtol=rtol, atol=atol * scale, err_msg=prefix + " samp")
     np.testing.assert_allclose(np.abs(a).astype(np.float64).sum(), g[prefix + "/abs"], rtol=max(rtol, 1e-4),
-                               err_msg=prefix + " abs")
+                               atol=atol * scale * a.size, err_msg=prefix + " abs")
+
+
+def sample_rel_err(arr, g, prefix):
+    """relative l2 error on the stored sample of a summarised array (head + strided sample)."""
+    a = np.asarray(arr, np.float64).ravel()
+    mine = np.concatenate([a[: g[prefix + "/head"].size], a[g[prefix + "/idx"]]])
+    ref = np.concatenate([g[prefix + "/head"], g[prefix + "/samp"]]).astype(np.float64)
+    return float(np.linalg.norm(mine - ref) / max(np.linalg.norm(ref), 1e-30)), float(np.linalg.norm(ref))
 
 
 CASES = {
@@ -46,6 +60,8 @@ CASES = {
                   lens=[[101, 90], [101, 101], [41, 33], [41, 41]]),
     "tiny2dp": dict(dim=128, depth=2, heads=2, ncrops=2, B=4, widths=[101, 101],
                     lens=[[101, 101, 60, 101], [101, 80, 101, 101]], drop_path=0.5),
+    "tiny2b32": dict(dim=128, depth=2, heads=2, ncrops=2, B=32, widths=[101, 101],
+                     lens=[[101 - (i * 7) % 60 for i in range(32)], [101 - (i * 11) % 45 for i in range(32)]]),
     "small2": dict(dim=384, depth=12, heads=6, ncrops=2, B=2, widths=[101, 101], lens=[[101, 64], [101, 101]]),
 }
 
