@@ -34,7 +34,7 @@ struct GemmCfg {
   static constexpr int kBBytes = BLOCK_N * kBlockKBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
-  static constexpr int kEpiBytes = 4 * 32 * kStagePad * 4;
+  static constexpr int kEpiBytes = 0;  // epilogue goes TMEM -> registers -> global, no smem staging
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kEpiBytes + 256;
   static constexpr int kTmemCols = 2 * BLOCK_N;  // 512 or 256: power of two
 };
@@ -74,7 +74,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
-  float* smem_epi = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kEpiBytes);
   uint64_t* full_bar = bars;                     // [kStages]
   uint64_t* empty_bar = bars + Cfg::kStages;     // [kStages]
@@ -213,10 +212,16 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
+    // Thread t of epilogue warp ew owns accumulator row 32*ew + t (TMEM lane) and walks its 32-column chunks:
+    // tcgen05.ld -> registers -> fused math -> 256-bit global stores, with the chunk's side input (residual /
+    // saved pre-activation) fetched one chunk ahead by 256-bit loads.  No shared-memory staging: the smem port
+    // is already saturated by the TMA fill + UMMA operand reads (96 + 96 B/cycle against 128 B/cycle), and every
+    // lane still reads/writes whole 32-byte sectors.
     const int ew = warp - 4;  // == warp % 4: TMEM lane quadrant
-    float* stg = smem_epi + ew * 32 * kStagePad;
     int acc = 0;
     uint32_t acc_phase = 0;
+    const float* side_ptr = (p.epi == EPI_RESID) ? p.resid : ((p.epi == EPI_DGELU) ? p.aux : nullptr);
+    const int side_ld = (p.epi == EPI_RESID) ? p.ldr : p.ldaux;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int split = tile / (m_tiles * n_tiles);
       const int rem = tile - split * (m_tiles * n_tiles);
@@ -224,27 +229,25 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int n0 = (rem % n_tiles) * BLOCK_N;
       const int kb0 = split * kb_per_split;
       const bool empty_split = min(kb0 + kb_per_split, kb_total) <= kb0;
+      const int gm = m0 + ew * 32 + lane;
+      const bool row_ok = gm < p.M && !empty_split;
+      const float rs = (p.rowscale != nullptr && row_ok) ? p.rowscale[gm / p.rows_per_seq] : 1.0f;
+      const float* side_row = side_ptr ? side_ptr + static_cast<size_t>(gm) * side_ld : nullptr;
+      float* c_row = p.C + static_cast<size_t>(gm) * p.ldc;
+      float* aux_row = (p.epi == EPI_GELU) ? p.aux + static_cast<size_t>(gm) * p.ldaux : nullptr;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(ew * 32) << 16);
-      // side inputs (residual / saved pre-activation) are fetched one 32-column chunk ahead of their use so
-      // their DRAM latency overlaps the TMEM load, the smem transpose and the math of the previous chunk
-      const float* side_ptr = (p.epi == EPI_RESID) ? p.resid : ((p.epi == EPI_DGELU) ? p.aux : nullptr);
-      const int side_ld = (p.epi == EPI_RESID) ? p.ldr : p.ldaux;
-      const int gm_base = m0 + ew * 32 + (lane >> 3);
-      const int gn_lane = n0 + (lane & 7) * 4;
-      auto load_side = [&](int c, float4 (&side)[8]) {
-        if (side_ptr == nullptr) return;
-        const int gn = gn_lane + c * 32;
+
+      auto load_side = [&](int c, float (&sd)[32]) {
+        const int gn = n0 + c * 32;
+        if (side_row == nullptr || !row_ok || gn >= p.N) return;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int gm = gm_base + 4 * i;
-          side[i] = (gm < p.M && gn < p.N)
-                        ? __ldg(reinterpret_cast<const float4*>(side_ptr + static_cast<size_t>(gm) * side_ld + gn))
-                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < 4; ++j) {
+          if (gn + 8 * j < p.N) ld_global_v8(side_row + gn + 8 * j, &sd[8 * j]);
         }
       };
-      auto process = [&](int c, const float4 (&side)[8]) {
+      auto process = [&](int c, const float (&sd)[32]) {
         uint32_t r[32];
         if (p.epi != EPI_DBG_NOLOAD) {
           tmem_ld_32x32(taddr + c * 32, r);
@@ -259,65 +262,59 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
-        if (n0 + c * 32 >= p.N || empty_split) return;
+        const int gn = n0 + c * 32;
+        if (!row_ok || gn >= p.N) return;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                 __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-          *reinterpret_cast<float4*>(&stg[lane * kStagePad + 4 * j]) = v;
-        }
-        __syncwarp();
-        const int gn = gn_lane + c * 32;
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias != nullptr && gn < p.N) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + gn));
+        for (int j = 0; j < 4; ++j) {  // 8 columns at a time
+          if (gn + 8 * j >= p.N) break;
+          float v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = 4 * i + (lane >> 3);
-          const int gm = m0 + ew * 32 + row;
-          if (gm >= p.M || gn >= p.N) continue;
-          float4 v = *reinterpret_cast<const float4*>(&stg[row * kStagePad + (lane & 7) * 4]);
-          v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
-          float* cptr = p.C + static_cast<size_t>(gm) * p.ldc + gn;
+          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * j + e]);
+          if (p.bias != nullptr) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + gn + 8 * j));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + gn + 8 * j + 4));
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+          }
           switch (p.epi) {
-            case EPI_GELU: {  // aux <- pre-activation, C <- gelu
-              *reinterpret_cast<float4*>(p.aux + static_cast<size_t>(gm) * p.ldaux + gn) = v;
-              v.x = gelu_exact(v.x); v.y = gelu_exact(v.y); v.z = gelu_exact(v.z); v.w = gelu_exact(v.w);
+            case EPI_GELU:  // aux <- pre-activation, C <- gelu
+              st_global_v8(aux_row + gn + 8 * j, v);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = gelu_exact(v[e]);
               break;
-            }
-            case EPI_DGELU: {  // C <- acc * gelu'(aux)
-              const float4 u = side[i];
-              v.x *= gelu_grad(u.x); v.y *= gelu_grad(u.y); v.z *= gelu_grad(u.z); v.w *= gelu_grad(u.w);
+            case EPI_DGELU:  // C <- acc * gelu'(aux)
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] *= gelu_grad(sd[8 * j + e]);
               break;
-            }
-            case EPI_RESID: {  // C <- resid + rowscale[seq] * acc
-              const float s = p.rowscale ? p.rowscale[gm / p.rows_per_seq] : 1.0f;
-              const float4 x = side[i];
-              v.x = fmaf(s, v.x, x.x); v.y = fmaf(s, v.y, x.y); v.z = fmaf(s, v.z, x.z); v.w = fmaf(s, v.w, x.w);
+            case EPI_RESID:  // C <- resid + rowscale[seq] * (acc + bias)
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = fmaf(rs, v[e], sd[8 * j + e]);
               break;
-            }
-            case EPI_SCALE: {  // C <- rowscale[seq] * acc   (dgrad through droppath)
-              const float s = p.rowscale ? p.rowscale[gm / p.rows_per_seq] : 1.0f;
-              v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+            case EPI_SCALE:  // C <- rowscale[seq] * acc   (dgrad through droppath)
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] *= rs;
               break;
-            }
             case EPI_RELU:
-              v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
               break;
             default:
               break;
           }
           if (p.round_out) {
-            v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = round_tf32(v[e]);
           }
+          float* cp = c_row + gn + 8 * j;
           if (p.epi == EPI_ATOMIC) {
-            atomicAdd(cptr + 0, v.x); atomicAdd(cptr + 1, v.y); atomicAdd(cptr + 2, v.z); atomicAdd(cptr + 3, v.w);
-          } else if (p.epi != EPI_DBG_NOSTORE || v.x == 123.456f) {
-            *reinterpret_cast<float4*>(cptr) = v;
+            red_add_v4(cp, v[0], v[1], v[2], v[3]);
+            red_add_v4(cp + 4, v[4], v[5], v[6], v[7]);
+          } else if (p.epi != EPI_DBG_NOSTORE || v[0] == 123.456f) {
+            st_global_v8(cp, v);
           }
         }
-        __syncwarp();
       };
-      float4 side_a[8], side_b[8];
+      float side_a[32], side_b[32];
       load_side(0, side_a);
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N / 32; c += 2) {
