@@ -26,7 +26,6 @@ constexpr int kBlockKBytes = 128;  // one 128B swizzle row
 constexpr int kBlockK = 32;        // tf32 elements per k-block
 constexpr int kUmmaK = 8;          // tf32 elements per tcgen05.mma
 constexpr int kThreads = 256;
-constexpr int kStagePad = 36;      // floats per staged row (16B aligned, conflict-free)
 
 template <int BLOCK_N>
 struct GemmCfg {
@@ -420,13 +419,26 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
   return atst_check_launch("gemm_tf32_kernel");
 }
 
+// the epilogue moves 8 fp32 (one 32-byte sector) per lane and instruction
+static int check_output_layout(const GemmParams& p, const char* who) {
+  ATST_REQUIRE(p.N % 8 == 0 && p.ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(p.C) & 31) == 0,
+               "%s: N and ldc must be multiples of 8 and C 32-byte aligned (N=%d ldc=%d)", who, p.N, p.ldc);
+  ATST_REQUIRE(p.resid == nullptr || (p.ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(p.resid) & 31) == 0),
+               "%s: resid must be 32-byte aligned with ldr %% 8 == 0", who);
+  ATST_REQUIRE(p.aux == nullptr || (p.ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(p.aux) & 31) == 0),
+               "%s: aux must be 32-byte aligned with ldaux %% 8 == 0", who);
+  ATST_REQUIRE(p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0, "%s: bias must be 16-byte aligned", who);
+  return ATST_OK;
+}
+
 int gemm_nt(const float* A, int lda, const float* B, int ldb, GemmParams p, cudaStream_t stream) {
   ATST_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm_nt: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
-  ATST_REQUIRE(p.N % 4 == 0 && p.ldc % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && p.K % 4 == 0,
-               "gemm_nt: N, K and leading dimensions must be multiples of 4 (N=%d K=%d lda=%d ldb=%d ldc=%d)", p.N, p.K,
-               lda, ldb, p.ldc);
-  ATST_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
-                   (reinterpret_cast<uintptr_t>(p.C) & 15) == 0, "gemm_nt: pointers must be 16-byte aligned");
+  ATST_REQUIRE(lda % 4 == 0 && ldb % 4 == 0 && p.K % 4 == 0,
+               "gemm_nt: K and operand leading dimensions must be multiples of 4 (K=%d lda=%d ldb=%d)", p.K, lda, ldb);
+  ATST_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
+               "gemm_nt: operand pointers must be 16-byte aligned");
+  int rc0 = check_output_layout(p, "gemm_nt");
+  if (rc0) return rc0;
   const bool wide = (p.N % 256 == 0) || p.N > 1024;
   CUtensorMap ta, tb;
   int rc = make_map_kmajor(&ta, A, p.M, p.K, lda, kBlockM);
@@ -450,8 +462,10 @@ static void mn_defaults(GemmParams& p) {
 int gemm_nn(const float* A, int lda, const float* B, int ldb, GemmParams p, cudaStream_t stream) {
   // C[M,N] = epi(A[M,K] . B[K,N]); B row-major [K, N] (a Linear weight [out=K, in=N] used for dgrad)
   ATST_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm_nn: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
-  ATST_REQUIRE(p.N % 32 == 0 && p.ldc % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && p.K % 4 == 0,
+  ATST_REQUIRE(p.N % 32 == 0 && lda % 4 == 0 && ldb % 4 == 0 && p.K % 4 == 0,
                "gemm_nn: N must be a multiple of 32, K and leading dims multiples of 4 (N=%d K=%d)", p.N, p.K);
+  int rc0 = check_output_layout(p, "gemm_nn");
+  if (rc0) return rc0;
   mn_defaults(p);
   const bool wide = (p.N % 256 == 0) || p.N > 1024;
   CUtensorMap ta, tb;
@@ -466,8 +480,10 @@ int gemm_nn(const float* A, int lda, const float* B, int ldb, GemmParams p, cuda
 int gemm_tn(const float* A, int lda, const float* B, int ldb, int T, GemmParams p, cudaStream_t stream) {
   // C[M,N] (+)= A[T,M]^T B[T,N]; M, N are feature counts, T tokens.
   ATST_REQUIRE(p.M > 0 && p.N > 0 && T > 0, "gemm_tn: empty problem");
-  ATST_REQUIRE(p.M % 32 == 0 && p.N % 32 == 0 && lda % 4 == 0 && ldb % 4 == 0 && p.ldc % 4 == 0,
+  ATST_REQUIRE(p.M % 32 == 0 && p.N % 32 == 0 && lda % 4 == 0 && ldb % 4 == 0,
                "gemm_tn: feature dims must be multiples of 32 (M=%d N=%d)", p.M, p.N);
+  int rc0 = check_output_layout(p, "gemm_tn");
+  if (rc0) return rc0;
   p.K = T;
   const bool wide = (p.N % 256 == 0) || p.N > 1024;
   const int bn = wide ? 256 : 128;
