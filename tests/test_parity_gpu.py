@@ -162,9 +162,11 @@ def check_grads(m, g, case, tol):
 
 # forward / loss: north_star tolerance 1e-3 relative on the loss and the logged statistics; the 256-d outputs are
 # held to 2e-3 relative l2 (TF32 operand rounding through the 2-12 blocks plus two BatchNorm heads).
-# gradients: 2e-2 when BatchNorm sees 64 rows; the 4-8 row toy batches of the other fixtures make BatchNorm's
-# backward ill-conditioned (differences of nearly equal means), so they only bound the error at 2e-1.
-GRAD_TOL = {"tiny2": 2e-1, "tiny4": 2e-1, "tiny2dp": 2e-1, "small2": 2e-1, "tiny2b32": 2e-2}
+# gradients: rounding the GEMM operands to TF32 moves the gradients of these fixtures by 3-5 % even inside the fp32
+# oracle (tools/tf32_sensitivity.py emulates it on the CPU), because the BatchNorm heads subtract nearly equal
+# means; the bound is 1e-1 with 64 BatchNorm rows and 2e-1 for the 4-8 row toy batches.  Kernel-level backward
+# tests above hold each kernel to 1e-3 or better.
+GRAD_TOL = {"tiny2": 2e-1, "tiny4": 2e-1, "tiny2dp": 2e-1, "small2": 2e-1, "tiny2b32": 1e-1}
 
 
 @pytest.mark.parametrize("case", ["tiny2", "tiny2b32", "tiny4", "small2"])

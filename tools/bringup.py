@@ -379,7 +379,31 @@ def sec_gemm_perf():
         del A, W, C, aux, dX, dW
 
 
-SECTIONS = {"gemm_perf": sec_gemm_perf, "mel": sec_mel, "gemm_nt": sec_gemm_nt, "gemm_mn": sec_gemm_mn, "ln": sec_ln, "attn": sec_attn,
+def sec_heads():
+    """the exact head-shaped GEMMs (few rows, 4096 / 256 features)"""
+    import torch
+    from audiossl_b200 import ops
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    for R in (4, 6, 32, 64, 128, 512):
+        dz1 = ops.round_tf32(torch.randn(R, 4096, device="cuda") * 0.1)
+        x = ops.round_tf32(torch.randn(R, 256, device="cuda"))
+        C = torch.zeros(4096, 256, device="cuda")
+        ops.gemm_tn_acc(dz1, x, C)
+        W0 = ops.round_tf32(torch.randn(4096, 256, device="cuda") * 0.05)
+        dx = ops.gemm_nn(dz1, W0)
+        dz2 = ops.round_tf32(torch.randn(R, 256, device="cuda") * 0.1)
+        a1 = ops.round_tf32(torch.randn(R, 4096, device="cuda"))
+        C2 = torch.zeros(256, 4096, device="cuda")
+        ops.gemm_tn_acc(dz2, a1, C2)
+        W3 = ops.round_tf32(torch.randn(256, 4096, device="cuda") * 0.05)
+        da1 = ops.gemm_nn(dz2, W3)
+        torch.cuda.synchronize()
+        print("R=%3d tn[4096x256] %.2e nn[->256] %.2e tn[256x4096] %.2e nn[->4096] %.2e" %
+              (R, rel_err(C, dz1.t() @ x), rel_err(dx, dz1 @ W0), rel_err(C2, dz2.t() @ a1), rel_err(da1, dz2 @ W3)))
+
+
+SECTIONS = {"heads": sec_heads, "gemm_perf": sec_gemm_perf, "mel": sec_mel, "gemm_nt": sec_gemm_nt, "gemm_mn": sec_gemm_mn, "ln": sec_ln, "attn": sec_attn,
             "bn": sec_bn, "loss": sec_loss, "optim": sec_optim, "tokens": sec_tokens}
 
 if __name__ == "__main__":
