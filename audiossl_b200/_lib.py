@@ -40,6 +40,8 @@ SIGNATURES = {
     "atst_byol_finalize": [P, F, F, I, I, P, P],
     "atst_ema_update": [P, P, F, L, P],
     "atst_adamw_step": [P, P, P, P, L, I, F, F, F, F, F, F, P],
+    "atst_gather_rows": [P, P, P, I, I, P],
+    "atst_scatter_rows": [P, P, P, I, I, P],
     "atst_gelu_forward": [P, P, L, P],
     "atst_gelu_backward": [P, P, L, P],
     "atst_round_tf32": [P, P, L, P],

@@ -150,6 +150,12 @@ int atst_adamw_step(float* p, const float* g, float* m, float* v, long long n, i
                     float beta1, float beta2, float eps, float grad_scale, void* stream) {
   return adamw_step(p, g, m, v, n, step, lr, wd, beta1, beta2, eps, grad_scale, ST(stream));
 }
+int atst_gather_rows(const float* x, const int* idx, float* out, int rows, int D, void* stream) {
+  return gather_rows(x, idx, out, rows, D, ST(stream));
+}
+int atst_scatter_rows(const float* src, const int* idx, float* dst, int rows, int D, void* stream) {
+  return scatter_rows(src, idx, dst, rows, D, ST(stream));
+}
 int atst_gelu_forward(const float* u, float* g, long long n, void* stream) { return gelu_forward(u, g, n, ST(stream)); }
 int atst_gelu_backward(float* d, const float* u, long long n, void* stream) { return gelu_backward(d, u, n, ST(stream)); }
 int atst_round_tf32(const float* src, float* dst, long long n, void* stream) {

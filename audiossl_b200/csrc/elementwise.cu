@@ -224,7 +224,7 @@ __global__ void bn_relu_bwd_apply_kernel(const float* __restrict__ dY, const flo
 __device__ __forceinline__ void gelu_cdf_pdf(float u, float& cdf, float& pdf) {
   const float x = u * 0.70710678118654752f;
   const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));  // MUFU.RCP, branch-free (keeps the 8 chains interleaved)
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
@@ -260,6 +260,27 @@ __global__ void gelu_bwd_kernel(float* __restrict__ d, const float* __restrict__
     gelu_cdf_pdf(v.z, c, p); o.z = round_tf32(o.z * fmaf(v.z, p, c));
     gelu_cdf_pdf(v.w, c, p); o.w = round_tf32(o.w * fmaf(v.w, p, c));
     reinterpret_cast<float4*>(d)[i] = o;
+  }
+}
+
+// out[r, :] = x[idx[r], :]   (ATST-Frame: masked valid frames -> compact rows, atstframe/audio_transformer.py:207)
+__global__ void gather_rows_kernel(const float* __restrict__ x, const int* __restrict__ idx, float* __restrict__ out,
+                                   long long total4, int d4) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / d4;
+    const int c = static_cast<int>(i - r * d4);
+    reinterpret_cast<float4*>(out)[i] = reinterpret_cast<const float4*>(x)[static_cast<long long>(idx[r]) * d4 + c];
+  }
+}
+// dst[idx[r], :] = src[r, :]   (dst zero-filled by the caller; indices are unique)
+__global__ void scatter_rows_kernel(const float* __restrict__ src, const int* __restrict__ idx, float* __restrict__ dst,
+                                    long long total4, int d4) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / d4;
+    const int c = static_cast<int>(i - r * d4);
+    reinterpret_cast<float4*>(dst)[static_cast<long long>(idx[r]) * d4 + c] = reinterpret_cast<const float4*>(src)[i];
   }
 }
 
@@ -346,6 +367,20 @@ int bn_relu_backward_apply(const float* dY, const float* X, const float* mean, c
   bn_relu_bwd_apply_kernel<<<grid_for(total), 256, 0, st>>>(dY, X, mean, rstd, gamma, beta, s1, s2, 1.0f / count, dX,
                                                            total, cols);
   return atst_check_launch("bn_relu_bwd_apply_kernel");
+}
+int gather_rows(const float* x, const int* idx, float* out, int rows, int D, cudaStream_t st) {
+  ATST_REQUIRE(D % 4 == 0 && rows >= 0, "gather_rows: D %% 4 != 0");
+  if (rows == 0) return ATST_OK;
+  const long long total4 = static_cast<long long>(rows) * (D / 4);
+  gather_rows_kernel<<<grid_for(total4), 256, 0, st>>>(x, idx, out, total4, D / 4);
+  return atst_check_launch("gather_rows_kernel");
+}
+int scatter_rows(const float* src, const int* idx, float* dst, int rows, int D, cudaStream_t st) {
+  ATST_REQUIRE(D % 4 == 0 && rows >= 0, "scatter_rows: D %% 4 != 0");
+  if (rows == 0) return ATST_OK;
+  const long long total4 = static_cast<long long>(rows) * (D / 4);
+  scatter_rows_kernel<<<grid_for(total4), 256, 0, st>>>(src, idx, dst, total4, D / 4);
+  return atst_check_launch("scatter_rows_kernel");
 }
 int gelu_forward(const float* u, float* g, long long n, cudaStream_t st) {
   ATST_REQUIRE(n % 4 == 0, "gelu_forward: n %% 4 != 0");

@@ -45,7 +45,7 @@ struct GeluParts { float cdf, pdf; };
 __device__ __forceinline__ GeluParts gelu_parts(float u) {
   const float x = u * 0.70710678118654752f;
   const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));  // MUFU.RCP, branch-free (keeps the 8 chains interleaved)
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);

@@ -29,6 +29,8 @@ int bn_relu_backward_stats(const float* dY, const float* X, const float* mean, c
 int bn_relu_backward_apply(const float* dY, const float* X, const float* mean, const float* rstd, const float* gamma,
                            const float* beta, const float* s1, const float* s2, float count, float* dX, int rows,
                            int cols, cudaStream_t st);
+int gather_rows(const float* x, const int* idx, float* out, int rows, int D, cudaStream_t st);
+int scatter_rows(const float* src, const int* idx, float* dst, int rows, int D, cudaStream_t st);
 int gelu_forward(const float* u, float* g, long long n, cudaStream_t st);
 int gelu_backward(float* d, const float* u, long long n, cudaStream_t st);
 int round_tf32_copy(const float* src, float* dst, long long n, cudaStream_t st);

@@ -48,13 +48,15 @@ class _Runtime:
         self.ft = FlatParams(list(model.teacher.named_parameters()), device)
         assert self.ft.total == self.fs.ema_count and self.ft.order == self.fs.order[:len(self.ft.order)], \
             "teacher layout must be the encoder+projector prefix of the student layout"
-        self.enc = EncoderEngine(enc.embed_dim, enc.depth, enc.num_heads, use_cls=enc.use_cls,
-                                 max_frames=enc.spec_w)
+        self.enc = self._make_encoder(enc)
         self.proj = HeadEngine("projector.", enc.embed_dim)
         self.pred = HeadEngine("predictor.", 256)
         self.ws = Workspace(device)
         self.saved = None
         self.anchor = torch.zeros((), device=device, requires_grad=True)
+
+    def _make_encoder(self, enc):
+        return EncoderEngine(enc.embed_dim, enc.depth, enc.num_heads, use_cls=enc.use_cls, max_frames=enc.spec_w)
 
     def current(self):
         return self.fs.is_current() and self.ft.is_current()

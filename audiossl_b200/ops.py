@@ -278,6 +278,20 @@ def adamw_step(p, g, m, v, step, lr, wd, beta1=0.9, beta2=0.999, eps=1e-6, grad_
     _count(1)
 
 
+def gather_rows(x, idx, out):
+    rows, D = out.shape
+    check(_lib.lib().atst_gather_rows(ptr(x), ptr(idx), ptr(out), rows, D, _lib.stream()), "atst_gather_rows")
+    _count(1)
+    return out
+
+
+def scatter_rows(src, idx, dst):
+    rows, D = src.shape
+    check(_lib.lib().atst_scatter_rows(ptr(src), ptr(idx), ptr(dst), rows, D, _lib.stream()), "atst_scatter_rows")
+    _count(1)
+    return dst
+
+
 def gelu_fwd(u, out):
     check(_lib.lib().atst_gelu_forward(ptr(u), ptr(out), u.numel(), _lib.stream()), "atst_gelu_forward")
     _count(1)

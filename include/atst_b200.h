@@ -109,6 +109,11 @@ int atst_ema_update(float* k, const float* q, float m, long long n, void* stream
 int atst_adamw_step(float* p, const float* g, float* m, float* v, long long n, int step, float lr, float wd,
                     float beta1, float beta2, float eps, float grad_scale, void* stream);
 
+/* ---- ATST-Frame row selection (audiossl/methods/atstframe/audio_transformer.py:187-207: frame_repr[mask & valid]):
+ *      out[r] = x[idx[r]] and its adjoint dst[idx[r]] = src[r] (dst pre-zeroed, unique indices) */
+int atst_gather_rows(const float* x, const int* idx, float* out, int rows, int D, void* stream);
+int atst_scatter_rows(const float* src, const int* idx, float* dst, int rows, int D, void* stream);
+
 /* ---- exact-erf GELU as separate passes (audiossl/modules/transformer.py:78,88): g = gelu(u); d *= gelu'(u) */
 int atst_gelu_forward(const float* u, float* g, long long n, void* stream);
 int atst_gelu_backward(float* d, const float* u, long long n, void* stream);

@@ -311,6 +311,37 @@ class OracleATST(nn.Module):
         ema_update(self, m)
 
 
+class OracleFrameATST(nn.Module):
+    """ATST-Frame, symmetric branch: audiossl/methods/atstframe/model.py:24-76, byol.py:57-84,118-138,
+    audio_transformer.py:161-207 (no CLS, mask_embed blend for the student, masked valid frames returned)."""
+
+    def __init__(self, arch="small", embed_dim=None, depth=None, num_heads=None):
+        super().__init__()
+        if embed_dim is None:
+            embed_dim, depth, num_heads = OracleATST.CFG[arch]
+        mk = lambda: OracleAST(embed_dim, depth, num_heads, use_cls=False, norm_name="norm_frame")
+        self.student = OracleMultiCrop(mk(), embed_dim, True)
+        self.teacher = OracleMultiCrop(mk(), embed_dim, False)
+        for p in self.teacher.parameters():
+            p.requires_grad = False
+        self.teacher.load_state_dict({k: v for k, v in self.student.state_dict().items()
+                                      if "predictor" not in k})
+
+    @staticmethod
+    def _net(net, crops, lengths, masks, mask_input):
+        frames = net.encoder(torch.cat(crops), torch.cat(lengths), None, torch.cat(masks), mask_input)
+        return net.predictor(net.projector(frames))
+
+    def forward(self, crops, lengths, masks):
+        t = self._net(self.teacher, crops, lengths, masks, False)
+        s = self._net(self.student, crops, lengths, masks, True)
+        return byol_loss(s, t, 2)
+
+    @torch.no_grad()
+    def update_teacher(self, m):
+        ema_update(self, m)
+
+
 @torch.no_grad()
 def ema_update(model, m):
     for q, k in zip(model.student.encoder.parameters(), model.teacher.encoder.parameters()):

@@ -184,6 +184,74 @@ def gen_atst():
     print("atst.npz", len(out))
 
 
+def frame_stubs():
+    """sys.modules stand-ins for packages the frame model imports but this image lacks."""
+    import types
+    if "pytorch_lightning" not in sys.modules:
+        pl = types.ModuleType("pytorch_lightning")
+
+        class LightningModule(nn.Module):
+            pass
+        pl.LightningModule = LightningModule
+        sys.modules["pytorch_lightning"] = pl
+    if "fairseq" not in sys.modules:
+        fs, fd, fdu = (types.ModuleType(n) for n in ("fairseq", "fairseq.data", "fairseq.data.data_utils"))
+        fdu.compute_mask_indices = lambda *a, **k: None  # masks are inputs of the fixtures
+        sys.modules.update({"fairseq": fs, "fairseq.data": fd, "fairseq.data.data_utils": fdu})
+    import transformers.optimization as to
+    if not hasattr(to, "AdamW"):
+        to.AdamW = torch.optim.AdamW  # never stepped here
+
+
+def frame_masks(tag, B, P):
+    m = detfill.det_array(tag + "/mask", (B, P), 1.0, "uniform") > 0.0
+    m[:, 0] = True  # every clip has at least one masked frame inside any length
+    return torch.from_numpy(m)
+
+
+def gen_frame():
+    """ATST-Frame (methods/atstframe): FrameAST + symmetric frame-level BYOL loss on masked frames."""
+    harness()
+    frame_stubs()
+    from audiossl.methods.atstframe.audio_transformer import FrameAST
+    from audiossl.methods.atstframe.byol import ByolLoss, MultiCropWrapper
+    out = {}
+
+    class RefFrame(nn.Module):
+        def __init__(self, dim, depth, heads):
+            super().__init__()
+            mk = lambda: FrameAST(patch_h=64, patch_w=4, embed_dim=dim, depth=depth, num_heads=heads, qkv_bias=False,
+                                  norm_layer=partial(nn.LayerNorm, eps=1e-6), drop_path_rate=0.0)
+            self.student = MultiCropWrapper(mk(), dim, predictor=True)
+            self.teacher = MultiCropWrapper(mk(), dim, predictor=False)
+            for p in self.teacher.parameters():
+                p.requires_grad = False
+            self.loss_fn = ByolLoss(symmetric=True)
+
+        def forward(self, x, length, mask):  # FrameATST.forward, symmetric branch (model.py:68-72)
+            tea = self.teacher(x, length, mask, False)
+            stu = self.student(x, length, mask, True)
+            return self.loss_fn(stu, tea), stu, tea
+
+    for tag, B, lens in (("frame2", 4, [[101, 101, 77, 60], [101, 101, 77, 60]]),
+                         ("frame2b16", 16, [[101 - (i * 5) % 40 for i in range(16)]] * 2)):
+        m = RefFrame(128, 2, 2)
+        load_det(m)
+        m.train()
+        crops, lengths = make_inputs(tag, B, [101, 101], lens)
+        mask = frame_masks(tag, B, 25)
+        (loss, std_s, std_t), s, t = m(crops, lengths, [mask, mask])
+        loss.backward()
+        out[tag + "/loss"] = np.float32(loss.item())
+        out[tag + "/std_s"] = np.float32(std_s.item())
+        out[tag + "/std_t"] = np.float32(std_t.item())
+        out[tag + "/student_out"] = s.detach().numpy()
+        out[tag + "/teacher_out"] = t.detach().numpy()
+        grads_summary(m.student, out, tag)
+    np.savez_compressed(os.path.join(HERE, "frame.npz"), **out)
+    print("frame.npz", len(out))
+
+
 def gen_sched():
     from audiossl.utils.common import cosine_scheduler_step, get_params_groups
     out = {"ema": cosine_scheduler_step(0.99, 1, 1000, 0), "wd": cosine_scheduler_step(0.04, 0.4, 1000, 0),
@@ -200,4 +268,5 @@ if __name__ == "__main__":
     torch.manual_seed(0)
     gen_mel()
     gen_atst()
+    gen_frame()
     gen_sched()

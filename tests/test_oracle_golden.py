@@ -106,3 +106,40 @@ def test_schedules_and_param_groups():
     m, _ = build("tiny2")
     reg, noreg = O.param_groups(m.student)
     assert reg == list(g["reg"]) and noreg == list(g["noreg"])
+
+
+def frame_masks(tag, B, P):
+    m = detfill.det_array(tag + "/mask", (B, P), 1.0, "uniform") > 0.0
+    m[:, 0] = True
+    return torch.from_numpy(m)
+
+
+FRAME_CASES = {"frame2": (4, [[101, 101, 77, 60], [101, 101, 77, 60]]),
+               "frame2b16": (16, [[101 - (i * 5) % 40 for i in range(16)]] * 2)}
+
+
+@pytest.mark.parametrize("case", list(FRAME_CASES))
+def test_frame_model_matches_reference(case):
+    g = util.gold("frame.npz")
+    B, lens = FRAME_CASES[case]
+    m = O.OracleFrameATST(embed_dim=128, depth=2, num_heads=2)
+    util.load_det(m)
+    m.train()
+    crops, lengths = util.make_inputs(case, B, [101, 101], lens)
+    mask = frame_masks(case, B, 25)
+    t = m._net(m.teacher, crops, lengths, [mask, mask], False)
+    s = m._net(m.student, crops, lengths, [mask, mask], True)
+    loss, std_s, std_t = O.byol_loss(s, t, 2)
+    loss.backward()
+    assert s.shape == g[case + "/student_out"].shape
+    np.testing.assert_allclose(s.detach().numpy(), g[case + "/student_out"], rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(t.detach().numpy(), g[case + "/teacher_out"], rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(loss.item(), g[case + "/loss"], rtol=1e-5)
+    np.testing.assert_allclose(std_s.item(), g[case + "/std_s"], rtol=1e-4)
+    n = 0
+    for name, p in m.student.named_parameters():
+        key = case + "/grad/" + name
+        if key + "/idx" in g.files:
+            util.check_summary(p.grad.numpy(), g, key, rtol=2e-3, atol=2e-4)
+            n += 1
+    assert n > 20 and m.student.encoder.mask_embed.grad is not None

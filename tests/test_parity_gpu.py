@@ -258,3 +258,33 @@ def test_too_long_clip_is_rejected():
     x = [torch.zeros(2, 1, 64, 1101, device="cuda")] * 2
     with pytest.raises(ValueError):
         m(x, [torch.full((2,), 1101, device="cuda")] * 2)
+
+
+# --------------------------------------------------------------------------- ATST-Frame
+FRAME_CASES = {"frame2": (4, [[101, 101, 77, 60], [101, 101, 77, 60]]),
+               "frame2b16": (16, [[101 - (i * 5) % 40 for i in range(16)]] * 2)}
+
+
+@pytest.mark.parametrize("case", list(FRAME_CASES))
+def test_frame_step_matches_reference_golden(case):
+    from audiossl_b200.methods.atstframe.model import FrameATST
+    g = util.gold("frame.npz")
+    B, lens = FRAME_CASES[case]
+    m = FrameATST(arch=dict(embed_dim=128, depth=2, num_heads=2), drop_path_rate=0.0)
+    util.load_det(m)
+    m.cuda().train()
+    crops, lengths = util.make_inputs(case, B, [101, 101], lens)
+    mk = detfill.det_array(case + "/mask", (B, 25), 1.0, "uniform") > 0.0
+    mk[:, 0] = True
+    mask = torch.from_numpy(mk).cuda()
+    loss, std_s, std_t = m([c.cuda() for c in crops], [l.cuda() for l in lengths], [mask, mask])
+    loss.backward()
+    s_out, t_out = m._rt.last_outputs
+    assert tuple(s_out.shape) == g[case + "/student_out"].shape  # masked-row count and order are exact
+    assert rel(s_out, g[case + "/student_out"]) < 2e-3
+    assert rel(t_out, g[case + "/teacher_out"]) < 2e-3
+    np.testing.assert_allclose(loss.item(), g[case + "/loss"], rtol=1e-3)
+    np.testing.assert_allclose(std_s.item(), g[case + "/std_s"], rtol=1e-3)
+    np.testing.assert_allclose(std_t.item(), g[case + "/std_t"], rtol=1e-3)
+    assert m.student.encoder.mask_embed.grad is not None
+    check_grads(m, g, case, 2e-1)
