@@ -54,3 +54,41 @@ def sample_rel_err(arr, g, prefix):
     rms = np.sqrt(float(g[prefix + "/sq"]) / max(a.size, 1))
     err = np.sqrt(np.mean((mine - ref) ** 2)) / max(rms, 1e-30)
     return float(err), float(np.sqrt(float(g[prefix + "/sq"])))
+
+
+CASES = {
+    "tiny2": dict(dim=128, depth=2, heads=2, ncrops=2, B=3, widths=[101, 101],
+                  lens=[[101, 77, 50], [101, 101, 9]]),
+    "tiny4": dict(dim=128, depth=2, heads=2, ncrops=4, B=2, widths=[101, 101, 41, 41],
+                  lens=[[101, 90], [101, 101], [41, 33], [41, 41]]),
+    "tiny2dp": dict(dim=128, depth=2, heads=2, ncrops=2, B=4, widths=[101, 101],
+                    lens=[[101, 101, 60, 101], [101, 80, 101, 101]], drop_path=0.5),
+    "tiny2b32": dict(dim=128, depth=2, heads=2, ncrops=2, B=32, widths=[101, 101],
+                     lens=[[101 - (i * 7) % 60 for i in range(32)], [101 - (i * 11) % 45 for i in range(32)]]),
+    "small2": dict(dim=384, depth=12, heads=6, ncrops=2, B=2, widths=[101, 101], lens=[[101, 64], [101, 101]]),
+}
+
+
+def dp_scales_from_rand(rand, depth, keep_per_block, n_groups_teacher=1, n_groups_student=1):
+    """Rebuild per-block (attn, mlp) DropPath scales from the recorded torch.rand stream.
+
+    Reference order of torch.rand calls (modules/transformer.py:48-57, 136-150): teacher encoder
+    call(s) first, then student; inside an encoder call block 0 attn, block 0 mlp, block 1 attn, ...
+    Blocks whose drop prob is 0 use nn.Identity and draw nothing.
+    scale = floor(keep + u) / keep.
+    """
+    rows = list(rand)
+    out = []
+    for _ in range(n_groups_teacher + n_groups_student):
+        blocks = []
+        for i in range(depth):
+            keep = keep_per_block[i]
+            if keep >= 1.0:
+                blocks.append(None)
+                continue
+            a = torch.from_numpy(np.floor(keep + rows.pop(0)) / keep).float()
+            m = torch.from_numpy(np.floor(keep + rows.pop(0)) / keep).float()
+            blocks.append((a, m))
+        out.append(blocks)
+    assert not rows
+    return out[:n_groups_teacher], out[n_groups_teacher:]
