@@ -46,12 +46,13 @@ def check_summary(arr, g, prefix, rtol, atol, scale=None):
 
 
 def sample_rel_err(arr, g, prefix):
-    """error on the stored sample (head + strided sample) of a summarised array, relative to the rms of the WHOLE
-    golden array (the sample alone may consist of small entries); also returns the golden array's l2 norm."""
+    """error on the stored sample (head + strided sample) of a summarised array, relative to the larger of the sample's
+    own rms and the rms of the WHOLE golden array (a sample may consist of small entries, or - pos_embed - the
+    array may be mostly structural zeros); also returns the golden array's l2 norm."""
     a = np.asarray(arr, np.float64).ravel()
     mine = np.concatenate([a[: g[prefix + "/head"].size], a[g[prefix + "/idx"]]])
     ref = np.concatenate([g[prefix + "/head"], g[prefix + "/samp"]]).astype(np.float64)
-    rms = np.sqrt(float(g[prefix + "/sq"]) / max(a.size, 1))
+    rms = max(np.sqrt(float(g[prefix + "/sq"]) / max(a.size, 1)), np.sqrt(np.mean(ref ** 2)))
     err = np.sqrt(np.mean((mine - ref) ** 2)) / max(rms, 1e-30)
     return float(err), float(np.sqrt(float(g[prefix + "/sq"])))
 
