@@ -24,7 +24,7 @@ SIGNATURES = {
     "atst_gemm_tn": [P, I, P, I, P, I, I, I, I, P],
     "atst_gemm_mn_debug": [I, P, I, P, I, P, I, I, I, I, U, U, U, U, I, I, P],
     "atst_layernorm_forward": [P, L, P, P, P, L, P, P, I, I, F, I, P],
-    "atst_layernorm_backward": [P, L, P, L, P, P, P, P, L, P, L, P, P, I, I, P],
+    "atst_layernorm_backward": [P, L, P, L, P, P, P, P, L, P, L, P, P, I, I, P, L, P, I, P, P],
     "atst_attention_forward": [P, P, P, P, I, I, I, P],
     "atst_attention_backward": [P, P, P, P, P, P, P, I, I, I, P],
     "atst_patchify": [P, L, I, I, P, P],
@@ -43,7 +43,7 @@ SIGNATURES = {
     "atst_gather_rows": [P, P, P, I, I, P],
     "atst_scatter_rows": [P, P, P, I, I, P],
     "atst_gelu_forward": [P, P, L, P],
-    "atst_gelu_backward": [P, P, L, P],
+    "atst_gelu_backward": [P, P, I, I, P, P],
     "atst_round_tf32": [P, P, L, P],
     "atst_axpy": [P, P, F, L, P],
 }

@@ -88,9 +88,10 @@ int atst_layernorm_forward(const float* x, long long x_stride, const float* gamm
 int atst_layernorm_backward(const float* dy, long long dy_stride, const float* x, long long x_stride,
                             const float* mean, const float* rstd, const float* gamma, const float* dres,
                             long long dres_stride, float* dx, long long dx_stride, float* dgamma, float* dbeta,
-                            int rows, int D, void* stream) {
+                            int rows, int D, float* dys, long long dys_stride, const float* rowscale,
+                            int rows_per_seq, float* colsum_out, void* stream) {
   return layernorm_backward(dy, dy_stride, x, x_stride, mean, rstd, gamma, dres, dres_stride, dx, dx_stride, dgamma,
-                            dbeta, rows, D, ST(stream));
+                            dbeta, rows, D, dys, dys_stride, rowscale, rows_per_seq, colsum_out, ST(stream));
 }
 int atst_attention_forward(const float* qkv, float* o, float* lse, const int* lengths, int S, int N, int H,
                            void* stream) {
@@ -157,7 +158,9 @@ int atst_scatter_rows(const float* src, const int* idx, float* dst, int rows, in
   return scatter_rows(src, idx, dst, rows, D, ST(stream));
 }
 int atst_gelu_forward(const float* u, float* g, long long n, void* stream) { return gelu_forward(u, g, n, ST(stream)); }
-int atst_gelu_backward(float* d, const float* u, long long n, void* stream) { return gelu_backward(d, u, n, ST(stream)); }
+int atst_gelu_backward(float* d, const float* u, int rows, int cols, float* colsum_out, void* stream) {
+  return gelu_backward(d, u, rows, cols, colsum_out, ST(stream));
+}
 int atst_round_tf32(const float* src, float* dst, long long n, void* stream) {
   return round_tf32_copy(src, dst, n, ST(stream));
 }

@@ -248,18 +248,42 @@ __global__ void gelu_fwd_kernel(const float* __restrict__ u, float* __restrict__
     reinterpret_cast<float4*>(g)[i] = o;
   }
 }
-// d = tf32(d * gelu'(u)) in place
-__global__ void gelu_bwd_kernel(float* __restrict__ d, const float* __restrict__ u, long long n4) {
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float4 v = __ldcs(reinterpret_cast<const float4*>(u) + i);
-    float4 o = reinterpret_cast<float4*>(d)[i];
-    float c, p;
-    gelu_cdf_pdf(v.x, c, p); o.x = round_tf32(o.x * fmaf(v.x, p, c));
-    gelu_cdf_pdf(v.y, c, p); o.y = round_tf32(o.y * fmaf(v.y, p, c));
-    gelu_cdf_pdf(v.z, c, p); o.z = round_tf32(o.z * fmaf(v.z, p, c));
-    gelu_cdf_pdf(v.w, c, p); o.w = round_tf32(o.w * fmaf(v.w, p, c));
-    reinterpret_cast<float4*>(d)[i] = o;
+// d = tf32(d * gelu'(u)) in place; optionally colsum_out += column sums of the result (fc1 bias gradient).
+// CTA = 128 columns (32 lanes x float4) x a row chunk; warps stride over the rows, 512 B contiguous per warp-row.
+__global__ void __launch_bounds__(256)
+gelu_bwd_kernel(float* __restrict__ d, const float* __restrict__ u, int rows, int cols, float* __restrict__ colsum_out) {
+  __shared__ float red[8][128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c4 = blockIdx.x * 32 + lane;  // float4 column index
+  const int cols4 = cols >> 2;
+  const int rows_per = (rows + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per, r1 = min(r0 + rows_per, rows);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c4 < cols4) {
+    for (int r = r0 + warp; r < r1; r += 8) {
+      const size_t i = static_cast<size_t>(r) * cols4 + c4;
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(u) + i);
+      float4 o = reinterpret_cast<float4*>(d)[i];
+      float c, p;
+      gelu_cdf_pdf(v.x, c, p); o.x = round_tf32(o.x * fmaf(v.x, p, c));
+      gelu_cdf_pdf(v.y, c, p); o.y = round_tf32(o.y * fmaf(v.y, p, c));
+      gelu_cdf_pdf(v.z, c, p); o.z = round_tf32(o.z * fmaf(v.z, p, c));
+      gelu_cdf_pdf(v.w, c, p); o.w = round_tf32(o.w * fmaf(v.w, p, c));
+      reinterpret_cast<float4*>(d)[i] = o;
+      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    }
+  }
+  if (colsum_out == nullptr) return;
+  *reinterpret_cast<float4*>(&red[warp][lane * 4]) = acc;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int col = blockIdx.x * 128 + threadIdx.x;
+    if (col < cols) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+      atomicAdd(colsum_out + col, s);
+    }
   }
 }
 
@@ -387,9 +411,13 @@ int gelu_forward(const float* u, float* g, long long n, cudaStream_t st) {
   gelu_fwd_kernel<<<grid_for(n / 4, 256, 148 * 32), 256, 0, st>>>(u, g, n / 4);
   return atst_check_launch("gelu_fwd_kernel");
 }
-int gelu_backward(float* d, const float* u, long long n, cudaStream_t st) {
-  ATST_REQUIRE(n % 4 == 0, "gelu_backward: n %% 4 != 0");
-  gelu_bwd_kernel<<<grid_for(n / 4, 256, 148 * 32), 256, 0, st>>>(d, u, n / 4);
+int gelu_backward(float* d, const float* u, int rows, int cols, float* colsum_out, cudaStream_t st) {
+  ATST_REQUIRE(cols % 4 == 0 && rows > 0, "gelu_backward: cols %% 4 != 0");
+  const int gx = (cols / 4 + 31) / 32;
+  int gy = (148 * 8 + gx - 1) / gx;
+  if (gy > (rows + 63) / 64) gy = (rows + 63) / 64;
+  if (gy < 1) gy = 1;
+  gelu_bwd_kernel<<<dim3(gx, gy), 256, 0, st>>>(d, u, rows, cols, colsum_out);
   return atst_check_launch("gelu_bwd_kernel");
 }
 int round_tf32_copy(const float* src, float* dst, long long n, cudaStream_t st) {

@@ -57,14 +57,18 @@ __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const float* __restrict__ dy, long long dy_stride, const float* __restrict__ x, long long x_stride,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
               const float* __restrict__ dres, long long dres_stride, float* __restrict__ dx, long long dx_stride,
-              float* __restrict__ dgamma, float* __restrict__ dbeta, int rows) {
+              float* __restrict__ dgamma, float* __restrict__ dbeta, int rows,
+              float* __restrict__ dys, long long dys_stride, const float* __restrict__ rowscale, int rows_per_seq,
+              float* __restrict__ colsum_out) {
+  // optional second output for the consumer branch of dx: dys = tf32(rowscale[row / rows_per_seq] * dx) (the
+  // DropPath-scaled, GEMM-ready copy) and colsum_out += column sums of dys (= the consumer Linear's bias gradient)
   constexpr int D = NV * 128;
-  __shared__ float red[2][8][32 * 4];  // [dgamma|dbeta][warp][lane*4] for one i at a time
+  __shared__ float red[3][8][32 * 4];  // [dgamma|dbeta|colsum][warp][lane*4] for one i at a time
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int warps_per_cta = blockDim.x >> 5;
-  float4 pg[NV], pb[NV];
+  float4 pg[NV], pb[NV], pc[NV];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) pg[i] = pb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < NV; ++i) pg[i] = pb[i] = pc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 gm[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) gm[i] = reinterpret_cast<const float4*>(gamma)[lane + 32 * i];
@@ -101,6 +105,12 @@ ln_bwd_kernel(const float* __restrict__ dy, long long dy_stride, const float* __
         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
       }
       ox[lane + 32 * i] = o;
+      if (dys != nullptr) {
+        const float sc = rowscale != nullptr ? rowscale[row / rows_per_seq] : 1.0f;
+        float4 y = make_float4(round_tf32(sc * o.x), round_tf32(sc * o.y), round_tf32(sc * o.z), round_tf32(sc * o.w));
+        reinterpret_cast<float4*>(dys + static_cast<long long>(row) * dys_stride)[lane + 32 * i] = y;
+        pc[i].x += y.x; pc[i].y += y.y; pc[i].z += y.z; pc[i].w += y.w;
+      }
     }
   }
   // cross-warp reduction of the parameter-gradient partials, one 128-column slab at a time
@@ -108,13 +118,19 @@ ln_bwd_kernel(const float* __restrict__ dy, long long dy_stride, const float* __
   for (int i = 0; i < NV; ++i) {
     *reinterpret_cast<float4*>(&red[0][warp][lane * 4]) = pg[i];
     *reinterpret_cast<float4*>(&red[1][warp][lane * 4]) = pb[i];
+    *reinterpret_cast<float4*>(&red[2][warp][lane * 4]) = pc[i];
     __syncthreads();
-    if (threadIdx.x < 256) {
-      const int which = threadIdx.x >> 7, col = threadIdx.x & 127;
+    {
+      const int which = threadIdx.x >> 7, col = threadIdx.x & 127;  // 256 threads: dgamma | dbeta
       float acc = 0.f;
       for (int w = 0; w < warps_per_cta; ++w) acc += red[which][w][col];
       // column of this slab: float4 index (lane + 32 i) -> element (lane*4 + j) + 128 i
       atomicAdd((which ? dbeta : dgamma) + 128 * i + col, acc);
+      if (colsum_out != nullptr && which == 0) {
+        float c = 0.f;
+        for (int w = 0; w < warps_per_cta; ++w) c += red[2][w][col];
+        atomicAdd(colsum_out + 128 * i + col, c);
+      }
     }
     __syncthreads();
   }
@@ -131,10 +147,12 @@ static int ln_fwd_launch(const float* x, long long xs, const float* g, const flo
 template <int NV>
 static int ln_bwd_launch(const float* dy, long long dys, const float* x, long long xs, const float* mean,
                          const float* rstd, const float* g, const float* dres, long long drs, float* dx,
-                         long long dxs, float* dg, float* db, int rows, cudaStream_t st) {
+                         long long dxs, float* dg, float* db, int rows, float* dys2, long long dys2s,
+                         const float* rowscale, int rps, float* colsum_out, cudaStream_t st) {
   int grid = (rows + 7) / 8;
   if (grid > 148 * 2) grid = 148 * 2;
-  ln_bwd_kernel<NV><<<grid, 256, 0, st>>>(dy, dys, x, xs, mean, rstd, g, dres, drs, dx, dxs, dg, db, rows);
+  ln_bwd_kernel<NV><<<grid, 256, 0, st>>>(dy, dys, x, xs, mean, rstd, g, dres, drs, dx, dxs, dg, db, rows, dys2, dys2s,
+                                         rowscale, rps > 0 ? rps : 1, colsum_out);
   return atst_check_launch("ln_bwd_kernel");
 }
 
@@ -156,15 +174,17 @@ int layernorm_forward(const float* x, long long x_stride, const float* gamma, co
 
 int layernorm_backward(const float* dy, long long dy_stride, const float* x, long long x_stride, const float* mean,
                        const float* rstd, const float* gamma, const float* dres, long long dres_stride, float* dx,
-                       long long dx_stride, float* dgamma, float* dbeta, int rows, int D, cudaStream_t st) {
+                       long long dx_stride, float* dgamma, float* dbeta, int rows, int D, float* dys,
+                       long long dys_stride, const float* rowscale, int rows_per_seq, float* colsum_out,
+                       cudaStream_t st) {
   ATST_REQUIRE(rows > 0 && D % 128 == 0 && D <= 1024, "layernorm_backward: unsupported D=%d", D);
   switch (D / 128) {
-    case 1: return ln_bwd_launch<1>(dy, dy_stride, x, x_stride, mean, rstd, gamma, dres, dres_stride, dx, dx_stride, dgamma, dbeta, rows, st);
-    case 2: return ln_bwd_launch<2>(dy, dy_stride, x, x_stride, mean, rstd, gamma, dres, dres_stride, dx, dx_stride, dgamma, dbeta, rows, st);
-    case 3: return ln_bwd_launch<3>(dy, dy_stride, x, x_stride, mean, rstd, gamma, dres, dres_stride, dx, dx_stride, dgamma, dbeta, rows, st);
-    case 4: return ln_bwd_launch<4>(dy, dy_stride, x, x_stride, mean, rstd, gamma, dres, dres_stride, dx, dx_stride, dgamma, dbeta, rows, st);
-    case 6: return ln_bwd_launch<6>(dy, dy_stride, x, x_stride, mean, rstd, gamma, dres, dres_stride, dx, dx_stride, dgamma, dbeta, rows, st);
-    case 8: return ln_bwd_launch<8>(dy, dy_stride, x, x_stride, mean, rstd, gamma, dres, dres_stride, dx, dx_stride, dgamma, dbeta, rows, st);
+    case 1: return ln_bwd_launch<1>(dy, dy_stride, x, x_stride, mean, rstd, gamma, dres, dres_stride, dx, dx_stride, dgamma, dbeta, rows, dys, dys_stride, rowscale, rows_per_seq, colsum_out, st);
+    case 2: return ln_bwd_launch<2>(dy, dy_stride, x, x_stride, mean, rstd, gamma, dres, dres_stride, dx, dx_stride, dgamma, dbeta, rows, dys, dys_stride, rowscale, rows_per_seq, colsum_out, st);
+    case 3: return ln_bwd_launch<3>(dy, dy_stride, x, x_stride, mean, rstd, gamma, dres, dres_stride, dx, dx_stride, dgamma, dbeta, rows, dys, dys_stride, rowscale, rows_per_seq, colsum_out, st);
+    case 4: return ln_bwd_launch<4>(dy, dy_stride, x, x_stride, mean, rstd, gamma, dres, dres_stride, dx, dx_stride, dgamma, dbeta, rows, dys, dys_stride, rowscale, rows_per_seq, colsum_out, st);
+    case 6: return ln_bwd_launch<6>(dy, dy_stride, x, x_stride, mean, rstd, gamma, dres, dres_stride, dx, dx_stride, dgamma, dbeta, rows, dys, dys_stride, rowscale, rows_per_seq, colsum_out, st);
+    case 8: return ln_bwd_launch<8>(dy, dy_stride, x, x_stride, mean, rstd, gamma, dres, dres_stride, dx, dx_stride, dgamma, dbeta, rows, dys, dys_stride, rowscale, rows_per_seq, colsum_out, st);
     default: atst_set_error("layernorm_backward: unsupported D=%d", D); return ATST_ERR_ARG;
   }
 }

@@ -9,7 +9,9 @@ int layernorm_forward(const float* x, long long x_stride, const float* gamma, co
                       cudaStream_t st);
 int layernorm_backward(const float* dy, long long dy_stride, const float* x, long long x_stride, const float* mean,
                        const float* rstd, const float* gamma, const float* dres, long long dres_stride, float* dx,
-                       long long dx_stride, float* dgamma, float* dbeta, int rows, int D, cudaStream_t st);
+                       long long dx_stride, float* dgamma, float* dbeta, int rows, int D, float* dys,
+                       long long dys_stride, const float* rowscale, int rows_per_seq, float* colsum_out,
+                       cudaStream_t st);
 int attention_forward(const float* qkv, float* o, float* lse, const int* lengths, int S, int N, int H, cudaStream_t);
 int attention_backward(const float* qkv, const float* o, const float* d_o, const float* lse, float* delta_ws,
                        float* dqkv, const int* lengths, int S, int N, int H, cudaStream_t);
@@ -32,7 +34,7 @@ int bn_relu_backward_apply(const float* dY, const float* X, const float* mean, c
 int gather_rows(const float* x, const int* idx, float* out, int rows, int D, cudaStream_t st);
 int scatter_rows(const float* src, const int* idx, float* dst, int rows, int D, cudaStream_t st);
 int gelu_forward(const float* u, float* g, long long n, cudaStream_t st);
-int gelu_backward(float* d, const float* u, long long n, cudaStream_t st);
+int gelu_backward(float* d, const float* u, int rows, int cols, float* colsum_out, cudaStream_t st);
 int round_tf32_copy(const float* src, float* dst, long long n, cudaStream_t st);
 int axpy(float* y, const float* x, float a, long long n, cudaStream_t st);
 int byol_loss(const float* student, const float* teacher, int ncrops, int B, float* dstudent, float* acc_ws,

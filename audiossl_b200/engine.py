@@ -143,77 +143,78 @@ class EncoderEngine:
     # ------------------------------------------------------------------ backward
     def backward(self, fp, ws, ctx, d_out):
         """d_out: gradient wrt forward()'s output ([S,D] clip model / [S*N,D] frame model).
-        Accumulates parameter gradients into fp.grad."""
+        Accumulates parameter gradients into fp.grad.
+
+        Every LayerNorm-backward launch also emits, for the branch that consumes its result, the GEMM-ready copy
+        dys = tf32(droppath_scale * dx) and that branch's bias gradient (column sums of dys), so the DropPath
+        backward and the proj / fc2 bias gradients cost no extra pass; the fc1 bias gradient rides on the GELU'
+        pass."""
         px, D, H = self.px, self.D, self.H
         S, P, N, M, tag = ctx["S"], ctx["P"], ctx["N"], ctx["M"], ctx["tag"]
         t = (lambda name, shape: ws.get(tag + "/bwd/" + name, shape))
         nm = px + self.norm_name
-        dxa, dxb = t("dxa", (M, D)), t("dxb", (M, D))
+        dp = ctx["dp"]
+        scales = [(None, None) if (dp is None or dp[i] is None) else dp[i] for i in range(self.depth)]
+        blk = (lambda i: "%sblocks.%d." % (px, i))
+        dxa, dxb, dys = t("dxa", (M, D)), t("dxb", (M, D)), t("dys", (M, D))
+        last = self.depth - 1
         if self.use_cls:
             dxa.zero_()
+            dys.zero_()
             ops.layernorm_bwd(d_out, ctx["x_final"], ctx["meanf"], ctx["rstdf"], fp.p(nm + ".weight"),
-                              fp.g(nm + ".weight"), fp.g(nm + ".bias"), S, D, dx=dxa, x_stride=N * D, dx_stride=N * D)
+                              fp.g(nm + ".weight"), fp.g(nm + ".bias"), S, D, dx=dxa, x_stride=N * D, dx_stride=N * D,
+                              dys=dys, dys_stride=N * D, rowscale=scales[last][1], rows_per_seq=1,
+                              colsum_out=fp.g(blk(last) + "mlp.fc2.bias"))
         else:
             ops.layernorm_bwd(d_out, ctx["x_final"], ctx["meanf"], ctx["rstdf"], fp.p(nm + ".weight"),
-                              fp.g(nm + ".weight"), fp.g(nm + ".bias"), M, D, dx=dxa)
-        dx = dxa
-        other = dxb
-        dp = ctx["dp"]
+                              fp.g(nm + ".weight"), fp.g(nm + ".bias"), M, D, dx=dxa, dys=dys,
+                              rowscale=scales[last][1], rows_per_seq=N, colsum_out=fp.g(blk(last) + "mlp.fc2.bias"))
+        dx, other = dxa, dxb
         dbg = (lambda name, i, t_: self.debug.append((name, i, t_.clone()))) if self.debug is not None else (lambda *a: None)
         dbg("dx_out", self.depth, dx)
         for i in reversed(range(self.depth)):
-            b = "%sblocks.%d." % (px, i)
+            b = blk(i)
             L = ctx["layers"][i]
-            s_attn = s_mlp = None
-            if dp is not None and dp[i] is not None:
-                s_attn, s_mlp = dp[i]
-            # ---- MLP branch: x2 = x1 + s * (g W2^T + b2)
-            dys = self._scaled(dx, s_mlp, N, t("dys", (M, D)))
-            ops.colsum_acc(dys, fp.g(b + "mlp.fc2.bias"))
+            s_attn = scales[i][0]
+            # ---- MLP branch: x2 = x1 + s * (g W2^T + b2); dys = tf32(s * dx), fc2.bias gradient already accumulated
             ops.gemm_tn_acc(dys, L["g"], fp.g(b + "mlp.fc2.weight"))
             if FUSE_GELU:
                 du = ops.gemm_nn(dys, fp.c(b + "mlp.fc2.weight"), epi=ops.EPI_DGELU, aux=L["u"], round_out=True,
                                  out=t("du", (M, 4 * D)))
+                ops.colsum_acc(du, fp.g(b + "mlp.fc1.bias"))
             else:
                 du = ops.gemm_nn(dys, fp.c(b + "mlp.fc2.weight"), out=t("du", (M, 4 * D)))
-                ops.gelu_bwd_(du, L["u"])
+                ops.gelu_bwd_(du, L["u"], colsum_out=fp.g(b + "mlp.fc1.bias"))
             dbg("du", i, du)
-            ops.colsum_acc(du, fp.g(b + "mlp.fc1.bias"))
             ops.gemm_tn_acc(du, L["h2"], fp.g(b + "mlp.fc1.weight"))
             dh2 = ops.gemm_nn(du, fp.c(b + "mlp.fc1.weight"), out=t("dh", (M, D)))
             dx1 = ops.layernorm_bwd(dh2, L["x1"], L["mean2"], L["rstd2"], fp.p(b + "norm2.weight"),
-                                    fp.g(b + "norm2.weight"), fp.g(b + "norm2.bias"), M, D, dres=dx, dx=other)
-            dbg("dh2", i, dh2)
+                                    fp.g(b + "norm2.weight"), fp.g(b + "norm2.bias"), M, D, dres=dx, dx=other,
+                                    dys=dys, rowscale=s_attn, rows_per_seq=N, colsum_out=fp.g(b + "attn.proj.bias"))
             dbg("dx1", i, dx1)
             # ---- attention branch: x1 = x + s * (o Wp^T + bp)
-            dys = self._scaled(dx1, s_attn, N, t("dys", (M, D)))
-            ops.colsum_acc(dys, fp.g(b + "attn.proj.bias"))
             ops.gemm_tn_acc(dys, L["o"], fp.g(b + "attn.proj.weight"))
             d_o = ops.gemm_nn(dys, fp.c(b + "attn.proj.weight"), round_out=True, out=t("d_o", (M, D)))
             dqkv = ops.attention_bwd(L["qkv"], L["o"], d_o, L["lse"], S, N, H, ctx["key_len"],
                                      dqkv=t("dqkv", (M, 3 * D)), delta_ws=t("delta", (S, H, N)))
-            dbg("d_o", i, d_o)
             dbg("dqkv", i, dqkv)
             ops.gemm_tn_acc(dqkv, L["h"], fp.g(b + "attn.qkv.weight"))
             dh = ops.gemm_nn(dqkv, fp.c(b + "attn.qkv.weight"), out=t("dh", (M, D)))
-            ops.layernorm_bwd(dh, L["x"], L["mean1"], L["rstd1"], fp.p(b + "norm1.weight"), fp.g(b + "norm1.weight"),
-                              fp.g(b + "norm1.bias"), M, D, dres=dx1, dx=dx)
+            if i > 0:  # the block input feeds block i-1's MLP branch
+                ops.layernorm_bwd(dh, L["x"], L["mean1"], L["rstd1"], fp.p(b + "norm1.weight"),
+                                  fp.g(b + "norm1.weight"), fp.g(b + "norm1.bias"), M, D, dres=dx1, dx=dx, dys=dys,
+                                  rowscale=scales[i - 1][1], rows_per_seq=N,
+                                  colsum_out=fp.g(blk(i - 1) + "mlp.fc2.bias"))
+            else:
+                ops.layernorm_bwd(dh, L["x"], L["mean1"], L["rstd1"], fp.p(b + "norm1.weight"),
+                                  fp.g(b + "norm1.weight"), fp.g(b + "norm1.bias"), M, D, dres=dx1, dx=dx)
             dbg("dx_in", i, dx)
-            # dx now holds the gradient wrt the block input; `other` is free again
         dpe = t("dpe", (S * P, D))
         ops.tokens_bwd(dx, dpe, fp.g(px + "pos_embed"), fp.g(px + "cls_token") if self.use_cls else None, S, P, D,
                        use_cls=self.use_cls, mask=ctx["mask"],
                        dmask_embed=fp.g(px + "mask_embed") if ctx["mask"] is not None else None)
         ops.colsum_acc(dpe, fp.g(px + "patch_embed.patch_embed.bias"))
         ops.gemm_tn_acc(dpe, ctx["patches"], fp.g(px + "patch_embed.patch_embed.weight"))
-
-    def _scaled(self, dy, scale, rows_per_seq, buf):
-        """s[row // rows_per_seq] * dy (DropPath backward); identity when the path is never dropped."""
-        if scale is None:
-            return dy
-        M, D = dy.shape
-        torch.mul(dy.view(-1, rows_per_seq, D), scale.view(-1, 1, 1), out=buf.view(-1, rows_per_seq, D))
-        return buf
 
 
 class HeadEngine:

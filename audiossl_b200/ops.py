@@ -125,7 +125,8 @@ def layernorm_fwd(x, gamma, beta, rows, D, x_stride=None, out=None, out_stride=N
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, rows, D, dres=None, dx=None, dy_stride=None,
-                  x_stride=None, dres_stride=None, dx_stride=None):
+                  x_stride=None, dres_stride=None, dx_stride=None, dys=None, dys_stride=None, rowscale=None,
+                  rows_per_seq=1, colsum_out=None):
     dy_stride = D if dy_stride is None else dy_stride
     x_stride = D if x_stride is None else x_stride
     dres_stride = D if dres_stride is None else dres_stride
@@ -134,7 +135,8 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, rows, D, dres=None, d
     dx_stride = D if dx_stride is None else dx_stride
     check(_lib.lib().atst_layernorm_backward(ptr(dy), dy_stride, ptr(x), x_stride, ptr(mean), ptr(rstd), ptr(gamma),
                                              ptr(dres), dres_stride, ptr(dx), dx_stride, ptr(dgamma), ptr(dbeta),
-                                             rows, D, _lib.stream()), "atst_layernorm_backward")
+                                             rows, D, ptr(dys), D if dys_stride is None else dys_stride, ptr(rowscale),
+                                             rows_per_seq, ptr(colsum_out), _lib.stream()), "atst_layernorm_backward")
     _count(1)
     return dx
 
@@ -298,8 +300,9 @@ def gelu_fwd(u, out):
     return out
 
 
-def gelu_bwd_(d, u):
-    check(_lib.lib().atst_gelu_backward(ptr(d), ptr(u), d.numel(), _lib.stream()), "atst_gelu_backward")
+def gelu_bwd_(d, u, colsum_out=None):
+    rows, cols = d.shape
+    check(_lib.lib().atst_gelu_backward(ptr(d), ptr(u), rows, cols, ptr(colsum_out), _lib.stream()), "atst_gelu_backward")
     _count(1)
     return d
 

@@ -61,10 +61,14 @@ int atst_gemm_mn_debug(int nn, const float* A, int lda, const float* B, int ldb,
 int atst_layernorm_forward(const float* x, long long x_stride, const float* gamma, const float* beta, float* y,
                            long long y_stride, float* mean, float* rstd, int rows, int D, float eps, int round_out,
                            void* stream);
+/* backward: dx = dres + LN'(dy); dgamma/dbeta accumulate.  Optional GEMM-ready copy for the branch that consumes dx:
+ * dys = tf32(rowscale[row / rows_per_seq] * dx) (DropPath backward) and colsum_out += column sums of dys
+ * (the consumer Linear's bias gradient).  Pass NULLs to skip. */
 int atst_layernorm_backward(const float* dy, long long dy_stride, const float* x, long long x_stride,
                             const float* mean, const float* rstd, const float* gamma, const float* dres,
                             long long dres_stride, float* dx, long long dx_stride, float* dgamma, float* dbeta,
-                            int rows, int D, void* stream);
+                            int rows, int D, float* dys, long long dys_stride, const float* rowscale,
+                            int rows_per_seq, float* colsum_out, void* stream);
 
 /* ---- attention core with key padding by length (audiossl/modules/transformer.py:107-121,152-159).
  *   qkv [S*N, 3*H*64] as written by the qkv Linear; o [S*N, H*64]; lse [S,H,N]; lengths int32 [S] or NULL */
@@ -116,7 +120,8 @@ int atst_scatter_rows(const float* src, const int* idx, float* dst, int rows, in
 
 /* ---- exact-erf GELU as separate passes (audiossl/modules/transformer.py:78,88): g = gelu(u); d *= gelu'(u) */
 int atst_gelu_forward(const float* u, float* g, long long n, void* stream);
-int atst_gelu_backward(float* d, const float* u, long long n, void* stream);
+/* d[rows, cols] *= gelu'(u) in place (tf32-rounded); colsum_out (nullable) += column sums of the result */
+int atst_gelu_backward(float* d, const float* u, int rows, int cols, float* colsum_out, void* stream);
 
 /* ---- misc */
 int atst_round_tf32(const float* src, float* dst, long long n, void* stream);

@@ -171,9 +171,15 @@ def sec_ln():
         y, mean, rstd = ops.layernorm_fwd(x, g, b, rows, D, round_out=False)
         dg, db = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
         dres = torch.randn(rows, D, device="cuda")
-        dx = ops.layernorm_bwd(dy, x, mean, rstd, g, dg, db, rows, D, dres=dres)
-        print("ln D=%4d fwd=%.2e dx=%.2e dg=%.2e db=%.2e" % (D, rel_err(y, y_ref), rel_err(dx, xr.grad + dres),
-                                                             rel_err(dg, gr.grad), rel_err(db, br.grad)))
+        dys = torch.empty(rows, D, device="cuda")
+        cs = torch.zeros(D, device="cuda")
+        sc = torch.rand((rows + 36) // 37, device="cuda") + 0.5
+        dx = ops.layernorm_bwd(dy, x, mean, rstd, g, dg, db, rows, D, dres=dres, dys=dys, rowscale=sc, rows_per_seq=37,
+                               colsum_out=cs)
+        ref_dys = (xr.grad + dres) * sc.repeat_interleave(37)[:rows, None]
+        print("ln D=%4d fwd=%.2e dx=%.2e dg=%.2e db=%.2e dys=%.2e colsum=%.2e" %
+              (D, rel_err(y, y_ref), rel_err(dx, xr.grad + dres), rel_err(dg, gr.grad), rel_err(db, br.grad),
+               rel_err(dys, ref_dys), rel_err(cs, ref_dys.sum(0))))
 
 
 def sec_attn():
@@ -343,7 +349,8 @@ def sec_gemm_perf():
     u = torch.randn(M, 3072, device="cuda")
     gg = torch.empty_like(u)
     tm(lambda: ops.gelu_fwd(u, gg), 1.0, "gelu_fwd elementwise [M,3072]")
-    tm(lambda: ops.gelu_bwd_(gg, u), 1.0, "gelu_bwd elementwise [M,3072]")
+    cs = torch.zeros(3072, device="cuda")
+    tm(lambda: ops.gelu_bwd_(gg, u, colsum_out=cs), 1.0, "gelu_bwd+colsum elementwise [M,3072]")
     del A, W, C, u, gg
     for pf in (0,):
         _lib.lib().atst_set_option(b"gemm_l2_prefetch", pf)

@@ -53,7 +53,7 @@ for i in reversed(range(depth)):
     name = ("dx_out", depth) if i == depth - 1 else ("dx_in", i + 1)
     mine = dbg[name].reshape(g.shape)
     print("grad wrt block %d output: rel %.3e  (|ref| %.3e |mine| %.3e)" % (i, rel(mine, g), g.norm(), mine.norm()))
-for k in ("du", "dh2", "dx1", "d_o", "dqkv", "dx_in"):
+for k in ("du", "dx1", "dqkv", "dx_in"):
     for i in reversed(range(depth)):
         print(k, i, "norm %.4e" % dbg[(k, i)].norm().item())
 print("---- parameter grads")
