@@ -195,13 +195,21 @@ def run_ours(args):
     lengths = [torch.full((B,), n // 160 + 1, device=dev, dtype=torch.int64)] * 2
     stage = torch.empty_like(wav_dev)
 
+    mel_events = []
+
     def step(i, from_host):
         if from_host:
             stage.copy_(wav_host, non_blocking=True)
             src = stage
         else:
             src = wav_dev
+        if ops.STATS["time_gemms"]:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         crops = [mel(src[0]), mel(src[1])]
+        if ops.STATS["time_gemms"]:
+            ev[1].record()
+            mel_events.append(ev)
         lm.global_step = i
         loss = lm.training_step(((crops, lengths), None), i)
         opt.zero_grad()
@@ -267,11 +275,13 @@ def run_ours(args):
             for tag, (cnt, t_ms, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
                 fh.write("%-28s n=%3d  %8.3f ms  %7.1f TFLOP/s\n" % (tag, cnt, t_ms, fl / t_ms / 1e9))
 
+    mel_ms = sum(a.elapsed_time(b2) for a, b2 in mel_events)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     pk = peaks()
+    mel_bytes = 2 * B * (4 * n + 4 * 64 * (n // 160 + 1))  # 896 256 B per 10 s clip-view
     ms_step = ms / args.steps
     value = B * world / (ms_step / 1e3)
     e2e_val = B * world / (ms_e2e / args.steps / 1e3)
@@ -296,6 +306,11 @@ def run_ours(args):
                      "gemm_share_of_step": gemm_ms / ms_step,
                      "algorithmic_gemm_tflop_per_step": gemm_flops_step / 1e12,
                      "model_flops_utilisation_of_step": STEP_GFLOP_PER_CLIP * 1e9 * B / (ms_step / 1e3) / 1e12 / pk["tflops"]},
+        "roofline_mel": {"bound": "hbm", "kernel": "mel_db_kernel + mel_norm_kernel (fused STFT/mel/dB/MinMax)",
+                         "achieved": mel_bytes / (mel_ms / 1e3) / 1e9 if mel_ms > 0 else 0.0, "peak": pk["hbm_gbs"],
+                         "unit": "GB/s", "frac": (mel_bytes / (mel_ms / 1e3) / 1e9 / pk["hbm_gbs"]) if mel_ms > 0 else 0.0,
+                         "ms_per_step": mel_ms, "algorithmic_bytes_per_step": mel_bytes, "traffic": None,
+                         "note": "FFT issue / smem bound (40 flop/B), not HBM bound"},
     }
     if world == 1 and not args.no_cpu_baseline:
         cores = pick_cpu_threads()

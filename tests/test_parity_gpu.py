@@ -114,6 +114,42 @@ def test_attention_matches_reference_formula():
     assert rel(dqkv, q.grad) < 1e-3
 
 
+def test_layernorm_backward_fused_outputs():
+    from audiossl_b200 import ops
+    torch.manual_seed(0)
+    rows, D, rps = 333, 768, 37
+    x = torch.randn(rows, D, device="cuda") * 2 + 0.5
+    g, b = torch.randn(D, device="cuda"), torch.randn(D, device="cuda")
+    xr, gr, br = x.clone().requires_grad_(True), g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    dy = torch.randn(rows, D, device="cuda")
+    torch.nn.functional.layer_norm(xr, (D,), gr, br, 1e-6).backward(dy)
+    y, mean, rstd = ops.layernorm_fwd(x, g, b, rows, D, round_out=False)
+    dg, db, cs = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+    dres, dys = torch.randn(rows, D, device="cuda"), torch.empty(rows, D, device="cuda")
+    sc = torch.rand((rows + rps - 1) // rps, device="cuda") + 0.5
+    dx = ops.layernorm_bwd(dy, x, mean, rstd, g, dg, db, rows, D, dres=dres, dys=dys, rowscale=sc, rows_per_seq=rps,
+                           colsum_out=cs)
+    ref_dx = xr.grad + dres
+    ref_dys = ref_dx * sc.repeat_interleave(rps)[:rows, None]
+    assert rel(dx, ref_dx) < 1e-5 and rel(dg, gr.grad) < 1e-5 and rel(db, br.grad) < 1e-5
+    assert rel(dys, ref_dys) < 1e-3 and rel(cs, ref_dys.sum(0)) < 1e-3  # dys is tf32-rounded
+
+
+def test_gelu_passes_match_torch():
+    from audiossl_b200 import ops
+    torch.manual_seed(0)
+    u = torch.randn(300, 512, device="cuda") * 2
+    ur = u.clone().requires_grad_(True)
+    gref = torch.nn.functional.gelu(ur)
+    d = torch.randn_like(u)
+    gref.backward(d)
+    g = ops.gelu_fwd(u, torch.empty_like(u))
+    cs = torch.zeros(512, device="cuda")
+    dd = ops.gelu_bwd_(d.clone(), u, colsum_out=cs)
+    assert rel(g, gref) < 1e-3 and rel(dd, ur.grad) < 1e-3 and rel(cs, ur.grad.sum(0)) < 1e-3
+    assert (g - gref).abs().max().item() < 2e-3  # tf32 rounding of outputs up to |u| ~ 8
+
+
 # --------------------------------------------------------------------------- full model vs oracle / golden
 def build_cuda_model(case):
     from audiossl_b200.models.atst import ATST
