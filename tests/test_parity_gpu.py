@@ -147,7 +147,7 @@ def test_gelu_passes_match_torch():
     cs = torch.zeros(512, device="cuda")
     dd = ops.gelu_bwd_(d.clone(), u, colsum_out=cs)
     assert rel(g, gref) < 1e-3 and rel(dd, ur.grad) < 1e-3 and rel(cs, ur.grad.sum(0)) < 1e-3
-    assert (g - gref).abs().max().item() < 2e-3  # tf32 rounding of outputs up to |u| ~ 8
+    assert (g - gref).abs().max().item() < 5e-3  # tf32 rounding of outputs up to |u| ~ 8 (8 * 2^-11)
 
 
 # --------------------------------------------------------------------------- full model vs oracle / golden
