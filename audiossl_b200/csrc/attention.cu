@@ -2,7 +2,7 @@
 // mask) v, never materialising [S,H,N,N].  Flash-style, tf32 tensor cores (mma.sync.m16n8k8), fp32 softmax.
 //
 // One templated kernel covers forward and both halves of the backward pass.  A CTA (4 warps) owns 64
-// "row" items of one (sequence, head) and streams over 64-wide "column" blocks held in padded smem:
+// "row" items of one (sequence, head) and streams over 64-wide "column" blocks held in swizzled smem:
 //   MODE 0 forward : rows = queries, cols = keys.   S = Q K^T -> online softmax -> O = P V, LSE (log2 domain)
 //   MODE 1 dQ      : rows = queries, cols = keys.   P = exp2(S c - L_row); dP = dO V^T; dS = P (dP - delta_row)
 //                                                   dQ = scale * dS K
@@ -17,7 +17,7 @@ namespace atst {
 constexpr int kAttnRows = 64;
 constexpr int kAttnCols = 64;
 constexpr int kHd = 64;
-constexpr int kLds = 68;  // padded smem row (floats): conflict-free fragment loads
+constexpr int kLds = 64;  // smem row (floats), unpadded: 16-byte chunks are XOR-swizzled by row (see swz())
 
 struct AttnParams {
   const float* qkv;   // [S*N, 3D]  q | k | v, head h at column h*64
@@ -49,7 +49,16 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool va
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// stage rows [r0, r0+64) x 64 floats (global row stride ld) into smem [64][kLds]; rows >= nrows are zero
+// Shared-memory blocks are [64 rows][64 floats] with the sixteen 16-byte chunks of a row XOR-swizzled by
+//   swz(r) = bit1(r) | ((bit2(r) ^ bit0(r)) << 2)
+// which makes every 128-bit fragment load below bank-conflict free: the row-contiguous loads of mma_abt
+// (8 lanes of a phase = rows {2j, 2j+1} x chunks t) as well as the key-row loads of mma_py (rows 8ks+2t).
+__device__ __forceinline__ int swz(int r) { return ((r >> 1) & 1) | ((((r >> 2) ^ r) & 1) << 2); }
+__device__ __forceinline__ float4 ld4(const float* blk, int r, int chunk) {
+  return *reinterpret_cast<const float4*>(blk + r * kLds + ((chunk ^ swz(r)) << 2));
+}
+
+// stage rows [r0, r0+64) x 64 floats (global row stride ld) into a swizzled smem block; rows >= nrows are zero
 __device__ __forceinline__ void stage_block(float* dst, const float* src, int ld, int r0, int nrows, int tid) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -57,50 +66,75 @@ __device__ __forceinline__ void stage_block(float* dst, const float* src, int ld
     const int r = c >> 4, ch = c & 15;
     const bool ok = (r0 + r) < nrows;
     const float* g = src + static_cast<size_t>(ok ? (r0 + r) : 0) * ld + ch * 4;
-    cp_async16(dst + r * kLds + ch * 4, g, ok);
+    cp_async16(dst + r * kLds + ((ch ^ swz(r)) << 2), g, ok);
   }
 }
 
-// acc[nt] += A(16 rows of R, 64 wide) . Y^T  for the 8 column tiles of a 64-row block Y
-__device__ __forceinline__ void mma_abt(float (&acc)[8][4], const float* R, const float* Y, int g, int t) {
+// acc[nt] += A(rows ra0+g, ra0+g+8 of block R, 64 wide) . Y^T for the 8 column tiles of a 64-row block Y.
+// The contraction index (head dim) is permuted so that one 128-bit load feeds two k-steps: within a group of 16,
+// lane t supplies physical indices 4t..4t+3 = logical (t, t+4) of step 0 and (t, t+4) of step 1; A and B use the
+// same permutation, so the sum is unchanged.
+__device__ __forceinline__ void mma_abt(float (&acc)[8][4], const float* R, int ra0, const float* Y, int g, int t) {
 #pragma unroll
-  for (int ks = 0; ks < 8; ++ks) {
-    const uint32_t a0 = __float_as_uint(R[g * kLds + 8 * ks + t]);
-    const uint32_t a1 = __float_as_uint(R[(g + 8) * kLds + 8 * ks + t]);
-    const uint32_t a2 = __float_as_uint(R[g * kLds + 8 * ks + t + 4]);
-    const uint32_t a3 = __float_as_uint(R[(g + 8) * kLds + 8 * ks + t + 4]);
+  for (int kp = 0; kp < 4; ++kp) {
+    const float4 x0 = ld4(R, ra0 + g, 4 * kp + t);
+    const float4 x1 = ld4(R, ra0 + g + 8, 4 * kp + t);
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const uint32_t b0 = __float_as_uint(Y[(8 * nt + g) * kLds + 8 * ks + t]);
-      const uint32_t b1 = __float_as_uint(Y[(8 * nt + g) * kLds + 8 * ks + t + 4]);
-      mma_tf32(acc[nt], a0, a1, a2, a3, b0, b1);
+      const float4 y = ld4(Y, 8 * nt + g, 4 * kp + t);
+      mma_tf32(acc[nt], __float_as_uint(x0.x), __float_as_uint(x1.x), __float_as_uint(x0.y), __float_as_uint(x1.y),
+               __float_as_uint(y.x), __float_as_uint(y.y));
+      mma_tf32(acc[nt], __float_as_uint(x0.z), __float_as_uint(x1.z), __float_as_uint(x0.w), __float_as_uint(x1.w),
+               __float_as_uint(y.z), __float_as_uint(y.w));
     }
   }
 }
 // acc[dt] += P(16 x 64, C-fragment layout, columns = rows of Y) . Y(64 x 64)
-// C fragment columns (2t, 2t+1) of tile ks are used as k-indices (t, t+4); Y rows are permuted to match.
+//  * C fragment columns (2t, 2t+1) of tile ks are used as k-indices (t, t+4): Y rows 8ks+2t / 8ks+2t+1.
+//  * output columns are permuted: logical column j of tile dt  <->  physical column 8j + dt, so that the eight
+//    tiles' B values of one Y row are contiguous (two 128-bit loads per row).  Thread (g,t) therefore ends up
+//    with physical columns 16t..16t+7 in acc[0..7][0|2] and 16t+8..16t+15 in acc[0..7][1|3].
 __device__ __forceinline__ void mma_py(float (&acc)[8][4], const float (&P)[8][4], const float* Y, int g, int t) {
 #pragma unroll
   for (int ks = 0; ks < 8; ++ks) {
     const uint32_t a0 = tf32_bits(P[ks][0]), a1 = tf32_bits(P[ks][2]);
     const uint32_t a2 = tf32_bits(P[ks][1]), a3 = tf32_bits(P[ks][3]);
-#pragma unroll
-    for (int dt = 0; dt < 8; ++dt) {
-      const uint32_t b0 = __float_as_uint(Y[(8 * ks + 2 * t) * kLds + 8 * dt + g]);
-      const uint32_t b1 = __float_as_uint(Y[(8 * ks + 2 * t + 1) * kLds + 8 * dt + g]);
-      mma_tf32(acc[dt], a0, a1, a2, a3, b0, b1);
-    }
+    const int r = 8 * ks + 2 * t;
+    const float4 u0 = ld4(Y, r, 2 * g), u1 = ld4(Y, r, 2 * g + 1);
+    const float4 v0 = ld4(Y, r + 1, 2 * g), v1 = ld4(Y, r + 1, 2 * g + 1);
+    mma_tf32(acc[0], a0, a1, a2, a3, __float_as_uint(u0.x), __float_as_uint(v0.x));
+    mma_tf32(acc[1], a0, a1, a2, a3, __float_as_uint(u0.y), __float_as_uint(v0.y));
+    mma_tf32(acc[2], a0, a1, a2, a3, __float_as_uint(u0.z), __float_as_uint(v0.z));
+    mma_tf32(acc[3], a0, a1, a2, a3, __float_as_uint(u0.w), __float_as_uint(v0.w));
+    mma_tf32(acc[4], a0, a1, a2, a3, __float_as_uint(u1.x), __float_as_uint(v1.x));
+    mma_tf32(acc[5], a0, a1, a2, a3, __float_as_uint(u1.y), __float_as_uint(v1.y));
+    mma_tf32(acc[6], a0, a1, a2, a3, __float_as_uint(u1.z), __float_as_uint(v1.z));
+    mma_tf32(acc[7], a0, a1, a2, a3, __float_as_uint(u1.w), __float_as_uint(v1.w));
   }
+}
+// store the permuted accumulator of mma_py: row `row`, 16 contiguous columns starting at 16t
+__device__ __forceinline__ void store_py_row(float* dst, const float (&acc)[8][4], int half, float scale) {
+  // half 0: fragment slots (0,1) = row g ; half 1: slots (2,3) = row g+8
+  const int s0 = half * 2;
+  float4 o0 = make_float4(acc[0][s0], acc[1][s0], acc[2][s0], acc[3][s0]);
+  float4 o1 = make_float4(acc[4][s0], acc[5][s0], acc[6][s0], acc[7][s0]);
+  float4 o2 = make_float4(acc[0][s0 + 1], acc[1][s0 + 1], acc[2][s0 + 1], acc[3][s0 + 1]);
+  float4 o3 = make_float4(acc[4][s0 + 1], acc[5][s0 + 1], acc[6][s0 + 1], acc[7][s0 + 1]);
+  float4* q = reinterpret_cast<float4*>(dst);
+  auto rnd = [&](float4 v) {
+    return make_float4(round_tf32(v.x * scale), round_tf32(v.y * scale), round_tf32(v.z * scale), round_tf32(v.w * scale));
+  };
+  q[0] = rnd(o0); q[1] = rnd(o1); q[2] = rnd(o2); q[3] = rnd(o3);
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(128) attn_kernel(AttnParams p) {
   extern __shared__ float sm[];
-  float* sR1 = sm;                          // [64][68] row operand 1
-  float* sR2 = sR1 + kAttnRows * kLds;      // [64][68] row operand 2 (backward only)
-  float* sY1 = sR2 + kAttnRows * kLds;      // [64][68]
-  float* sY2 = sY1 + kAttnCols * kLds;      // [64][68]
-  float* sStat = sY2 + kAttnCols * kLds;    // [2][64] column stats (MODE 2): lse, delta
+  float* sR1 = sm;                                                  // [64][64] row operand 1
+  float* sR2 = sR1 + kAttnRows * kLds;                              // [64][64] row operand 2 (backward only)
+  float* sY1 = (MODE == 0) ? sR2 : sR2 + kAttnRows * kLds;          // forward has no second row operand
+  float* sY2 = sY1 + kAttnCols * kLds;
+  float* sStat = sY2 + kAttnCols * kLds;                            // [2][64] column stats (MODE 2): lse, delta
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int r0 = blockIdx.x * kAttnRows;
@@ -124,8 +158,7 @@ __global__ void __launch_bounds__(128) attn_kernel(AttnParams p) {
   stage_block(sR1, r1p, ld3, r0, N, tid);
   if (MODE != 0) stage_block(sR2, r2p, r2ld, r0, N, tid);
 
-  const float* R1w = sR1 + warp * 16 * kLds;
-  const float* R2w = sR2 + warp * 16 * kLds;
+  const int ra0 = warp * 16;  // this warp's first row inside the row blocks
   const int row_a = r0 + warp * 16 + g, row_b = row_a + 8;  // the two rows this thread's C fragments cover
 
   float acc1[8][4], acc2[8][4];
@@ -162,7 +195,7 @@ __global__ void __launch_bounds__(128) attn_kernel(AttnParams p) {
     for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) sc[i][j] = 0.f;
-    mma_abt(sc, R1w, sY1, g, t);
+    mma_abt(sc, sR1, ra0, sY1, g, t);
 
     if (MODE == 0) {
       // online softmax over this key block; thread holds cols 8nt+2t, +1 of rows g (c0,c1) and g+8 (c2,c3)
@@ -229,7 +262,7 @@ __global__ void __launch_bounds__(128) attn_kernel(AttnParams p) {
       for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) dp[i][j] = 0.f;
-      mma_abt(dp, R2w, sY2, g, t);  // dP = dO V^T   |   dP^T = V dO^T
+      mma_abt(dp, sR2, ra0, sY2, g, t);  // dP = dO V^T   |   dP^T = V dO^T
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
         if (MODE == 1) {
@@ -253,37 +286,19 @@ __global__ void __launch_bounds__(128) attn_kernel(AttnParams p) {
       if (row_a < N) lse[row_a] = m_a * c + log2f(l_a);
       if (row_b < N) lse[row_b] = m_b * c + log2f(l_b);
     }
-    float* op = p.out_o + tok0 * D + h * kHd;
-#pragma unroll
-    for (int dt = 0; dt < 8; ++dt) {
-      const int col = 8 * dt + 2 * t;
-      if (row_a < N)
-        *reinterpret_cast<float2*>(op + static_cast<size_t>(row_a) * D + col) =
-            make_float2(round_tf32(acc1[dt][0] * inv_a), round_tf32(acc1[dt][1] * inv_a));
-      if (row_b < N)
-        *reinterpret_cast<float2*>(op + static_cast<size_t>(row_b) * D + col) =
-            make_float2(round_tf32(acc1[dt][2] * inv_b), round_tf32(acc1[dt][3] * inv_b));
-    }
+    float* op = p.out_o + tok0 * D + h * kHd + 16 * t;
+    if (row_a < N) store_py_row(op + static_cast<size_t>(row_a) * D, acc1, 0, inv_a);
+    if (row_b < N) store_py_row(op + static_cast<size_t>(row_b) * D, acc1, 1, inv_b);
   } else {
-    float* d1 = p.dqkv + tok0 * ld3 + h * kHd + (MODE == 2 ? D : 0);  // dQ or dK
-    float* d2 = p.dqkv + tok0 * ld3 + h * kHd + 2 * D;                // dV
-#pragma unroll
-    for (int dt = 0; dt < 8; ++dt) {
-      const int col = 8 * dt + 2 * t;
-      if (row_a < N) {
-        *reinterpret_cast<float2*>(d1 + static_cast<size_t>(row_a) * ld3 + col) =
-            make_float2(round_tf32(acc1[dt][0] * p.scale), round_tf32(acc1[dt][1] * p.scale));
-        if (MODE == 2)
-          *reinterpret_cast<float2*>(d2 + static_cast<size_t>(row_a) * ld3 + col) =
-              make_float2(round_tf32(acc2[dt][0]), round_tf32(acc2[dt][1]));
-      }
-      if (row_b < N) {
-        *reinterpret_cast<float2*>(d1 + static_cast<size_t>(row_b) * ld3 + col) =
-            make_float2(round_tf32(acc1[dt][2] * p.scale), round_tf32(acc1[dt][3] * p.scale));
-        if (MODE == 2)
-          *reinterpret_cast<float2*>(d2 + static_cast<size_t>(row_b) * ld3 + col) =
-              make_float2(round_tf32(acc2[dt][2]), round_tf32(acc2[dt][3]));
-      }
+    float* d1 = p.dqkv + tok0 * ld3 + h * kHd + (MODE == 2 ? D : 0) + 16 * t;  // dQ or dK
+    float* d2 = p.dqkv + tok0 * ld3 + h * kHd + 2 * D + 16 * t;                // dV
+    if (row_a < N) {
+      store_py_row(d1 + static_cast<size_t>(row_a) * ld3, acc1, 0, p.scale);
+      if (MODE == 2) store_py_row(d2 + static_cast<size_t>(row_a) * ld3, acc2, 0, 1.0f);
+    }
+    if (row_b < N) {
+      store_py_row(d1 + static_cast<size_t>(row_b) * ld3, acc1, 1, p.scale);
+      if (MODE == 2) store_py_row(d2 + static_cast<size_t>(row_b) * ld3, acc2, 1, 1.0f);
     }
   }
 }
@@ -306,18 +321,18 @@ __global__ void attn_delta_kernel(const float* __restrict__ o, const float* __re
   }
 }
 
-constexpr int kAttnSmem = (4 * 64 * kLds + 128) * 4;
+template <int MODE> constexpr int attn_smem() { return ((MODE == 0 ? 3 : 4) * 64 * kLds + 128) * 4; }
 
 template <int MODE>
 static int launch_attn(const AttnParams& p, int S, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    cudaError_t e = cudaFuncSetAttribute(attn_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem<MODE>());
     if (e != cudaSuccess) { atst_set_error("attn smem attr: %s", cudaGetErrorString(e)); return ATST_ERR_CUDA; }
     configured = true;
   }
   dim3 grid((p.N + kAttnRows - 1) / kAttnRows, p.H, S);
-  attn_kernel<MODE><<<grid, 128, kAttnSmem, stream>>>(p);
+  attn_kernel<MODE><<<grid, 128, attn_smem<MODE>(), stream>>>(p);
   return atst_check_launch("attn_kernel");
 }
 

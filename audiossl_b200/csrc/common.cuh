@@ -55,6 +55,9 @@ __device__ __forceinline__ void st_global_v8(float* p, const float* r) {
                "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7])
                : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p) : "memory");
+}
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }

@@ -34,7 +34,8 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
   static constexpr int kEpiBytes = 0;  // epilogue goes TMEM -> registers -> global, no smem staging
-  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kEpiBytes + 256;
+  static constexpr int kBiasBytes = 2 * 256 * 4;  // per accumulator stage: the tile's bias slice
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kEpiBytes + 256 + kBiasBytes;
   static constexpr int kTmemCols = 2 * BLOCK_N;  // 512 or 256: power of two
 };
 
@@ -79,6 +80,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull_bar = bars + 2 * Cfg::kStages; // [2]
   uint64_t* tempty_bar = tfull_bar + 2;          // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* smem_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2][256]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -234,6 +236,18 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const float* side_row = side_ptr ? side_ptr + static_cast<size_t>(gm) * side_ld : nullptr;
       float* c_row = p.C + static_cast<size_t>(gm) * p.ldc;
       float* aux_row = (p.epi == EPI_GELU) ? p.aux + static_cast<size_t>(gm) * p.ldaux : nullptr;
+      // while this tile's main loop is still running: pull the side-input rows into L2 and stage the bias slice
+      if (side_row != nullptr && row_ok) {
+#pragma unroll
+        for (int c = 0; c < BLOCK_N / 32; ++c)
+          if (n0 + c * 32 < p.N) prefetch_l2(side_row + n0 + c * 32);
+      }
+      float* sbias = smem_bias + acc * 256;
+      if (p.bias != nullptr) {
+        const int t128 = ew * 32 + lane;
+        for (int j = t128; j < BLOCK_N; j += 128) sbias[j] = (n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(ew * 32) << 16);
@@ -270,8 +284,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * j + e]);
           if (p.bias != nullptr) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + gn + 8 * j));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + gn + 8 * j + 4));
+            const float4 b0 = *reinterpret_cast<const float4*>(sbias + c * 32 + 8 * j);  // smem broadcast
+            const float4 b1 = *reinterpret_cast<const float4*>(sbias + c * 32 + 8 * j + 4);
             v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
             v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
           }
