@@ -25,6 +25,21 @@ CLIP_SECONDS = 10.0
 SR = 16000
 STEP_GFLOP_PER_CLIP = 360.5  # BASELINE.md section 4, config 2 (teacher fwd + student fwd + student bwd)
 
+# BASELINE.json configs (per-GPU shapes).  c2 is the benchmark line; the others are run for the record
+# (profiles/) with `--config`.  crops: list of (seconds, count); gflop: algorithmic step GFLOP per clip
+CONFIGS = {
+    "c1": dict(kind="clip", arch="small", crops=[(1.0, 2)], batch=8, gflop=9.0,
+               name="ATST-small, 1 s clips, batch 8"),
+    "c2": dict(kind="clip", arch="base", crops=[(10.0, 2)], batch=256, gflop=360.5,
+               name="ATST-base, 10 s clips, 256 clips/GPU"),
+    "c3": dict(kind="clip", arch="base", crops=[(6.0, 2), (1.0, 6)], batch=128, gflop=292.5,
+               name="ATST-base, 2x6 s + 6x1 s crops, 128 clips/GPU"),
+    "c4": dict(kind="frame", arch="base", crops=[(10.0, 2)], batch=64, gflop=370.0,
+               name="ATST-Frame base, 10 s clips, 64 clips/GPU"),
+    "c5": dict(kind="clip", arch="large", crops=[(6.0, 2)], batch=256, gflop=748.0,
+               name="ATST-large, 6 s clips, 256 clips/GPU"),
+}
+
 
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -156,8 +171,8 @@ def run_reference(args):
             "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "ATST-base, 10 s 16 kHz clips, 64 mel, 2 views, DropPath 0.1; CPU sample of %d clips/step"
-                                   % batch},
+            "config": {"workload": "ATST-base, 10 s clips, 256 clips/GPU [c2], 16 kHz, 64 mel, 2 crops, DropPath 0.1; "
+                                   "CPU sample of %d clips/step" % batch},
             "cpu_baseline": {"value": val, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
                              "sample": "%d steps of %d clips (oracle port of the reference algorithm, torch CPU fp32)"
                                        % (args.steps, batch)},
@@ -181,37 +196,59 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B = args.batch
-    n = int(CLIP_SECONDS * SR)
+    cfg = CONFIGS[args.config]
+    B = args.batch if args.batch > 0 else cfg["batch"]
+    arch = args.arch or cfg["arch"]
     torch.manual_seed(0)
-    lm = ATSTLightningModule(arch=args.arch, learning_rate=2e-4, warmup_steps=10, max_steps=100000, ema=0.9995)
+    ncrops = sum(c for _, c in cfg["crops"])
+    if cfg["kind"] == "frame":
+        from audiossl_b200.methods.atstframe.model import FrameATSTLightningModule
+        from audiossl_b200.methods.atstframe import random_mask
+        lm = FrameATSTLightningModule(arch=arch, learning_rate=8e-5, warmup_steps=10, max_steps=100000, ema=0.9996)
+    else:
+        lm = ATSTLightningModule(arch=arch, learning_rate=2e-4, warmup_steps=10, max_steps=100000, ema=0.9995,
+                                 ncrops=ncrops)
     lm.cuda().train()
     opt = lm.configure_optimizers()[0]
     lm.trainer.optimizers = [opt]
     mel = LogMelSpectrogram()
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    wav_dev = torch.randn(2, B, 1, n, device=dev, generator=g) * 0.1
-    wav_host = wav_dev.cpu().pin_memory()
-    lengths = [torch.full((B,), n // 160 + 1, device=dev, dtype=torch.int64)] * 2
-    stage = torch.empty_like(wav_dev)
+    # one device / pinned-host waveform tensor per crop group: [count, B, 1, n]
+    wav_dev = [torch.randn(cnt, B, 1, int(sec * SR), device=dev, generator=g) * 0.1 for sec, cnt in cfg["crops"]]
+    wav_host = [w.cpu().pin_memory() for w in wav_dev]
+    stage = [torch.empty_like(w) for w in wav_dev]
+    lengths = []
+    for sec, cnt in cfg["crops"]:
+        lengths += [torch.full((B,), int(sec * SR) // 160 + 1, device=dev, dtype=torch.int64)] * cnt
+    n = int(cfg["crops"][0][0] * SR)
+    masks = None
+    if cfg["kind"] == "frame":
+        import numpy as np
+        np.random.seed(1234 + rank)
+        P = (n // 160 + 1) // 4
+        mk = random_mask.get_mask(B, P, 0.65, no_overlap=False, min_length=5).to(dev)
+        masks = [mk, mk]
+    h2d_bytes = sum(w.numel() * 4 for w in wav_host)
 
     mel_events = []
 
     def step(i, from_host):
         if from_host:
-            stage.copy_(wav_host, non_blocking=True)
+            for s_, h_ in zip(stage, wav_host):
+                s_.copy_(h_, non_blocking=True)
             src = stage
         else:
             src = wav_dev
         if ops.STATS["time_gemms"]:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
-        crops = [mel(src[0]), mel(src[1])]
+        crops = [mel(w[k]) for w in src for k in range(w.shape[0])]
         if ops.STATS["time_gemms"]:
             ev[1].record()
             mel_events.append(ev)
         lm.global_step = i
-        loss = lm.training_step(((crops, lengths), None), i)
+        batch = ((crops, lengths, masks), None) if masks is not None else ((crops, lengths), None)
+        loss = lm.training_step(batch, i)
         opt.zero_grad()
         loss.backward()
         opt.step()
@@ -281,7 +318,13 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     pk = peaks()
-    mel_bytes = 2 * B * (4 * n + 4 * 64 * (n // 160 + 1))  # 896 256 B per 10 s clip-view
+    # 4 n + 4 * 64 * (n // 160 + 1) bytes per clip-view (896 256 B for 10 s)
+    mel_bytes = sum(cnt * B * (4 * int(sec * SR) + 4 * 64 * (int(sec * SR) // 160 + 1)) for sec, cnt in cfg["crops"])
+    step_gflop = cfg["gflop"]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    if args.config == "c2" and os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
     ms_step = ms / args.steps
     value = B * world / (ms_step / 1e3)
     e2e_val = B * world / (ms_e2e / args.steps / 1e3)
@@ -291,28 +334,27 @@ def run_ours(args):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
         "data": "synthetic",
-        "config": {"workload": "ATST-%s, 10 s 16 kHz clips, 64 mel, 2 views, %d clips/GPU, DropPath 0.1, "
-                               "mel+teacher fwd+student fwd+loss+bwd+AdamW+EMA" % (args.arch, B),
-                   "parallelism": "dp%d" % world, "l2": "inputs_exceed_l2 (>=80 GB of activations per step)",
-                   "step_gflop_per_clip_algorithmic": STEP_GFLOP_PER_CLIP},
+        "config": {"workload": "%s [%s], 16 kHz, 64 mel, %d crops, %d clips/GPU, DropPath 0.1, "
+                               "mel+teacher fwd+student fwd+loss+bwd+AdamW+EMA" % (cfg["name"], args.config, ncrops, B),
+                   "parallelism": "dp%d" % world, "l2": "inputs_exceed_l2 (tens of GB of activations per step)",
+                   "step_gflop_per_clip_algorithmic": step_gflop},
         "clocks": sampler.summary(),
-        "e2e": {"value": e2e_val, "unit": "clips/s", "h2d_bytes_per_step": wav_host.numel() * 4,
-                "d2h_bytes_per_step": 4},
+        "e2e": {"value": e2e_val, "unit": "clips/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "kernel": "gemm_tf32_kernel (tcgen05 kind::tf32)", "achieved": achieved,
-                     "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None,
+                     "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": traffic,
                      "peak_source": pk["src"] + " bf16 cuBLAS sustained; TF32 tensor rate is half of bf16",
                      "launches_per_step": n_gemm, "gemm_ms_per_step": gemm_ms,
                      "gemm_share_of_step": gemm_ms / ms_step,
                      "algorithmic_gemm_tflop_per_step": gemm_flops_step / 1e12,
-                     "model_flops_utilisation_of_step": STEP_GFLOP_PER_CLIP * 1e9 * B / (ms_step / 1e3) / 1e12 / pk["tflops"]},
+                     "model_flops_utilisation_of_step": step_gflop * 1e9 * B / (ms_step / 1e3) / 1e12 / pk["tflops"]},
         "roofline_mel": {"bound": "hbm", "kernel": "mel_db_kernel + mel_norm_kernel (fused STFT/mel/dB/MinMax)",
                          "achieved": mel_bytes / (mel_ms / 1e3) / 1e9 if mel_ms > 0 else 0.0, "peak": pk["hbm_gbs"],
                          "unit": "GB/s", "frac": (mel_bytes / (mel_ms / 1e3) / 1e9 / pk["hbm_gbs"]) if mel_ms > 0 else 0.0,
                          "ms_per_step": mel_ms, "algorithmic_bytes_per_step": mel_bytes, "traffic": None,
                          "note": "FFT issue / smem bound (40 flop/B), not HBM bound"},
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.config == "c2":
         cores = pick_cpu_threads()
         cstep = cpu_reference_step_fn(4, cores)
         cstep()
@@ -335,8 +377,9 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="clips per GPU")
-    ap.add_argument("--arch", default="base")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE.json config (c2 = benchmark)")
+    ap.add_argument("--batch", type=int, default=0, help="clips per GPU (0 = the config's)")
+    ap.add_argument("--arch", default="", help="override the config's architecture")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="warm-up + one step only (for ncu captures)")
     ap.add_argument("--breakdown", default="", help="write a per-GEMM-shape timing table to this file")
