@@ -12,17 +12,19 @@ EPI_STORE, EPI_GELU, EPI_DGELU, EPI_RESID, EPI_SCALE, EPI_RELU = 0, 1, 2, 3, 4, 
 
 # launch accounting for bench.py: kernels launched through the C ABI, algorithmic GEMM flops, and (optionally)
 # a CUDA-event pair around every GEMM launch to measure the dominant kernel in place
-STATS = {"launches": 0, "gemm_flops": 0.0, "gemm_launches": 0, "time_gemms": False, "gemm_events": []}
+STATS = {"launches": 0, "gemm_flops": 0.0, "gemm_bytes": 0.0, "gemm_launches": 0, "time_gemms": False,
+         "gemm_events": []}
 
 
 def reset_stats():
-    STATS.update(launches=0, gemm_flops=0.0, gemm_launches=0, gemm_events=[])
+    STATS.update(launches=0, gemm_flops=0.0, gemm_bytes=0.0, gemm_launches=0, gemm_events=[])
 
 
 class _GemmTimer:
-    def __init__(self, flops, tag=""):
+    def __init__(self, flops, tag="", nbytes=0.0):
         self.flops = flops
         self.tag = tag
+        STATS["gemm_bytes"] += nbytes  # algorithmic operand + result bytes of this launch
         STATS["launches"] += 1
         STATS["gemm_launches"] += 1
         STATS["gemm_flops"] += flops
@@ -71,7 +73,8 @@ def gemm_nt(A, B, bias=None, epi=EPI_STORE, resid=None, aux=None, rowscale=None,
     assert B.shape[1] == K
     if out is None:
         out = torch.empty((M, N), device=A.device, dtype=torch.float32)
-    _t = _GemmTimer(2.0 * M * N * K, "nt %dx%dx%d e%d" % (M, N, K, epi))
+    _t = _GemmTimer(2.0 * M * N * K, "nt %dx%dx%d e%d" % (M, N, K, epi),
+                   4.0 * (M * K + N * K + M * N * (1 + (resid is not None) + (aux is not None))))
     check(_lib.lib().atst_gemm_nt(ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(out), out.stride(0), M, N, K,
                                   ptr(bias), epi, ptr(resid), resid.stride(0) if resid is not None else 0,
                                   ptr(aux), aux.stride(0) if aux is not None else 0, ptr(rowscale), rows_per_seq,
@@ -87,7 +90,7 @@ def gemm_nn(A, W, epi=EPI_STORE, aux=None, rowscale=None, rows_per_seq=1, round_
     assert W.shape[0] == K
     if out is None:
         out = torch.empty((M, N), device=A.device, dtype=torch.float32)
-    _t = _GemmTimer(2.0 * M * N * K, "nn %dx%dx%d e%d" % (M, N, K, epi))
+    _t = _GemmTimer(2.0 * M * N * K, "nn %dx%dx%d e%d" % (M, N, K, epi), 4.0 * (M * K + N * K + M * N * (1 + (aux is not None))))
     check(_lib.lib().atst_gemm_nn(ptr(A), A.stride(0), ptr(W), W.stride(0), ptr(out), out.stride(0), M, N, K, epi,
                                   ptr(aux), aux.stride(0) if aux is not None else 0, ptr(rowscale), rows_per_seq,
                                   1 if round_out else 0, _lib.stream()), "atst_gemm_nn")
@@ -100,7 +103,7 @@ def gemm_tn_acc(A, B, out):
     T, M = A.shape
     N = B.shape[1]
     assert B.shape[0] == T and tuple(out.shape) == (M, N)
-    _t = _GemmTimer(2.0 * M * N * T, "tn %dx%dx%d" % (M, N, T))
+    _t = _GemmTimer(2.0 * M * N * T, "tn %dx%dx%d" % (M, N, T), 4.0 * (T * M + T * N + M * N))
     check(_lib.lib().atst_gemm_tn(ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(out), out.stride(0), M, N, T,
                                   _lib.stream()), "atst_gemm_tn")
     _t.done()

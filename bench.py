@@ -288,6 +288,7 @@ def run_ours(args):
     ms = timed(False, args.steps, args.warmup)
     launches = ops.STATS["launches"]
     gemm_flops_step = ops.STATS["gemm_flops"] / args.steps
+    gemm_bytes_launch = ops.STATS["gemm_bytes"] / max(ops.STATS["gemm_launches"], 1)
     ms_e2e = timed(True, args.steps, args.warmup + args.steps)
     sampler.stop_flag = True
     sampler.join(timeout=2)
@@ -343,6 +344,7 @@ def run_ours(args):
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "kernel": "gemm_tf32_kernel (tcgen05 kind::tf32)", "achieved": achieved,
                      "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": traffic,
+                     "algorithmic_bytes_per_launch": gemm_bytes_launch,
                      "peak_source": pk["src"] + " bf16 cuBLAS sustained; TF32 tensor rate is half of bf16",
                      "launches_per_step": n_gemm, "gemm_ms_per_step": gemm_ms,
                      "gemm_share_of_step": gemm_ms / ms_step,
