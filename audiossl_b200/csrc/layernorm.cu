@@ -53,7 +53,7 @@ ln_fwd_kernel(const float* __restrict__ x, long long x_stride, const float* __re
 // dx = dres + rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
 // dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy   (per-lane register partials -> smem -> atomics)
 template <int NV>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256)
 ln_bwd_kernel(const float* __restrict__ dy, long long dy_stride, const float* __restrict__ x, long long x_stride,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
               const float* __restrict__ dres, long long dres_stride, float* __restrict__ dx, long long dx_stride,
@@ -69,7 +69,10 @@ ln_bwd_kernel(const float* __restrict__ dy, long long dy_stride, const float* __
   float4 pg[NV], pb[NV], pc[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) pg[i] = pb[i] = pc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  // gamma is re-read per row (L1 hit) instead of living in 4*NV registers: 2 CTAs/SM instead of 1
+  float4 gm[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) gm[i] = reinterpret_cast<const float4*>(gamma)[lane + 32 * i];
+
   for (int row = blockIdx.x * warps_per_cta + warp; row < rows; row += gridDim.x * warps_per_cta) {
     const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * x_stride);
     const float4* dr = reinterpret_cast<const float4*>(dy + static_cast<long long>(row) * dy_stride);
@@ -80,9 +83,8 @@ ln_bwd_kernel(const float* __restrict__ dy, long long dy_stride, const float* __
     for (int i = 0; i < NV; ++i) {
       const float4 xv = xr[lane + 32 * i];
       const float4 dv = dr[lane + 32 * i];
-      const float4 gmi = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
       xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-      g[i] = make_float4(dv.x * gmi.x, dv.y * gmi.y, dv.z * gmi.z, dv.w * gmi.w);
+      g[i] = make_float4(dv.x * gm[i].x, dv.y * gm[i].y, dv.z * gm[i].z, dv.w * gm[i].w);
       s1 += g[i].x + g[i].y + g[i].z + g[i].w;
       s2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
       pg[i].x += dv.x * xh[i].x; pg[i].y += dv.y * xh[i].y; pg[i].z += dv.z * xh[i].z; pg[i].w += dv.w * xh[i].w;
