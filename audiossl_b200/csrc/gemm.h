@@ -45,5 +45,6 @@ int gemm_nn(const float* A, int lda, const float* B, int ldb, GemmParams p, cuda
 int gemm_tn(const float* A, int lda, const float* B, int ldb, int T, GemmParams p, cudaStream_t stream);
 
 void gemm_set_l2_prefetch(int on);
+void gemm_set_cta_pair(int on);
 
 }  // namespace atst

@@ -1,0 +1,292 @@
+// CTA-pair TF32 GEMM (tcgen05 cta_group::2): 256 x 256 output tile per cluster of two CTAs.
+//
+// Why: with one CTA per 128x256 tile (gemm_tcgen05.cu) every k-block costs 96 B/clk of UMMA operand reads plus
+// 96 B/clk of TMA fill against a 128 B/clk shared-memory port, and 96 B/clk/SM of L2->SM traffic.  As a pair, each
+// CTA stages its own 128 rows of A and only HALF of the B tile (128 of the 256 N rows); the tensor cores of the
+// two SMs read the other half from the peer's shared memory.  Per CTA: 64 B/clk of TMA fill, 64 B/clk of UMMA
+// reads, 64 B/clk of L2 traffic, and the 32 KB stages make the smem ring 6 deep instead of 4.
+//
+// Roles per CTA (256 threads): warp 0 TMA producer (both CTAs; transactions complete on the LEADER's full
+// barrier), warp 1 MMA issuer (leader only: tcgen05.mma.cta_group::2, M=256; tcgen05.commit multicast frees the
+// smem slot / publishes the accumulator in both CTAs), warp 2 TMEM allocator (cta_group::2 alloc in both CTAs),
+// warps 4-7 epilogue (own 128 TMEM lanes; the accumulator stage is handed back on the leader's barrier, remotely
+// from the follower).  Operand majors as in the 1-CTA kernel (K-major 128B swizzle, or token-major tensors via
+// the 32B-atom swizzle).
+#include <cooperative_groups.h>
+#include "common.cuh"
+#include "gemm.h"
+#include "gemm_epilogue.cuh"
+
+namespace atst {
+
+namespace {
+
+constexpr int kBM = 128;       // rows per CTA (256 per pair)
+constexpr int kBN = 256;       // N columns per pair tile
+constexpr int kBNHalf = 128;   // B rows staged per CTA
+constexpr int kBK = 32;        // tf32 elements per k-block (128 B)
+constexpr int kStages2 = 6;
+constexpr int kA2 = kBM * 128;       // 16 KB
+constexpr int kB2 = kBNHalf * 128;   // 16 KB
+constexpr int kStage2 = kA2 + kB2;   // 32 KB
+constexpr int kSmem2 = 1024 + kStages2 * kStage2 + 256 + 2 * 256 * 4;
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> CTA 0 of the pair
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                             int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once the MMAs issued so far have completed) on the barrier at the same smem offset in BOTH CTAs
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
+                   "r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+// arrive on the barrier at this smem offset in CTA 0 of the pair (works from either CTA)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(smem_u32(bar))
+      : "memory");
+}
+
+}  // namespace
+
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+gemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+  extern __shared__ uint8_t smem_raw2[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw2) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages2 * kA2;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages2 * kStage2);
+  uint64_t* full_bar = bars;                    // [kStages2]  (the leader's are the live ones)
+  uint64_t* empty_bar = bars + kStages2;        // [kStages2]  per CTA, armed by the leader's multicast commit
+  uint64_t* tfull_bar = bars + 2 * kStages2;    // [2]         per CTA, multicast commit
+  uint64_t* tempty_bar = tfull_bar + 2;         // [2]         leader's: 8 arrivals (4 epilogue warps x 2 CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* smem_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2][256]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  const int m_tiles = (p.M + 2 * kBM - 1) / (2 * kBM);
+  const int n_tiles = (p.N + kBN - 1) / kBN;
+  const int kb_total = (p.K + kBK - 1) / kBK;
+  const int splits = p.splits > 0 ? p.splits : 1;
+  const int kb_per_split = (kb_total + splits - 1) / splits;
+  const int total_tiles = m_tiles * n_tiles * splits;
+  const int first_tile = blockIdx.x >> 1, tile_step = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages2; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc2(tmem_slot, 512);
+  tc_fence_before();
+  cluster_sync();  // barriers of both CTAs initialised before any remote arrive / transaction
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+        const int split = tile / (m_tiles * n_tiles);
+        const int rem = tile - split * (m_tiles * n_tiles);
+        const int m0 = (rem / n_tiles) * 2 * kBM + rank * kBM;   // this CTA's A rows
+        const int n0 = (rem % n_tiles) * kBN + rank * kBNHalf;   // this CTA's half of the B rows
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb0 + kb_per_split, kb_total);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * kStage2);  // both CTAs' bytes land on this barrier
+          void* sa = smem_a + stage * kA2;
+          void* sb = smem_b + stage * kB2;
+          if (A_MN) tma2_load_3d(sa, &tmA, &full_bar[stage], 0, kb * kBK, m0 / 32);
+          else      tma2_load_2d(sa, &tmA, &full_bar[stage], kb * kBK, m0);
+          if (B_MN) tma2_load_3d(sb, &tmB, &full_bar[stage], 0, kb * kBK, n0 / 32);
+          else      tma2_load_2d(sb, &tmB, &full_bar[stage], kb * kBK, n0);
+          if (++stage == kStages2) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader) {
+      const uint32_t idesc = make_idesc(2u, 2 * kBM, kBN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+        const int split = tile / (m_tiles * n_tiles);
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb0 + kb_per_split, kb_total);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kBN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_addr = smem_u32(smem_a + stage * kA2);
+            const uint32_t b_addr = smem_u32(smem_b + stage * kB2);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t da = A_MN ? make_smem_desc(a_addr + k * p.mn_kstep, p.mn_lbo, p.mn_sbo, p.mn_layout)
+                                       : make_smem_desc(a_addr + k * 32, 16, 1024, 2);
+              const uint64_t db = B_MN ? make_smem_desc(b_addr + k * p.mn_kstep, p.mn_lbo, p.mn_sbo, p.mn_layout)
+                                       : make_smem_desc(b_addr + k * 32, 16, 1024, 2);
+              umma2_tf32(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            umma2_commit_mc(&empty_bar[stage]);
+            if (kb == kb1 - 1) umma2_commit_mc(&tfull_bar[acc]);
+          }
+          __syncwarp();
+          if (++stage == kStages2) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (kb1 <= kb0 && lane == 0) umma2_commit_mc(&tfull_bar[acc]);
+        __syncwarp();
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
+    const int ew = warp - 4;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+      const int split = tile / (m_tiles * n_tiles);
+      const int rem = tile - split * (m_tiles * n_tiles);
+      const int m0 = (rem / n_tiles) * 2 * kBM + rank * kBM;
+      const int n0 = (rem % n_tiles) * kBN;
+      const int kb0 = split * kb_per_split;
+      const bool empty_split = min(kb0 + kb_per_split, kb_total) <= kb0;
+      uint64_t* tempty = &tempty_bar[acc];
+      epilogue_tile<kBN>(p, m0, n0, empty_split, tmem_base + acc * kBN, smem_bias + acc * 256, ew, lane, &tfull_bar[acc],
+                         acc_phase, [&]() {
+                           if (lane == 0) mbar_arrive_leader(tempty);
+                         });
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  cluster_sync();  // nobody exits (or frees TMEM) while the peer may still signal / read
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+int make_map_kmajor_pub(CUtensorMap* map, const float* ptr, int rows, int cols, int ld, int box_rows);
+int make_map_mnmajor_pub(CUtensorMap* map, const float* ptr, int tokens, int feats, int ld, int box_feats,
+                         int swizzle_mode);
+int gemm_num_sms();
+
+template <bool A_MN, bool B_MN>
+static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  static bool configured = false;
+  auto kfn = gemm2_tf32_kernel<A_MN, B_MN>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2);
+    if (e != cudaSuccess) { atst_set_error("cudaFuncSetAttribute(gemm2): %s", cudaGetErrorString(e)); return ATST_ERR_CUDA; }
+    configured = true;
+  }
+  const int m_tiles = (p.M + 2 * kBM - 1) / (2 * kBM);
+  const int n_tiles = (p.N + kBN - 1) / kBN;
+  const int tiles = m_tiles * n_tiles * (p.splits > 0 ? p.splits : 1);
+  const int pairs = gemm_num_sms() / 2;
+  const int grid = 2 * (tiles < pairs ? tiles : pairs);
+  kfn<<<grid, 256, kSmem2, stream>>>(ta, tb, p);
+  return atst_check_launch("gemm2_tf32_kernel");
+}
+
+// same contracts as gemm_nt / gemm_nn / gemm_tn (operands validated by the callers in gemm_tcgen05.cu)
+int gemm2_launch(int a_mn, int b_mn, const float* A, int lda, int a_rows, int a_cols, const float* B, int ldb, int b_rows,
+                 int b_cols, const GemmParams& p, cudaStream_t stream) {
+  CUtensorMap ta, tb;
+  int rc;
+  if (a_mn) rc = make_map_mnmajor_pub(&ta, A, a_rows, a_cols, lda, kBM, p.mn_tma_swizzle);
+  else      rc = make_map_kmajor_pub(&ta, A, a_rows, a_cols, lda, kBM);
+  if (rc) return rc;
+  if (b_mn) rc = make_map_mnmajor_pub(&tb, B, b_rows, b_cols, ldb, kBNHalf, p.mn_tma_swizzle);
+  else      rc = make_map_kmajor_pub(&tb, B, b_rows, b_cols, ldb, kBNHalf);
+  if (rc) return rc;
+  if (!a_mn && !b_mn) return launch2<false, false>(ta, tb, p, stream);
+  if (!a_mn && b_mn) return launch2<false, true>(ta, tb, p, stream);
+  return launch2<true, true>(ta, tb, p, stream);
+}
+
+}  // namespace atst

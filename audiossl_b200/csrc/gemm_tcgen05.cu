@@ -18,6 +18,7 @@
 // (cvt.rna.tf32) the activations/weights they hand to a GEMM so operand error is unbiased.
 #include "common.cuh"
 #include "gemm.h"
+#include "gemm_epilogue.cuh"
 
 namespace atst {
 
@@ -38,32 +39,6 @@ struct GemmCfg {
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kEpiBytes + 256 + kBiasBytes;
   static constexpr int kTmemCols = 2 * BLOCK_N;  // 512 or 256: power of two
 };
-
-// erf by Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, far below the TF32 operand rounding of the next GEMM):
-// one MUFU.RCP + one MUFU.EX2 + 7 FMA instead of libdevice erff's ~25 instructions.  The exp(-u^2/2) factor is
-// shared between the cdf and the pdf, so gelu'(u) costs no second exponential.
-struct GeluParts { float cdf, pdf; };
-__device__ __forceinline__ GeluParts gelu_parts(float u) {
-  const float x = u * 0.70710678118654752f;
-  const float ax = fabsf(x);
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));  // MUFU.RCP, branch-free (keeps the 8 chains interleaved)
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  const float e = __expf(-ax * ax);            // exp(-u^2 / 2)
-  const float erf_abs = fmaf(-poly, e, 1.0f);  // erf(|x|)
-  GeluParts g;
-  g.cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
-  g.pdf = 0.3989422804014327f * e;
-  return g;
-}
-__device__ __forceinline__ float gelu_exact(float u) { return u * gelu_parts(u).cdf; }
-__device__ __forceinline__ float gelu_grad(float u) {
-  const GeluParts g = gelu_parts(u);
-  return fmaf(u, g.pdf, g.cdf);
-}
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -399,6 +374,11 @@ static int make_map_mnmajor(CUtensorMap* map, const float* ptr, int tokens, int 
   return ATST_OK;
 }
 
+static int g_cta_pair = 0;  // route 256-wide problems to the CTA-pair kernel (gemm2_tcgen05.cu)
+void gemm_set_cta_pair(int on) { g_cta_pair = on; }
+int gemm2_launch(int a_mn, int b_mn, const float* A, int lda, int a_rows, int a_cols, const float* B, int ldb, int b_rows,
+                 int b_cols, const GemmParams& p, cudaStream_t stream);
+
 static int g_l2_prefetch = 0;  // measured: no gain (the ring is L2-bandwidth, not latency, limited)
 void gemm_set_l2_prefetch(int on) { g_l2_prefetch = on; }
 
@@ -412,6 +392,15 @@ static int num_sms() {
   }
   return g_num_sms;
 }
+
+int make_map_kmajor_pub(CUtensorMap* map, const float* ptr, int rows, int cols, int ld, int box_rows) {
+  return make_map_kmajor(map, ptr, rows, cols, ld, box_rows);
+}
+int make_map_mnmajor_pub(CUtensorMap* map, const float* ptr, int tokens, int feats, int ld, int box_feats,
+                         int swizzle_mode) {
+  return make_map_mnmajor(map, ptr, tokens, feats, ld, box_feats, swizzle_mode);
+}
+int gemm_num_sms() { return num_sms(); }
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
@@ -454,12 +443,13 @@ int gemm_nt(const float* A, int lda, const float* B, int ldb, GemmParams p, cuda
   int rc0 = check_output_layout(p, "gemm_nt");
   if (rc0) return rc0;
   const bool wide = (p.N % 256 == 0) || p.N > 1024;
+  p.splits = 1;
+  if (wide && g_cta_pair) return gemm2_launch(0, 0, A, lda, p.M, p.K, B, ldb, p.N, p.K, p, stream);
   CUtensorMap ta, tb;
   int rc = make_map_kmajor(&ta, A, p.M, p.K, lda, kBlockM);
   if (rc) return rc;
   rc = make_map_kmajor(&tb, B, p.N, p.K, ldb, wide ? 256 : 128);
   if (rc) return rc;
-  p.splits = 1;
   return wide ? launch<256, false, false>(ta, tb, p, stream) : launch<128, false, false>(ta, tb, p, stream);
 }
 
@@ -482,12 +472,13 @@ int gemm_nn(const float* A, int lda, const float* B, int ldb, GemmParams p, cuda
   if (rc0) return rc0;
   mn_defaults(p);
   const bool wide = (p.N % 256 == 0) || p.N > 1024;
+  p.splits = 1;
+  if (wide && g_cta_pair) return gemm2_launch(0, 1, A, lda, p.M, p.K, B, ldb, p.K, p.N, p, stream);
   CUtensorMap ta, tb;
   int rc = make_map_kmajor(&ta, A, p.M, p.K, lda, kBlockM);
   if (rc) return rc;
   rc = make_map_mnmajor(&tb, B, p.K, p.N, ldb, wide ? 256 : 128, p.mn_tma_swizzle);
   if (rc) return rc;
-  p.splits = 1;
   return wide ? launch<256, false, true>(ta, tb, p, stream) : launch<128, false, true>(ta, tb, p, stream);
 }
 
@@ -502,11 +493,13 @@ int gemm_tn(const float* A, int lda, const float* B, int ldb, int T, GemmParams 
   const bool wide = (p.N % 256 == 0) || p.N > 1024;
   const int bn = wide ? 256 : 128;
   mn_defaults(p);
-  const int m_tiles = (p.M + kBlockM - 1) / kBlockM, n_tiles = (p.N + bn - 1) / bn;
+  const bool pair = wide && g_cta_pair;
+  const int bm = pair ? 2 * kBlockM : kBlockM;
+  const int m_tiles = (p.M + bm - 1) / bm, n_tiles = (p.N + bn - 1) / bn;
   const int kb_total = (T + kBlockK - 1) / kBlockK;
   if (p.splits <= 0) {
     // pick the split count whose work-unit count fills whole waves of SMs best (>= 8 k-blocks per unit)
-    const int t = m_tiles * n_tiles, sms = num_sms();
+    const int t = m_tiles * n_tiles, sms = pair ? num_sms() / 2 : num_sms();
     int best = 1;
     double best_eff = 0.0;
     for (int s = 1; s <= 64 && s * 8 <= kb_total; ++s) {
@@ -520,6 +513,7 @@ int gemm_tn(const float* A, int lda, const float* B, int ldb, int T, GemmParams 
   // no empty splits: shrink until every split owns at least one k-block
   while (p.splits > 1 && (p.splits - 1) * ((kb_total + p.splits - 1) / p.splits) >= kb_total) --p.splits;
   p.epi = EPI_ATOMIC;
+  if (pair) return gemm2_launch(1, 1, A, lda, T, p.M, B, ldb, T, p.N, p, stream);
   CUtensorMap ta, tb;
   int rc = make_map_mnmajor(&ta, A, T, p.M, lda, kBlockM, p.mn_tma_swizzle);
   if (rc) return rc;

@@ -24,7 +24,7 @@ int atst_version(void);
 const char* atst_last_error(void);
 /* checks the current device is sm_100 and warms the driver entry points */
 int atst_init(void);
-/* tuning switches (bring-up / profiling): "gemm_l2_prefetch" = 0|1 */
+/* tuning switches (bring-up / profiling): "gemm_l2_prefetch" = 0|1, "gemm_cta_pair" = 0|1 (cta_group::2 kernel) */
 int atst_set_option(const char* name, int value);
 
 /* ---- mel front-end: torchaudio MelSpectrogram(16000,n_fft=1024,hop=160,win=1024|640,f_min=60,f_max=7800,

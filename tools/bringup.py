@@ -410,7 +410,74 @@ def sec_heads():
               (R, rel_err(C, dz1.t() @ x), rel_err(dx, dz1 @ W0), rel_err(C2, dz2.t() @ a1), rel_err(da1, dz2 @ W3)))
 
 
-SECTIONS = {"heads": sec_heads, "gemm_perf": sec_gemm_perf, "mel": sec_mel, "gemm_nt": sec_gemm_nt, "gemm_mn": sec_gemm_mn, "ln": sec_ln, "attn": sec_attn,
+def sec_pair():
+    """CTA-pair (cta_group::2) GEMM kernel: correctness of the three flavours + epilogues, then throughput"""
+    import torch
+    from audiossl_b200 import _lib, ops
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    L = _lib.lib()
+    L.atst_set_option(b"gemm_cta_pair", 1)
+    try:
+        for (M, N, K) in [(256, 256, 32), (256, 256, 128), (300, 512, 256), (1004, 2304, 768), (4096, 768, 3072),
+                          (70, 4096, 128), (128512, 768, 768)]:
+            A = ops.round_tf32(torch.randn(M, K, device="cuda"))
+            B = ops.round_tf32(torch.randn(N, K, device="cuda") * 0.05)
+            out = ops.gemm_nt(A, B)
+            torch.cuda.synchronize()
+            print("pair nt %6dx%5dx%5d rel=%.3e" % (M, N, K, rel_err(out, A @ B.t())), flush=True)
+        M, N, K = 520, 768, 256
+        A = ops.round_tf32(torch.randn(M, K, device="cuda"))
+        B = ops.round_tf32(torch.randn(N, K, device="cuda") * 0.05)
+        bias, resid = torch.randn(N, device="cuda"), torch.randn(M, N, device="cuda")
+        scale = torch.rand(M // 26, device="cuda") + 0.5
+        base = A @ B.t() + bias
+        out = ops.gemm_nt(A, B, bias=bias, epi=ops.EPI_RESID, resid=resid, rowscale=scale, rows_per_seq=26)
+        print("pair epi resid rel=%.3e" % rel_err(out, resid + scale.repeat_interleave(26)[:, None] * base))
+        aux = torch.empty(M, N, device="cuda")
+        out = ops.gemm_nt(A, B, bias=bias, epi=ops.EPI_GELU, aux=aux)
+        print("pair epi gelu  rel=%.3e aux=%.3e" % (rel_err(out, torch.nn.functional.gelu(base)), rel_err(aux, base)))
+        for (T, Mf, Nf) in [(96, 256, 256), (1000, 256, 512), (4000, 768, 2304), (130, 4096, 256), (128512, 768, 768)]:
+            A = ops.round_tf32(torch.randn(T, Mf, device="cuda") * 0.1)
+            B = ops.round_tf32(torch.randn(T, Nf, device="cuda") * 0.1)
+            C = torch.zeros(Mf, Nf, device="cuda")
+            ops.gemm_tn_acc(A, B, C)
+            W = ops.round_tf32(torch.randn(Mf, Nf, device="cuda") * 0.1)
+            dX = ops.gemm_nn(A, W)
+            torch.cuda.synchronize()
+            print("pair tn T=%6d %4dx%4d rel=%.3e | nn rel=%.3e" % (T, Mf, Nf, rel_err(C, A.t() @ B), rel_err(dX, A @ W)),
+                  flush=True)
+        M = 128512
+
+        def tm(fn, flops, name):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(4):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 4
+            print("%-34s %8.3f ms  %7.1f TFLOP/s" % (name, ms, flops / ms / 1e9), flush=True)
+        for pair in (0, 1):
+            L.atst_set_option(b"gemm_cta_pair", pair)
+            for (N, K) in [(2304, 768), (768, 768), (3072, 768), (768, 3072)]:
+                A = torch.randn(M, K, device="cuda")
+                W = torch.randn(N, K, device="cuda")
+                C = torch.empty(M, N, device="cuda")
+                tm(lambda: ops.gemm_nt(A, W, out=C), 2.0 * M * N * K, "pair=%d nt M x %d x %d" % (pair, N, K))
+                dX = torch.empty(M, K, device="cuda")
+                tm(lambda: ops.gemm_nn(C, W, out=dX), 2.0 * M * N * K, "pair=%d nn M x %d (K=%d)" % (pair, K, N))
+                dW = torch.zeros(N, K, device="cuda")
+                tm(lambda: ops.gemm_tn_acc(C, A, dW), 2.0 * M * N * K, "pair=%d tn %d x %d" % (pair, N, K))
+                del A, W, C, dX, dW
+    finally:
+        L.atst_set_option(b"gemm_cta_pair", 0)
+
+
+SECTIONS = {"pair": sec_pair, "heads": sec_heads, "gemm_perf": sec_gemm_perf, "mel": sec_mel, "gemm_nt": sec_gemm_nt, "gemm_mn": sec_gemm_mn, "ln": sec_ln, "attn": sec_attn,
             "bn": sec_bn, "loss": sec_loss, "optim": sec_optim, "tokens": sec_tokens}
 
 if __name__ == "__main__":
