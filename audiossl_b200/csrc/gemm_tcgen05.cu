@@ -374,7 +374,7 @@ static int make_map_mnmajor(CUtensorMap* map, const float* ptr, int tokens, int 
   return ATST_OK;
 }
 
-static int g_cta_pair = 0;  // route 256-wide problems to the CTA-pair kernel (gemm2_tcgen05.cu)
+static int g_cta_pair = 1;  // route 256-wide problems to the CTA-pair kernel (gemm2_tcgen05.cu)
 void gemm_set_cta_pair(int on) { g_cta_pair = on; }
 int gemm2_launch(int a_mn, int b_mn, const float* A, int lda, int a_rows, int a_cols, const float* B, int ldb, int b_rows,
                  int b_cols, const GemmParams& p, cudaStream_t stream);
