@@ -79,14 +79,18 @@ __device__ __forceinline__ void mma_abt(float (&acc)[8][4], const float* R, int 
   for (int kp = 0; kp < 4; ++kp) {
     const float4 x0 = ld4(R, ra0 + g, 4 * kp + t);
     const float4 x1 = ld4(R, ra0 + g + 8, 4 * kp + t);
+    float4 y[8];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const float4 y = ld4(Y, 8 * nt + g, 4 * kp + t);
+    for (int nt = 0; nt < 8; ++nt) y[nt] = ld4(Y, 8 * nt + g, 4 * kp + t);
+    // two passes over the 8 independent accumulators: a dependent mma pair is always 8 issues apart
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
       mma_tf32(acc[nt], __float_as_uint(x0.x), __float_as_uint(x1.x), __float_as_uint(x0.y), __float_as_uint(x1.y),
-               __float_as_uint(y.x), __float_as_uint(y.y));
+               __float_as_uint(y[nt].x), __float_as_uint(y[nt].y));
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
       mma_tf32(acc[nt], __float_as_uint(x0.z), __float_as_uint(x1.z), __float_as_uint(x0.w), __float_as_uint(x1.w),
-               __float_as_uint(y.z), __float_as_uint(y.w));
-    }
+               __float_as_uint(y[nt].z), __float_as_uint(y[nt].w));
   }
 }
 // acc[dt] += P(16 x 64, C-fragment layout, columns = rows of Y) . Y(64 x 64)
