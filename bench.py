@@ -231,12 +231,30 @@ def run_ours(args):
     h2d_bytes = sum(w.numel() * 4 for w in wav_host)
 
     mel_events = []
+    # e2e input pipeline: double-buffered device staging filled from pinned host memory on a copy stream, so the
+    # host->device copy of step i+1 (inside the timed region) overlaps the compute of step i
+    stage2 = [torch.empty_like(w) for w in wav_dev]
+    copy_stream = torch.cuda.Stream(device=dev)
+    h2d = {"ready": None, "buf": 0}
+
+    def issue_h2d():
+        bufs = stage if h2d["buf"] == 0 else stage2
+        copy_stream.wait_stream(torch.cuda.current_stream())  # the buffer's previous consumer (2 steps ago) is done
+        with torch.cuda.stream(copy_stream):
+            for s_, h_ in zip(bufs, wav_host):
+                s_.copy_(h_, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        h2d["ready"] = (ev, bufs)
+        h2d["buf"] ^= 1
 
     def step(i, from_host):
         if from_host:
-            for s_, h_ in zip(stage, wav_host):
-                s_.copy_(h_, non_blocking=True)
-            src = stage
+            if h2d["ready"] is None:
+                issue_h2d()
+            ev, src = h2d["ready"]
+            torch.cuda.current_stream().wait_event(ev)
+            issue_h2d()  # next step's batch starts copying now
         else:
             src = wav_dev
         if ops.STATS["time_gemms"]:
@@ -289,6 +307,7 @@ def run_ours(args):
     launches = ops.STATS["launches"]
     gemm_flops_step = ops.STATS["gemm_flops"] / args.steps
     gemm_bytes_launch = ops.STATS["gemm_bytes"] / max(ops.STATS["gemm_launches"], 1)
+    h2d["ready"] = None
     ms_e2e = timed(True, args.steps, args.warmup + args.steps)
     sampler.stop_flag = True
     sampler.join(timeout=2)
