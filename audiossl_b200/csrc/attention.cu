@@ -340,9 +340,14 @@ static int launch_attn(const AttnParams& p, int S, cudaStream_t stream) {
   return atst_check_launch("attn_kernel");
 }
 
+int attention_forward_tc(const float* qkv, float* o, float* lse, const int* lengths, int S, int N, int H,
+                         cudaStream_t stream);
+int attention_tc_enabled();
+
 int attention_forward(const float* qkv, float* o, float* lse, const int* lengths, int S, int N, int H,
                       cudaStream_t stream) {
   ATST_REQUIRE(S > 0 && N > 0 && H > 0, "attention_forward: bad shape S=%d N=%d H=%d", S, N, H);
+  if (attention_tc_enabled() && N <= 256) return attention_forward_tc(qkv, o, lse, lengths, S, N, H, stream);
   AttnParams p{};
   p.qkv = qkv; p.out_o = o; p.lse = lse; p.lengths = lengths;
   p.N = N; p.H = H; p.D = H * kHd; p.scale = 0.125f;

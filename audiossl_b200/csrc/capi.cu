@@ -5,6 +5,7 @@
 #include "ops.h"
 #include <string.h>
 
+namespace atst { void attention_set_tc(int on); }
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 using namespace atst;
 
@@ -15,6 +16,7 @@ int atst_version(void) { return 100; }
 int atst_set_option(const char* name, int value) {
   if (name != nullptr && strcmp(name, "gemm_l2_prefetch") == 0) { gemm_set_l2_prefetch(value); return ATST_OK; }
   if (name != nullptr && strcmp(name, "gemm_cta_pair") == 0) { gemm_set_cta_pair(value); return ATST_OK; }
+  if (name != nullptr && strcmp(name, "attn_tcgen05") == 0) { attention_set_tc(value); return ATST_OK; }
   atst_set_error("atst_set_option: unknown option '%s'", name ? name : "(null)");
   return ATST_ERR_ARG;
 }

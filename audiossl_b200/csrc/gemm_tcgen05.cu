@@ -402,6 +402,35 @@ int make_map_mnmajor_pub(CUtensorMap* map, const float* ptr, int tokens, int fea
 }
 int gemm_num_sms() { return num_sms(); }
 
+// generic tensor maps for other kernels (attention_tc.cu): K-major 2-D tiles and token-major 3-D tiles
+int make_map_generic_2d(CUtensorMap* map, const float* ptr, long long rows, int cols, int ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { atst_set_error("cuTensorMapEncodeTiled entry point not available"); return ATST_ERR_CUDA; }
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
+  cuuint32_t box[2] = {32, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { atst_set_error("cuTensorMapEncodeTiled(2d) failed: %d", (int)r); return ATST_ERR_CUDA; }
+  return ATST_OK;
+}
+int make_map_generic_3d(CUtensorMap* map, const float* ptr, long long rows, int feats, int ld, int box_rows,
+                        int box_chunks) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { atst_set_error("cuTensorMapEncodeTiled entry point not available"); return ATST_ERR_CUDA; }
+  cuuint64_t dims[3] = {32, static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(feats / 32)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 4, 128};
+  cuuint32_t box[3] = {32, static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(box_chunks)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { atst_set_error("cuTensorMapEncodeTiled(3d) failed: %d", (int)r); return ATST_ERR_CUDA; }
+  return ATST_OK;
+}
+
 template <int BLOCK_N, bool A_MN, bool B_MN>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;

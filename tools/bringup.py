@@ -182,6 +182,12 @@ def sec_ln():
                rel_err(dys, ref_dys), rel_err(cs, ref_dys.sum(0))))
 
 
+def sec_attn_tc():
+    from audiossl_b200 import _lib
+    _lib.lib().atst_set_option(b"attn_tcgen05", 1)
+    sec_attn()
+
+
 def sec_attn():
     import torch
     from audiossl_b200 import ops
@@ -477,7 +483,7 @@ def sec_pair():
         L.atst_set_option(b"gemm_cta_pair", 0)
 
 
-SECTIONS = {"pair": sec_pair, "heads": sec_heads, "gemm_perf": sec_gemm_perf, "mel": sec_mel, "gemm_nt": sec_gemm_nt, "gemm_mn": sec_gemm_mn, "ln": sec_ln, "attn": sec_attn,
+SECTIONS = {"attn_tc": sec_attn_tc, "pair": sec_pair, "heads": sec_heads, "gemm_perf": sec_gemm_perf, "mel": sec_mel, "gemm_nt": sec_gemm_nt, "gemm_mn": sec_gemm_mn, "ln": sec_ln, "attn": sec_attn,
             "bn": sec_bn, "loss": sec_loss, "optim": sec_optim, "tokens": sec_tokens}
 
 if __name__ == "__main__":
