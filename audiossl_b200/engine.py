@@ -66,10 +66,13 @@ class EncoderEngine:
         self.debug = None  # bring-up aid: list collecting (name, layer, tensor clone) during backward
 
     # ------------------------------------------------------------------ forward
-    def forward(self, fp, ws, mel, lengths, dp=None, save=True, tag="s", mask=None, mask_input=True):
+    def forward(self, fp, ws, mel, lengths, dp=None, save=True, tag="s", mask=None, mask_input=True, collect=0,
+                round_final=True):
         """mel [S,1,64,T] fp32 cuda contiguous; lengths [S] (valid frames) or None.
         Returns (out [S,D] tf32-rounded final-norm CLS rows, ctx) for the clip model, or
-        (x_norm [S*N, D], ctx) for the frame model (row selection is done by the caller)."""
+        (x_norm [S*N, D], ctx) for the frame model (row selection is done by the caller).
+        collect=n (inference, get_intermediate_layers): ctx["collected"] = final-norm of every token after each of
+        the last n blocks, n tensors [S*N, D] (fp32, not tf32-rounded)."""
         px, D, H = self.px, self.D, self.H
         S, _, Hm, T = mel.shape
         if T > self.max_frames:
@@ -121,6 +124,12 @@ class EncoderEngine:
                 ctx["layers"].append(dict(x=x, h=h, mean1=mean1, rstd1=rstd1, qkv=qkv, o=o, lse=lse, x1=x1, h2=h2,
                                           mean2=mean2, rstd2=rstd2, u=u, g=g))
             x = x2
+            if collect and self.depth - i <= collect:
+                nmw = px + self.norm_name
+                j = collect - (self.depth - i)
+                yn, _, _ = ops.layernorm_fwd(x, fp.p(nmw + ".weight"), fp.p(nmw + ".bias"), M, D, round_out=False,
+                                             out=ws.get("%s/collect%d" % (tag, j), (M, D)))
+                ctx.setdefault("collected", []).append(yn)
         ctx["x_final"] = x
         nm = px + self.norm_name
         if self.use_cls:
@@ -128,7 +137,7 @@ class EncoderEngine:
             mean = t("meanf", (S,))
             rstd = t("rstdf", (S,))
             ops.layernorm_fwd(x, fp.p(nm + ".weight"), fp.p(nm + ".bias"), S, D, x_stride=N * D, out=out, mean=mean,
-                              rstd=rstd)
+                              rstd=rstd, round_out=round_final)
         else:
             out = t("xn", (M, D))
             mean = t("meanf", (M,))

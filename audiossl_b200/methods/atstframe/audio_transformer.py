@@ -9,11 +9,11 @@ from functools import partial
 import torch
 from torch import nn
 
-from ...models.atst.audio_transformer import PatchEmbed_v2, get_num_patches
+from ...models.atst.audio_transformer import PatchEmbed_v2, _EncoderInference, get_num_patches
 from ...modules.transformer import Block, trunc_normal_
 
 
-class FrameAST(nn.Module):
+class FrameAST(_EncoderInference, nn.Module):
     def __init__(self, nprompt=0, spec_h=64, spec_w=1001, patch_w=16, patch_h=16, pos_type="cut", avg_blocks=0,
                  in_chans=1, num_classes=0, embed_dim=768, depth=12, num_heads=12, mlp_ratio=4., qkv_bias=False,
                  qk_scale=None, drop_rate=0., attn_drop_rate=0., drop_path_rate=0.1, norm_layer=nn.LayerNorm,

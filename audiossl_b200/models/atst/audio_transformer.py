@@ -24,7 +24,97 @@ class PatchEmbed_v2(nn.Module):
         self.patch_embed = nn.Linear(patch_height * patch_width, embed_dim)
 
 
-class AST(nn.Module):
+def get_cls_avg(output_i, cur_len, use_cls):
+    """CLS token and length-masked mean of the patch tokens for each collected layer
+    (audiossl/models/atst/audio_transformer.py:355-366)."""
+    n_tok = output_i[0].shape[1] - (1 if use_cls else 0)
+    length_mask = torch.arange(n_tok, device=output_i[0].device) < cur_len.unsqueeze(1)
+    if use_cls:
+        cls = [x[:, 0] for x in output_i]
+        avg = [torch.sum(x[:, 1:] * length_mask.unsqueeze(-1), dim=1) / (cur_len.unsqueeze(1) + 1e-6) for x in output_i]
+    else:
+        cls = [torch.zeros_like(x[:, 0]) for x in output_i]
+        avg = [torch.sum(x * length_mask.unsqueeze(-1), dim=1) / (cur_len.unsqueeze(1) + 1e-6) for x in output_i]
+    return cls, avg
+
+
+class _EncoderInference:
+    """Inference entry points shared by AST and FrameAST: the same CUDA engine as
+    training, no saved activations, no gradient.  The encoder gets its own flat parameter buffer the first time it
+    is called stand-alone (e.g. ``model.teacher.encoder`` handed to a downstream probe)."""
+
+    _inf = None
+
+    def _inference_runtime(self, device):
+        from ...engine import EncoderEngine, Workspace
+        from ...params import FlatParams
+        if device.type != "cuda":
+            raise RuntimeError("audiossl_b200 has no CPU path: move the encoder and its input to a B200 (cuda) device")
+        rt = self._inf
+        if rt is None or rt["device"] != device or not rt["fp"].is_current():
+            self.to(device)
+            fp = FlatParams(list(self.named_parameters()), device, ema_prefixes=("",))
+            eng = EncoderEngine(self.embed_dim, self.depth, self.num_heads, use_cls=self.use_cls,
+                                norm_name="norm" if self.use_cls else "norm_frame", prefix="", max_frames=self.spec_w)
+            rt = dict(device=device, fp=fp, eng=eng, ws=Workspace(device))
+            self._inf = rt
+        return rt
+
+    @torch.no_grad()
+    def _run(self, x, length, collect=0, mask_index=None, mask_input=False):
+        from ... import ops
+        rt = self._inference_runtime(x.device)
+        fp = rt["fp"]
+        ops.round_tf32(fp.data, fp.compute)
+        out, ctx = rt["eng"].forward(fp, rt["ws"], x.contiguous().float(), length, dp=None, save=False, tag="inf",
+                                     mask=mask_index, mask_input=mask_input, collect=collect, round_final=False)
+        return out, ctx
+
+    @torch.no_grad()
+    def get_intermediate_layers(self, x, length, n=1, scene=True):
+        """final-norm token outputs of the last n blocks.  AST: list of [B, N, D] (models/atst/audio_transformer.py:
+        235-256).  FrameAST: concatenation over layers of the length-masked mean (scene=True) or of the frame
+        sequences (scene=False) (methods/atstframe/audio_transformer.py:259-281)."""
+        B = x.shape[0]
+        _, ctx = self._run(x, length, collect=n)
+        N = ctx["N"]
+        layers = [y.view(B, N, self.embed_dim).clone() for y in ctx["collected"]]
+        if self.use_cls:
+            return layers
+        if not scene:
+            return torch.cat(layers, dim=-1)
+        plen = (length - length % self.patch_w) // self.patch_w
+        mask = (torch.arange(N, device=x.device) < plen.unsqueeze(1)).unsqueeze(-1)
+        return torch.cat([torch.sum(y * mask, dim=1) / (plen.unsqueeze(-1) + 1e-6) for y in layers], dim=-1)
+
+    @torch.no_grad()
+    def get_intermediate_layers_chunks(self, x, length, n=1, chunk_len=601, avgpool=True):
+        """long audio in chunk_len-frame chunks, CLS / mean-pooled tokens of the last n blocks averaged over the
+        chunks that contain audio (models/atst/audio_transformer.py:257-353)."""
+        total_len = x.shape[-1]
+        num_chunks = total_len // chunk_len + 1
+        cls, avg, marks = [], [], []
+        for i in range(num_chunks):
+            cur_len = torch.clip(length - i * chunk_len, 0)
+            marks.append(cur_len > 0 if i == 0 else cur_len > chunk_len // 2)
+            xc = x[:, :, :, i * chunk_len:min((i + 1) * chunk_len, total_len)]
+            if xc.shape[-1] < self.patch_w:
+                marks.pop()
+                continue
+            B = xc.shape[0]
+            _, ctx = self._run(xc, cur_len, collect=n)
+            outs = [y.view(B, ctx["N"], self.embed_dim) for y in ctx["collected"]]
+            plen = (cur_len - cur_len % self.patch_w) // self.patch_w
+            c_, a_ = get_cls_avg(outs, plen, self.use_cls)
+            cls.append(c_)
+            avg.append(a_)
+        mark = torch.stack(marks, dim=0).unsqueeze(-1).float()  # [chunks, B, 1]
+        cls_out = [torch.sum(torch.stack(list(c), 0) * mark, 0) / torch.sum(mark, 0) for c in zip(*cls)]
+        avg_out = [torch.sum(torch.stack(list(a), 0) * mark, 0) / torch.sum(mark, 0) for a in zip(*avg)]
+        return torch.cat(cls_out + avg_out, dim=-1) if avgpool else torch.cat(cls_out, dim=-1)
+
+
+class AST(_EncoderInference, nn.Module):
     def __init__(self, use_cls=True, spec_h=64, spec_w=1001, patch_w=16, patch_h=16, in_chans=1, num_classes=0,
                  embed_dim=768, depth=12, num_heads=12, mlp_ratio=4., qkv_bias=False, qk_scale=None, drop_rate=0.,
                  attn_drop_rate=0., drop_path_rate=0.1, norm_layer=nn.LayerNorm, mask_ratio=0, pos_type="cut",
@@ -67,6 +157,15 @@ class AST(nn.Module):
         elif isinstance(m, nn.LayerNorm):
             nn.init.constant_(m.bias, 0)
             nn.init.constant_(m.weight, 1.0)
+
+    @torch.no_grad()
+    def forward(self, x, mask_index=None, length=None, avg=False):
+        """stand-alone (inference) forward: final-norm CLS embedding [B, D] (audio_transformer.py:188-210).
+        Training goes through ATST.forward, which drives both networks and the backward pass."""
+        if avg or mask_index is not None:
+            raise NotImplementedError("avg=True / mask_index are not used by the ATST-clip recipes")
+        out, _ = self._run(x, length)
+        return out.clone()
 
 
 def AST_small(patch_h=64, patch_w=4, **kwargs):

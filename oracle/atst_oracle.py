@@ -230,6 +230,35 @@ class OracleAST(nn.Module):
         return x[mask_index.bool() & lm]
 
 
+def oracle_intermediate(enc, mel, length, n=1):
+    """final-norm token outputs of the last n blocks (inference; models/atst/audio_transformer.py:235-256)."""
+    x, plen = enc.tokens(mel, length, None, False)
+    outs = []
+    for i, blk in enumerate(enc.blocks):
+        x = blk(x, plen + 1 if enc.use_cls else plen)
+        if len(enc.blocks) - i <= n:
+            outs.append(getattr(enc, enc.norm_name)(x))
+    return outs, plen
+
+
+def oracle_intermediate_chunks(enc, mel, length, n=1, chunk_len=601):
+    """models/atst/audio_transformer.py:257-353 (avgpool=True): chunked CLS + masked-mean pooling."""
+    total = mel.shape[-1]
+    cls, avg, marks = [], [], []
+    for i in range(total // chunk_len + 1):
+        cur = torch.clip(length - i * chunk_len, 0)
+        marks.append(cur > 0 if i == 0 else cur > chunk_len // 2)
+        xc = mel[..., i * chunk_len:min((i + 1) * chunk_len, total)]
+        outs, plen = oracle_intermediate(enc, xc, cur, n)
+        lm = (torch.arange(outs[0].shape[1] - 1)[None, :] < plen[:, None]).unsqueeze(-1)
+        cls.append([o[:, 0] for o in outs])
+        avg.append([(o[:, 1:] * lm).sum(1) / (plen[:, None] + 1e-6) for o in outs])
+    mark = torch.stack(marks).unsqueeze(-1).float()
+    co = [(torch.stack(list(c)) * mark).sum(0) / mark.sum(0) for c in zip(*cls)]
+    ao = [(torch.stack(list(a)) * mark).sum(0) / mark.sum(0) for a in zip(*avg)]
+    return torch.cat(co + ao, dim=-1)
+
+
 def build_mlp(in_dim, hidden, out_dim):
     return nn.Sequential(nn.Linear(in_dim, hidden, bias=False), nn.BatchNorm1d(hidden),
                          nn.ReLU(inplace=True), nn.Linear(hidden, out_dim, bias=False))

@@ -252,6 +252,35 @@ def gen_frame():
     print("frame.npz", len(out))
 
 
+def gen_infer():
+    """inference entry points: get_intermediate_layers[_chunks] in eval mode."""
+    harness()
+    frame_stubs()
+    from audiossl.models.atst.audio_transformer import AST
+    from audiossl.methods.atstframe.audio_transformer import FrameAST
+    out = {}
+    kw = dict(patch_h=64, patch_w=4, embed_dim=128, depth=3, num_heads=2, qkv_bias=False,
+              norm_layer=partial(nn.LayerNorm, eps=1e-6))
+    enc = AST(**kw)
+    load_det(enc)
+    enc.eval()
+    x = torch.from_numpy(detfill.det_array("infer/x", (3, 1, 64, 250), 1.0, "uniform"))
+    length = torch.tensor([250, 180, 40])
+    with torch.no_grad():
+        out["clip/cls"] = enc(x[..., :101], length=torch.tensor([101, 101, 40])).numpy()
+        layers = enc.get_intermediate_layers(x[..., :101], torch.tensor([101, 101, 40]), n=2)
+        out["clip/layers"] = torch.stack(layers).numpy()
+        out["clip/chunks"] = enc.get_intermediate_layers_chunks(x, length, n=2, chunk_len=101, avgpool=True).numpy()
+    fenc = FrameAST(**kw)
+    load_det(fenc)
+    fenc.eval()
+    with torch.no_grad():
+        out["frame/scene"] = fenc.get_intermediate_layers(x[..., :101], torch.tensor([101, 101, 40]), n=2, scene=True).numpy()
+        out["frame/seq"] = fenc.get_intermediate_layers(x[..., :101], torch.tensor([101, 101, 40]), n=2, scene=False).numpy()
+    np.savez_compressed(os.path.join(HERE, "infer.npz"), **out)
+    print("infer.npz", len(out))
+
+
 def gen_sched():
     from audiossl.utils.common import cosine_scheduler_step, get_params_groups
     out = {"ema": cosine_scheduler_step(0.99, 1, 1000, 0), "wd": cosine_scheduler_step(0.04, 0.4, 1000, 0),
@@ -269,4 +298,5 @@ if __name__ == "__main__":
     gen_mel()
     gen_atst()
     gen_frame()
+    gen_infer()
     gen_sched()

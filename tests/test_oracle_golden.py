@@ -143,3 +143,24 @@ def test_frame_model_matches_reference(case):
             util.check_summary(p.grad.numpy(), g, key, rtol=2e-3, atol=2e-4)
             n += 1
     assert n > 20 and m.student.encoder.mask_embed.grad is not None
+
+
+def test_inference_entry_points_match_reference():
+    g = util.gold("infer.npz")
+    x = torch.from_numpy(detfill.det_array("infer/x", (3, 1, 64, 250), 1.0, "uniform"))
+    l101 = torch.tensor([101, 101, 40])
+    enc = O.OracleAST(128, 3, 2)
+    util.load_det(enc)
+    enc.eval()
+    with torch.no_grad():
+        np.testing.assert_allclose(enc(x[..., :101], l101).numpy(), g["clip/cls"], rtol=2e-4, atol=2e-5)
+        outs, _ = O.oracle_intermediate(enc, x[..., :101], l101, 2)
+        np.testing.assert_allclose(torch.stack(outs).numpy(), g["clip/layers"], rtol=2e-4, atol=2e-5)
+        ch = O.oracle_intermediate_chunks(enc, x, torch.tensor([250, 180, 40]), 2, 101)
+        np.testing.assert_allclose(ch.numpy(), g["clip/chunks"], rtol=2e-4, atol=2e-5)
+    fenc = O.OracleAST(128, 3, 2, use_cls=False, norm_name="norm_frame")
+    util.load_det(fenc)
+    fenc.eval()
+    with torch.no_grad():
+        outs, plen = O.oracle_intermediate(fenc, x[..., :101], l101, 2)
+        np.testing.assert_allclose(torch.cat(outs, -1).numpy(), g["frame/seq"], rtol=2e-4, atol=2e-5)

@@ -325,3 +325,29 @@ def test_frame_step_matches_reference_golden(case):
     np.testing.assert_allclose(std_t.item(), g[case + "/std_t"], rtol=1e-3)
     assert m.student.encoder.mask_embed.grad is not None
     check_grads(m, g, case, 2e-1)
+
+
+# --------------------------------------------------------------------------- inference entry points (row f3)
+def test_inference_entry_points_match_reference_golden():
+    from functools import partial
+    from torch import nn
+    from audiossl_b200.methods.atstframe.audio_transformer import FrameAST
+    from audiossl_b200.models.atst.audio_transformer import AST
+    g = util.gold("infer.npz")
+    kw = dict(patch_h=64, patch_w=4, embed_dim=128, depth=3, num_heads=2, qkv_bias=False,
+              norm_layer=partial(nn.LayerNorm, eps=1e-6))
+    x = torch.from_numpy(detfill.det_array("infer/x", (3, 1, 64, 250), 1.0, "uniform")).cuda()
+    l101 = torch.tensor([101, 101, 40]).cuda()
+    enc = AST(**kw)
+    util.load_det(enc)
+    enc.cuda().eval()
+    assert rel(enc(x[..., :101].contiguous(), length=l101), g["clip/cls"]) < 2e-3
+    layers = enc.get_intermediate_layers(x[..., :101].contiguous(), l101, n=2)
+    assert rel(torch.stack(layers), g["clip/layers"]) < 2e-3
+    ch = enc.get_intermediate_layers_chunks(x, torch.tensor([250, 180, 40]).cuda(), n=2, chunk_len=101)
+    assert tuple(ch.shape) == g["clip/chunks"].shape and rel(ch, g["clip/chunks"]) < 2e-3
+    fenc = FrameAST(**kw)
+    util.load_det(fenc)
+    fenc.cuda().eval()
+    assert rel(fenc.get_intermediate_layers(x[..., :101].contiguous(), l101, n=2, scene=True), g["frame/scene"]) < 2e-3
+    assert rel(fenc.get_intermediate_layers(x[..., :101].contiguous(), l101, n=2, scene=False), g["frame/seq"]) < 2e-3
