@@ -106,7 +106,7 @@ class _EncoderInference:
             outs = [y.view(B, ctx["N"], self.embed_dim) for y in ctx["collected"]]
             plen = (cur_len - cur_len % self.patch_w) // self.patch_w
             c_, a_ = get_cls_avg(outs, plen, self.use_cls)
-            cls.append(c_)
+            cls.append([t.clone() for t in c_])  # views of the reused workspace: copy before the next chunk runs
             avg.append(a_)
         mark = torch.stack(marks, dim=0).unsqueeze(-1).float()  # [chunks, B, 1]
         cls_out = [torch.sum(torch.stack(list(c), 0) * mark, 0) / torch.sum(mark, 0) for c in zip(*cls)]
