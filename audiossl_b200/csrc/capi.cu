@@ -154,6 +154,14 @@ int atst_adamw_step(float* p, const float* g, float* m, float* v, long long n, i
                     float beta1, float beta2, float eps, float grad_scale, void* stream) {
   return adamw_step(p, g, m, v, n, step, lr, wd, beta1, beta2, eps, grad_scale, ST(stream));
 }
+int atst_mixup_forward(const float* x, const float* bank, const int* idx, const float* alpha, float* out,
+                       long long per_clip, int B, void* stream) {
+  return mixup_forward(x, bank, idx, alpha, out, per_clip, B, ST(stream));
+}
+int atst_resize_crop_forward(const float* lms, const int* rect, float* out, int B, int Hm, int T, int canvas_h,
+                             int canvas_w, void* stream) {
+  return resize_crop_forward(lms, rect, out, B, Hm, T, canvas_h, canvas_w, ST(stream));
+}
 int atst_gather_rows(const float* x, const int* idx, float* out, int rows, int D, void* stream) {
   return gather_rows(x, idx, out, rows, D, ST(stream));
 }

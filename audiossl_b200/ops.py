@@ -283,6 +283,23 @@ def adamw_step(p, g, m, v, step, lr, wd, beta1=0.9, beta2=0.999, eps=1e-6, grad_
     _count(1)
 
 
+def mixup_fwd(x, bank, idx, alpha, out):
+    B = x.shape[0]
+    per_clip = x.numel() // B
+    check(_lib.lib().atst_mixup_forward(ptr(x), ptr(bank), ptr(idx), ptr(alpha), ptr(out), per_clip, B, _lib.stream()),
+          "atst_mixup_forward")
+    _count(1)
+    return out
+
+
+def resize_crop_fwd(lms, rect, out, canvas_h, canvas_w):
+    B, Hm, T = lms.shape[0], lms.shape[-2], lms.shape[-1]
+    check(_lib.lib().atst_resize_crop_forward(ptr(lms), ptr(rect), ptr(out), B, Hm, T, canvas_h, canvas_w,
+                                              _lib.stream()), "atst_resize_crop_forward")
+    _count(1)
+    return out
+
+
 def gather_rows(x, idx, out):
     rows, D = out.shape
     check(_lib.lib().atst_gather_rows(ptr(x), ptr(idx), ptr(out), rows, D, _lib.stream()), "atst_gather_rows")

@@ -113,6 +113,15 @@ int atst_ema_update(float* k, const float* q, float m, long long n, void* stream
 int atst_adamw_step(float* p, const float* g, float* m, float* v, long long n, int step, float lr, float wd,
                     float beta1, float beta2, float eps, float grad_scale, void* stream);
 
+/* ---- device-batched augmentations between mel and encoder (audiossl/transforms/byol_a.py:7-49,61-115):
+ *   mixup: out[b] = log((1-alpha[b]) e^x[b] + alpha[b] e^bank[idx[b]] + eps), idx[b] < 0 copies x[b]
+ *   resize_crop: crop rect[b] = (i, j, h, w) of the zero canvas [canvas_h, canvas_w] holding lms[b] centred,
+ *                bicubic (align_corners=True, A=-0.75) resize back to [Hm, T] */
+int atst_mixup_forward(const float* x, const float* bank, const int* idx, const float* alpha, float* out,
+                       long long per_clip, int B, void* stream);
+int atst_resize_crop_forward(const float* lms, const int* rect, float* out, int B, int Hm, int T, int canvas_h,
+                             int canvas_w, void* stream);
+
 /* ---- ATST-Frame row selection (audiossl/methods/atstframe/audio_transformer.py:187-207: frame_repr[mask & valid]):
  *      out[r] = x[idx[r]] and its adjoint dst[idx[r]] = src[r] (dst pre-zeroed, unique indices) */
 int atst_gather_rows(const float* x, const int* idx, float* out, int rows, int D, void* stream);

@@ -259,6 +259,23 @@ def oracle_intermediate_chunks(enc, mel, length, n=1, chunk_len=601):
     return torch.cat(co + ao, dim=-1)
 
 
+def oracle_resize_crop(lms, rect, virtual_crop_scale=(1.0, 1.5)):
+    """RandomResizeCrop.forward with the random draws given (transforms/byol_a.py:34-49): lms [C,H,W]."""
+    c, h, w = lms.shape
+    ch, cw = int(h * virtual_crop_scale[0]), int(w * virtual_crop_scale[1])
+    canvas = torch.zeros((c, ch, cw))
+    x0, y0 = (cw - w) // 2, (ch - h) // 2
+    canvas[:, y0:y0 + h, x0:x0 + w] = lms
+    i, j, hh, ww = rect
+    crop = canvas[:, i:i + hh, j:j + ww]
+    return F.interpolate(crop.unsqueeze(0), size=(h, w), mode="bicubic", align_corners=True).squeeze(0)
+
+
+def oracle_log_mixup_exp(x, z, alpha):
+    """log((1-alpha) e^x + alpha e^z + eps) (transforms/byol_a.py:61-82 with equal lengths; Mixup passes 1-alpha)."""
+    return torch.log((1.0 - alpha) * x.exp() + alpha * z.exp() + torch.finfo(x.dtype).eps)
+
+
 def build_mlp(in_dim, hidden, out_dim):
     return nn.Sequential(nn.Linear(in_dim, hidden, bias=False), nn.BatchNorm1d(hidden),
                          nn.ReLU(inplace=True), nn.Linear(hidden, out_dim, bias=False))

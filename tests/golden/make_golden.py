@@ -281,6 +281,27 @@ def gen_infer():
     print("infer.npz", len(out))
 
 
+AUG_RECTS = [(0, 0, 64, 151), (0, 25, 64, 101), (0, 10, 38, 60), (13, 40, 51, 111), (0, 150, 64, 1), (63, 0, 1, 151)]
+
+
+def gen_augment():
+    """Mixup arithmetic and RandomResizeCrop with injected draws."""
+    from audiossl.transforms.byol_a import RandomResizeCrop, log_mixup_exp
+    out = {}
+    lms = torch.from_numpy(detfill.det_array("aug/lms", (len(AUG_RECTS), 1, 64, 101), 1.0, "uniform"))
+    rrc = RandomResizeCrop((1, 1.5))
+    res = []
+    for b, rect in enumerate(AUG_RECTS):
+        RandomResizeCrop.get_params = staticmethod(lambda *a, rect=rect: rect)
+        res.append(rrc(lms[b]))
+    out["rrc"] = torch.stack(res).numpy()
+    z = torch.from_numpy(detfill.det_array("aug/bank", (3, 1, 64, 101), 1.0, "uniform"))
+    alphas = [0.0, 0.13, 0.4]
+    out["mixup"] = torch.stack([log_mixup_exp(lms[b].clone(), z[b].clone(), 1.0 - alphas[b]) for b in range(3)]).numpy()
+    np.savez_compressed(os.path.join(HERE, "augment.npz"), **out)
+    print("augment.npz", len(out))
+
+
 def gen_sched():
     from audiossl.utils.common import cosine_scheduler_step, get_params_groups
     out = {"ema": cosine_scheduler_step(0.99, 1, 1000, 0), "wd": cosine_scheduler_step(0.04, 0.4, 1000, 0),
@@ -299,4 +320,5 @@ if __name__ == "__main__":
     gen_atst()
     gen_frame()
     gen_infer()
+    gen_augment()
     gen_sched()

@@ -164,3 +164,16 @@ def test_inference_entry_points_match_reference():
     with torch.no_grad():
         outs, plen = O.oracle_intermediate(fenc, x[..., :101], l101, 2)
         np.testing.assert_allclose(torch.cat(outs, -1).numpy(), g["frame/seq"], rtol=2e-4, atol=2e-5)
+
+
+AUG_RECTS = [(0, 0, 64, 151), (0, 25, 64, 101), (0, 10, 38, 60), (13, 40, 51, 111), (0, 150, 64, 1), (63, 0, 1, 151)]
+
+
+def test_augmentations_match_reference():
+    g = util.gold("augment.npz")
+    lms = torch.from_numpy(detfill.det_array("aug/lms", (len(AUG_RECTS), 1, 64, 101), 1.0, "uniform"))
+    for b, rect in enumerate(AUG_RECTS):
+        np.testing.assert_allclose(O.oracle_resize_crop(lms[b], rect).numpy(), g["rrc"][b], rtol=1e-5, atol=1e-6)
+    z = torch.from_numpy(detfill.det_array("aug/bank", (3, 1, 64, 101), 1.0, "uniform"))
+    for b, a in enumerate([0.0, 0.13, 0.4]):
+        np.testing.assert_allclose(O.oracle_log_mixup_exp(lms[b], z[b], a).numpy(), g["mixup"][b], rtol=1e-5, atol=1e-6)

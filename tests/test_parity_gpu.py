@@ -351,3 +351,25 @@ def test_inference_entry_points_match_reference_golden():
     fenc.cuda().eval()
     assert rel(fenc.get_intermediate_layers(x[..., :101].contiguous(), l101, n=2, scene=True), g["frame/scene"]) < 2e-3
     assert rel(fenc.get_intermediate_layers(x[..., :101].contiguous(), l101, n=2, scene=False), g["frame/seq"]) < 2e-3
+
+
+# --------------------------------------------------------------------------- device-batched augmentations (row f1)
+AUG_RECTS = [(0, 0, 64, 151), (0, 25, 64, 101), (0, 10, 38, 60), (13, 40, 51, 111), (0, 150, 64, 1), (63, 0, 1, 151)]
+
+
+def test_batched_augmentations_match_reference_golden():
+    from audiossl_b200.transforms import BatchedMixup, BatchedRandomResizeCrop
+    g = util.gold("augment.npz")
+    lms = torch.from_numpy(detfill.det_array("aug/lms", (len(AUG_RECTS), 1, 64, 101), 1.0, "uniform")).cuda()
+    out = BatchedRandomResizeCrop((1, 1.5))(lms, rect=AUG_RECTS)
+    assert tuple(out.shape) == g["rrc"].shape
+    np.testing.assert_allclose(out.cpu().numpy(), g["rrc"], rtol=1e-4, atol=2e-5)
+    z = torch.from_numpy(detfill.det_array("aug/bank", (3, 1, 64, 101), 1.0, "uniform")).cuda()
+    mx = BatchedMixup(n_memory=8)
+    first = mx(z)  # empty bank: identity, and the batch becomes bank entries 0..2
+    assert torch.equal(first, z)
+    mixed = mx(lms[:3], alpha=[0.0, 0.13, 0.4], idx=[0, 1, 2])
+    np.testing.assert_allclose(mixed.cpu().numpy(), g["mixup"], rtol=1e-4, atol=2e-5)
+    assert mx.size == 6
+    rnd = BatchedRandomResizeCrop()(lms)  # random draws: shape / finiteness only
+    assert rnd.shape == lms.shape and torch.isfinite(rnd).all()
