@@ -144,7 +144,10 @@ __global__ void __launch_bounds__(128) attn_kernel(AttnParams p) {
   const int r0 = blockIdx.x * kAttnRows;
   const int h = blockIdx.y, s = blockIdx.z;
   const int N = p.N, D = p.D, ld3 = 3 * D;
-  const int len = p.lengths ? p.lengths[s] : N;
+  // keys >= length are masked; a length beyond the sequence masks nothing, and length <= 0 masks EVERY key, which
+  // shifts all scores by the same -10000 and leaves the softmax unchanged (reference semantics)
+  int len = p.lengths ? p.lengths[s] : N;
+  if (len <= 0 || len > N) len = N;
   const size_t tok0 = static_cast<size_t>(s) * N;
   const float* qp = p.qkv + tok0 * ld3 + h * kHd;
   const float* kp = qp + D;

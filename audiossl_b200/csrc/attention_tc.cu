@@ -55,7 +55,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, s = blockIdx.z;
   const int N = p.N, D = p.D;
-  const int len = p.lengths ? p.lengths[s] : N;
+  int len = p.lengths ? p.lengths[s] : N;
+  if (len <= 0 || len > N) len = N;  // see attention.cu
   const int nq = (len + 63) >> 6;  // 64-key quarters that contain valid keys
   const int row0 = s * N;          // first token row of this sequence in the [S*N, 3D] tensor
 

@@ -100,7 +100,7 @@ def test_attention_matches_reference_formula():
     S, N, H = 3, 151, 6
     D = H * 64
     qkv = ops.round_tf32(torch.randn(S * N, 3 * D, device="cuda"))
-    lengths = torch.tensor([N, 77, 1], dtype=torch.int32, device="cuda")
+    lengths = torch.tensor([N + 40, 77, 0], dtype=torch.int32, device="cuda")  # beyond the sequence / fully masked
     q = qkv.clone().requires_grad_(True)
     t = q.reshape(S, N, 3, H, 64).permute(2, 0, 3, 1, 4)
     att = (t[0] @ t[1].transpose(-2, -1)) * 0.125
