@@ -23,6 +23,7 @@ SIGNATURES = {
     "atst_gemm_nn": [P, I, P, I, P, I, I, I, I, I, P, I, P, I, I, P],
     "atst_gemm_tn": [P, I, P, I, P, I, I, I, I, P],
     "atst_gemm_mn_debug": [I, P, I, P, I, P, I, I, I, I, U, U, U, U, I, I, P],
+    "atst_umma_probe": [I, P, P, P, U, U, U, U, P],
     "atst_layernorm_forward": [P, L, P, P, P, L, P, P, I, I, F, I, P],
     "atst_layernorm_backward": [P, L, P, L, P, P, P, P, L, P, L, P, P, I, I, P, L, P, I, P, P],
     "atst_attention_forward": [P, P, P, P, I, I, I, P],

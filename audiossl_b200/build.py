@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libatst_b200.so")
-SOURCES = ["err.cu", "capi.cu", "gemm_tcgen05.cu", "gemm2_tcgen05.cu", "mel.cu", "attention.cu", "attention_tc.cu", "layernorm.cu", "elementwise.cu", "augment.cu",
+SOURCES = ["err.cu", "capi.cu", "gemm_tcgen05.cu", "gemm2_tcgen05.cu", "mel.cu", "attention.cu", "attention_tc.cu", "attention_bwd_tc.cu", "probe.cu", "layernorm.cu", "elementwise.cu", "augment.cu",
            "loss_optim.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "--use_fast_math=false" if False else "-Xptxas=-v"]

@@ -345,12 +345,20 @@ static int launch_attn(const AttnParams& p, int S, cudaStream_t stream) {
 
 int attention_forward_tc(const float* qkv, float* o, float* lse, const int* lengths, int S, int N, int H,
                          cudaStream_t stream);
-int attention_tc_enabled();
+int attention_backward_tc(const float* qkv, const float* o, const float* d_o, const float* lse, float* delta_ws,
+                          float* dqkv, const int* lengths, int S, int N, int H, cudaStream_t stream);
+int attention_tc_enabled();  // bit 0: forward on tcgen05, bit 1: backward on tcgen05
+
+int attention_delta(const float* o, const float* d_o, float* delta, int S, int N, int H, cudaStream_t stream) {
+  const long long threads = static_cast<long long>(S) * N * 32;
+  attn_delta_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(o, d_o, delta, S, N, H, H * kHd);
+  return atst_check_launch("attn_delta_kernel");
+}
 
 int attention_forward(const float* qkv, float* o, float* lse, const int* lengths, int S, int N, int H,
                       cudaStream_t stream) {
   ATST_REQUIRE(S > 0 && N > 0 && H > 0, "attention_forward: bad shape S=%d N=%d H=%d", S, N, H);
-  if (attention_tc_enabled() && N <= 256) return attention_forward_tc(qkv, o, lse, lengths, S, N, H, stream);
+  if ((attention_tc_enabled() & 1) && N <= 256) return attention_forward_tc(qkv, o, lse, lengths, S, N, H, stream);
   AttnParams p{};
   p.qkv = qkv; p.out_o = o; p.lse = lse; p.lengths = lengths;
   p.N = N; p.H = H; p.D = H * kHd; p.scale = 0.125f;
@@ -360,10 +368,10 @@ int attention_forward(const float* qkv, float* o, float* lse, const int* lengths
 int attention_backward(const float* qkv, const float* o, const float* d_o, const float* lse, float* delta_ws,
                        float* dqkv, const int* lengths, int S, int N, int H, cudaStream_t stream) {
   ATST_REQUIRE(S > 0 && N > 0 && H > 0, "attention_backward: bad shape S=%d N=%d H=%d", S, N, H);
+  if ((attention_tc_enabled() & 2) && N <= 256)
+    return attention_backward_tc(qkv, o, d_o, lse, delta_ws, dqkv, lengths, S, N, H, stream);
   const int D = H * kHd;
-  const long long threads = static_cast<long long>(S) * N * 32;
-  attn_delta_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(o, d_o, delta_ws, S, N, H, D);
-  int rc = atst_check_launch("attn_delta_kernel");
+  int rc = attention_delta(o, d_o, delta_ws, S, N, H, stream);
   if (rc) return rc;
   AttnParams p{};
   p.qkv = qkv; p.o = o; p.d_o = d_o; p.dqkv = dqkv; p.lse = const_cast<float*>(lse); p.delta = delta_ws;

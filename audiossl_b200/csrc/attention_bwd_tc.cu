@@ -1,0 +1,336 @@
+// Attention backward on tcgen05 for sequences of up to 256 tokens (every ATST config: N <= 251).  Same math and
+// outputs as attn_kernel<1> / attn_kernel<2> in attention.cu (reference: modules/transformer.py:107-121 under
+// autograd); TF32 operands, fp32 accumulation in tensor memory, fp32 softmax algebra.
+//
+// One templated kernel, two launches per layer (scores are recomputed in each, as in the mma.sync version):
+//   MODE 0 (dQ)     rows = queries, column blocks = keys.   S = Q K^T, dP = dO V^T, P = exp2(S c - L_row),
+//                   dS = P (dP - delta_row),  dQ = scale * dS K
+//   MODE 1 (dK dV)  rows = keys, column blocks = queries.   S^T = K Q^T, dP^T = V dO^T, P^T = exp2(S^T c - L_col),
+//                   dS^T = P^T (dP^T - delta_col),  dV = P^T dO,  dK = scale * dS^T Q
+//
+// One CTA per (sequence, head); it walks the 128-row tiles of the "row" operand and, per tile, the 64-wide
+// quarters of the "column" operand.  Operands are TMA-loaded ONCE in the token-major 32B-atom 128B swizzle and read
+// by the tensor core both K-major (contraction over the head dim: S, dP) and MN-major (contraction over tokens:
+// dQ / dK / dV) from the same bytes (profiles/r01_umma_operand_probe.log).  P and dS never touch shared memory: the
+// compute warps overwrite the S / dP quarter in tensor memory with tf32(P) / tf32(dS) (tcgen05.st) and the second
+// stage MMAs take that as their TMEM A operand.
+//
+// Shared memory (193 KB): R1, R2 = the row tile's two operands [2 k-chunks][128 rows][128 B]; Y1, Y2 = the column
+// operands [4 quarters][2 k-chunks][64 rows][128 B]; per-column lse / delta for MODE 1.
+// Tensor memory (512 columns): accumulators acc1 [0,64) (dQ | dK), acc2 [64,128) (dV); three ring slots of
+// {S quarter, dP quarter} at 128 + 128 s.
+// Warps: 0 TMA producer, 1 MMA issuer (one lane), 2 TMEM allocator, 4-11 compute (thread = row = TMEM lane; the two
+// warps of a lane quadrant split each quarter's 64 columns).
+#include "common.cuh"
+
+namespace atst {
+
+namespace {
+
+constexpr int kR1 = 0;
+constexpr int kR2 = 32 * 1024;
+constexpr int kY1 = 64 * 1024;
+constexpr int kY2 = 128 * 1024;
+constexpr int kStat = 192 * 1024;          // [2][256] floats
+constexpr int kBars = kStat + 2 * 256 * 4;  // mbarriers
+constexpr int kSmemBwd = 1024 + kBars + 256;
+constexpr int kSlots = 3;
+constexpr uint32_t kKLbo = 4096, kSbo = 512, kLayout = 1;  // 32B-atom 128B swizzle (see the operand probe)
+
+struct BwdTcParams {
+  float* dqkv;         // [S*N, 3D]
+  const float* lse;    // [S, H, N] log2 domain
+  const float* delta;  // [S, H, N]
+  const int* lengths;
+  int N, H, D;
+  float scale;
+};
+
+}  // namespace
+
+template <int MODE>
+__global__ void __launch_bounds__(384, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvR, const __grid_constant__ CUtensorMap tmQkvY,
+                   const __grid_constant__ CUtensorMap tmDoR, const __grid_constant__ CUtensorMap tmDoY, BwdTcParams p) {
+  extern __shared__ uint8_t smem_raw_bwd[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_bwd) + 1023) & ~uintptr_t(1023));
+  float* sL = reinterpret_cast<float*>(smem + kStat);
+  float* sD = sL + 256;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBars);
+  uint64_t* bar_r = bars + 0;
+  uint64_t* bar_rfree = bars + 1;
+  uint64_t* bar_acc = bars + 2;
+  uint64_t* bar_accfree = bars + 3;
+  uint64_t* bar_y = bars + 4;      // [4]
+  uint64_t* bar_full = bars + 8;   // [3]
+  uint64_t* bar_ds = bars + 11;    // [3]
+  uint64_t* bar_free = bars + 14;  // [3]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x, s = blockIdx.y;
+  const int N = p.N, D = p.D;
+  int len = p.lengths ? p.lengths[s] : N;
+  if (len <= 0 || len > N) len = N;  // see attention.cu
+  const int row0 = s * N;  // first token row of this sequence
+  const int tiles = (N + 127) >> 7;
+  const int ncols = (MODE == 0) ? len : N;  // dQ only needs keys < len; dK/dV walk every query
+  const int nq = (ncols + 63) >> 6;
+  const int W = tiles * nq;  // work quarters
+  // 32-float chunk index (third TMA coordinate) of this head's q / k / v / dO columns
+  const int cq = (h * 64) >> 5, ck = (D + h * 64) >> 5, cv = (2 * D + h * 64) >> 5, cdo = (h * 64) >> 5;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQkvR);
+    tma_prefetch_desc(&tmQkvY);
+    tma_prefetch_desc(&tmDoR);
+    tma_prefetch_desc(&tmDoY);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(bar_r, 1);
+    mbar_init(bar_rfree, 1);
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_accfree, 256);
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_y[i], 1);
+    for (int i = 0; i < kSlots; ++i) {
+      mbar_init(&bar_full[i], 1);
+      mbar_init(&bar_ds[i], 256);
+      mbar_init(&bar_free[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_acc1 = tmem_base, tm_acc2 = tmem_base + 64;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      auto load_rows = [&](int t) {
+        mbar_expect_tx(bar_r, 64 * 1024);
+        const int r = row0 + t * 128;
+        if (MODE == 0) {
+          tma_load_3d(smem + kR1, &tmQkvR, bar_r, 0, r, cq);
+          tma_load_3d(smem + kR2, &tmDoR, bar_r, 0, r, cdo);
+        } else {
+          tma_load_3d(smem + kR1, &tmQkvR, bar_r, 0, r, ck);
+          tma_load_3d(smem + kR2, &tmQkvR, bar_r, 0, r, cv);
+        }
+      };
+      load_rows(0);
+      for (int q = 0; q < nq; ++q) {
+        mbar_expect_tx(&bar_y[q], 32 * 1024);
+        const int r = row0 + q * 64;
+        if (MODE == 0) {
+          tma_load_3d(smem + kY1 + q * 16384, &tmQkvY, &bar_y[q], 0, r, ck);
+          tma_load_3d(smem + kY2 + q * 16384, &tmQkvY, &bar_y[q], 0, r, cv);
+        } else {
+          tma_load_3d(smem + kY1 + q * 16384, &tmQkvY, &bar_y[q], 0, r, cq);
+          tma_load_3d(smem + kY2 + q * 16384, &tmDoY, &bar_y[q], 0, r, cdo);
+        }
+      }
+      for (int t = 1; t < tiles; ++t) {
+        mbar_wait(bar_rfree, (t - 1) & 1);  // every S / dP MMA of tile t-1 has read R1, R2
+        load_rows(t);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    const uint32_t idesc_s = make_idesc(2u, 128, 64, 0u, 0u);    // A, B K-major
+    const uint32_t idesc_acc = make_idesc(2u, 128, 64, 0u, 1u);  // A in TMEM (K-major), B MN-major
+    const uint32_t r1 = smem_u32(smem + kR1), r2 = smem_u32(smem + kR2);
+    const uint32_t y1 = smem_u32(smem + kY1), y2 = smem_u32(smem + kY2);
+    auto produce = [&](int i) {
+      const int t = i / nq, q = i - t * nq, slot = i % kSlots, u = i / kSlots;
+      if (q == 0) mbar_wait(bar_r, t & 1);
+      if (t == 0) mbar_wait(&bar_y[q], 0);
+      if (u > 0) mbar_wait(&bar_free[slot], (u - 1) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t tm_s = tmem_base + 128 + slot * 128, tm_dp = tm_s + 64;
+#pragma unroll
+        for (int kc = 0; kc < 2; ++kc)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_tf32(tm_s, make_smem_desc(r1 + kc * 16384 + k * 32, kKLbo, kSbo, kLayout),
+                      make_smem_desc(y1 + q * 16384 + kc * 8192 + k * 32, kKLbo, kSbo, kLayout), idesc_s,
+                      (kc | k) ? 1u : 0u);
+#pragma unroll
+        for (int kc = 0; kc < 2; ++kc)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_tf32(tm_dp, make_smem_desc(r2 + kc * 16384 + k * 32, kKLbo, kSbo, kLayout),
+                      make_smem_desc(y2 + q * 16384 + kc * 8192 + k * 32, kKLbo, kSbo, kLayout), idesc_s,
+                      (kc | k) ? 1u : 0u);
+        umma_commit(&bar_full[slot]);
+        if (q == nq - 1) umma_commit(bar_rfree);
+      }
+      __syncwarp();
+    };
+    auto consume = [&](int i) {
+      const int t = i / nq, q = i - t * nq, slot = i % kSlots, u = i / kSlots;
+      mbar_wait(&bar_ds[slot], u & 1);
+      if (q == 0 && t > 0) mbar_wait(bar_accfree, (t - 1) & 1);  // the previous tile's accumulators were read out
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t tm_s = tmem_base + 128 + slot * 128, tm_dp = tm_s + 64;
+#pragma unroll
+        for (int k8 = 0; k8 < 8; ++k8) {
+          const uint32_t acc = (q | k8) ? 1u : 0u;
+          if (MODE == 1)  // dV += P^T dO
+            umma_tf32_ts(tm_acc2, tm_s + k8 * 8, make_smem_desc(y2 + q * 16384 + k8 * 1024, 8192, kSbo, kLayout),
+                         idesc_acc, acc);
+          // dQ += dS K   |   dK += dS^T Q
+          umma_tf32_ts(tm_acc1, tm_dp + k8 * 8, make_smem_desc(y1 + q * 16384 + k8 * 1024, 8192, kSbo, kLayout),
+                       idesc_acc, acc);
+        }
+        umma_commit(&bar_free[slot]);
+        if (q == nq - 1) umma_commit(bar_acc);
+      }
+      __syncwarp();
+    };
+    produce(0);
+    if (W > 1) produce(1);
+    for (int i = 0; i < W; ++i) {
+      consume(i);
+      if (i + 2 < W) produce(i + 2);
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ compute warps (thread = row = TMEM lane)
+    const int cw = warp - 4;
+    const int quad = cw & 3, half = cw >> 2;
+    const int rt = quad * 32 + lane;  // row inside the tile
+    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+    const float c = p.scale * 1.4426950408889634f;
+    const size_t stat_base = (static_cast<size_t>(s) * p.H + h) * N;
+    if (MODE == 1) {
+      const int i = threadIdx.x - 128;  // 0..255
+      sL[i] = i < N ? p.lse[stat_base + i] : 0.f;
+      sD[i] = i < N ? p.delta[stat_base + i] : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // compute warps only
+    }
+    for (int t = 0; t < tiles; ++t) {
+      const int row = t * 128 + rt;
+      float Lr = 0.f, dr = 0.f;
+      if (MODE == 0 && row < N) {
+        Lr = p.lse[stat_base + row];
+        dr = p.delta[stat_base + row];
+      }
+      const bool row_ok = (MODE == 0) ? (row < N) : (row < len);
+      for (int q = 0; q < nq; ++q) {
+        const int i = t * nq + q, slot = i % kSlots, u = i / kSlots;
+        mbar_wait(&bar_full[slot], u & 1);
+        tc_fence_after();
+        const uint32_t tm_s = tmem_base + 128 + slot * 128 + lane_addr + half * 32, tm_dp = tm_s + 64;
+        uint32_t sv[32], dv[32];
+        tmem_ld_32x32(tm_s, sv);
+        tmem_ld_32x32(tm_dp, dv);
+        tmem_ld_wait();
+        const int col0 = q * 64 + half * 32;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = col0 + j;
+          float Lc, dc;
+          bool ok;
+          if (MODE == 0) {
+            Lc = Lr; dc = dr;
+            ok = row_ok && col < len;
+          } else {
+            Lc = sL[col]; dc = sD[col];  // warp-uniform address: shared-memory broadcast
+            ok = row_ok && col < N;
+          }
+          const float pv = ok ? ex2_approx(fmaf(__uint_as_float(sv[j]), c, -Lc)) : 0.f;
+          const float ds = pv * (__uint_as_float(dv[j]) - dc);
+          if (MODE == 1) sv[j] = __float_as_uint(round_tf32(pv));
+          dv[j] = __float_as_uint(round_tf32(ds));
+        }
+        if (MODE == 1) tmem_st_32x32(tm_s, sv);
+        tmem_st_32x32(tm_dp, dv);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&bar_ds[slot]);
+      }
+      // ---- tile epilogue: accumulators -> global (this warp's 32 of the 64 head-dim columns)
+      mbar_wait(bar_acc, t & 1);
+      tc_fence_after();
+      uint32_t a1[32], a2[32];
+      tmem_ld_32x32(tm_acc1 + lane_addr + half * 32, a1);
+      if (MODE == 1) tmem_ld_32x32(tm_acc2 + lane_addr + half * 32, a2);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(bar_accfree);
+      if (row < N) {
+        float* base = p.dqkv + (static_cast<size_t>(row0) + row) * (3 * D) + h * 64 + half * 32;
+        float* d1 = base + (MODE == 0 ? 0 : D);  // dQ | dK
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float o8[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o8[e] = round_tf32(__uint_as_float(a1[8 * j + e]) * p.scale);
+          st_global_v8(d1 + 8 * j, o8);
+        }
+        if (MODE == 1) {
+          float* d2 = base + 2 * D;  // dV
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float o8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o8[e] = round_tf32(__uint_as_float(a2[8 * j + e]));
+            st_global_v8(d2 + 8 * j, o8);
+          }
+        }
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+int make_map_generic_3d(CUtensorMap* map, const float* ptr, long long rows, int feats, int ld, int box_rows,
+                        int box_chunks);
+int attention_delta(const float* o, const float* d_o, float* delta, int S, int N, int H, cudaStream_t stream);
+
+int attention_backward_tc(const float* qkv, const float* o, const float* d_o, const float* lse, float* delta_ws,
+                          float* dqkv, const int* lengths, int S, int N, int H, cudaStream_t stream) {
+  const int D = H * 64;
+  ATST_REQUIRE(N <= 256, "attention_backward_tc: N=%d > 256", N);
+  ATST_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_o) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(dqkv) & 31) == 0,
+               "attention_backward_tc: qkv / d_o must be 16-byte and dqkv 32-byte aligned");
+  int rc = attention_delta(o, d_o, delta_ws, S, N, H, stream);
+  if (rc) return rc;
+  const long long rows = static_cast<long long>(S) * N;
+  CUtensorMap tqr, tqy, tdr, tdy;
+  if ((rc = make_map_generic_3d(&tqr, qkv, rows, 3 * D, 3 * D, 128, 2))) return rc;
+  if ((rc = make_map_generic_3d(&tqy, qkv, rows, 3 * D, 3 * D, 64, 2))) return rc;
+  if ((rc = make_map_generic_3d(&tdr, d_o, rows, D, D, 128, 2))) return rc;
+  if ((rc = make_map_generic_3d(&tdy, d_o, rows, D, D, 64, 2))) return rc;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBwd);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_bwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBwd);
+    if (e != cudaSuccess) { atst_set_error("attn_bwd_tc smem attr: %s", cudaGetErrorString(e)); return ATST_ERR_CUDA; }
+    configured = true;
+  }
+  BwdTcParams p{};
+  p.dqkv = dqkv; p.lse = lse; p.delta = delta_ws; p.lengths = lengths; p.N = N; p.H = H; p.D = D; p.scale = 0.125f;
+  dim3 grid(H, S);
+  attn_bwd_tc_kernel<0><<<grid, 384, kSmemBwd, stream>>>(tqr, tqy, tdr, tdy, p);
+  rc = atst_check_launch("attn_bwd_tc_kernel<dQ>");
+  if (rc) return rc;
+  attn_bwd_tc_kernel<1><<<grid, 384, kSmemBwd, stream>>>(tqr, tqy, tdr, tdy, p);
+  return atst_check_launch("attn_bwd_tc_kernel<dKdV>");
+}
+
+}  // namespace atst

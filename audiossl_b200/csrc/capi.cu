@@ -5,7 +5,11 @@
 #include "ops.h"
 #include <string.h>
 
-namespace atst { void attention_set_tc(int on); }
+namespace atst {
+void attention_set_tc(int on);
+int umma_probe(int mode, const float* A, const float* B, float* D, unsigned layout, unsigned lbo, unsigned sbo,
+               unsigned kstep, cudaStream_t stream);
+}
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 using namespace atst;
 
@@ -81,6 +85,11 @@ int atst_gemm_mn_debug(int nn, const float* A, int lda, const float* B, int ldb,
   p.splits = splits;
   if (nn) return gemm_nn(A, lda, B, ldb, p, ST(stream));
   return gemm_tn(A, lda, B, ldb, K, p, ST(stream));
+}
+
+int atst_umma_probe(int mode, const float* A, const float* B, float* D, unsigned layout, unsigned lbo, unsigned sbo,
+                    unsigned kstep, void* stream) {
+  return umma_probe(mode, A, B, D, layout, lbo, sbo, kstep, ST(stream));
 }
 
 int atst_layernorm_forward(const float* x, long long x_stride, const float* gamma, const float* beta, float* y,

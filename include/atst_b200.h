@@ -55,6 +55,10 @@ int atst_gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int
 int atst_gemm_mn_debug(int nn, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K,
                        unsigned lbo, unsigned sbo, unsigned kstep, unsigned layout, int tma_swizzle, int splits,
                        void* stream);
+/* bring-up probe of tcgen05 operand forms (K-major reads of 32B-atom-swizzled tiles, A operand in tensor memory):
+ * mode 0/1: D[128,128] = A[128,64] . B[128,64]^T ; mode 2: D[128,128] = A[128,64] . B[64,128] */
+int atst_umma_probe(int mode, const float* A, const float* B, float* D, unsigned layout, unsigned lbo, unsigned sbo,
+                    unsigned kstep, void* stream);
 
 /* ---- LayerNorm(eps) forward/backward, row strides in elements (audiossl/modules/transformer.py:128,132;
  *      final norm on the CLS row only: audiossl/models/atst/audio_transformer.py:201,210) */

@@ -182,9 +182,41 @@ def sec_ln():
                rel_err(dys, ref_dys), rel_err(cs, ref_dys.sum(0))))
 
 
+def sec_umma_probe():
+    """which tcgen05 operand forms work: K-major reads of 32B-atom-swizzled tiles, A operand in tensor memory."""
+    import torch
+    from audiossl_b200 import _lib, ops
+    from audiossl_b200._lib import ptr
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    L = _lib.lib()
+    A = ops.round_tf32(torch.randn(128, 64, device="cuda"))
+    B = ops.round_tf32(torch.randn(128, 64, device="cuda"))
+    B2 = ops.round_tf32(torch.randn(64, 128, device="cuda"))
+    ref = A @ B.t()
+    for mode, name, r, b in ((1, "A in TMEM, B K-major", ref, B), (2, "A in TMEM, B token-major", A @ B2, B2)):
+        D = torch.zeros(128, 128, device="cuda")
+        rc = L.atst_umma_probe(mode, ptr(A), ptr(b), ptr(D), 0, 0, 0, 0, _lib.stream())
+        torch.cuda.synchronize()
+        print("mode %d (%s): rc=%d rel=%.3e" % (mode, name, rc, rel_err(D, r)))
+    combos = list(itertools.product((1, 2), (16, 4096, 16384), (256, 512, 1024, 2048), (32, 64)))
+    if os.environ.get("PROBE_COMBO"):  # one combination per process: a bad descriptor leaves a sticky error
+        combos = [tuple(int(x) for x in os.environ["PROBE_COMBO"].split(","))]
+    for layout, lbo, sbo, kstep in combos:
+        D = torch.zeros(128, 128, device="cuda")
+        rc = L.atst_umma_probe(0, ptr(A), ptr(B), ptr(D), layout, lbo, sbo, kstep, _lib.stream())
+        try:
+            torch.cuda.synchronize()
+        except Exception as e:
+            print("CUDA error at layout=%d lbo=%d sbo=%d kstep=%d: %s" % (layout, lbo, sbo, kstep, str(e).splitlines()[0]))
+            return
+        err = rel_err(D, ref)
+        print("%s mode 0 layout=%d lbo=%5d sbo=%4d kstep=%3d rel=%.3e" % ("OK " if err < 2e-3 else "   ", layout, lbo, sbo, kstep, err))
+
+
 def sec_attn_tc():
     from audiossl_b200 import _lib
-    _lib.lib().atst_set_option(b"attn_tcgen05", 1)
+    _lib.lib().atst_set_option(b"attn_tcgen05", int(os.environ.get("ATTN_TC", "3")))
     sec_attn()
 
 
@@ -483,7 +515,7 @@ def sec_pair():
         L.atst_set_option(b"gemm_cta_pair", 0)
 
 
-SECTIONS = {"attn_tc": sec_attn_tc, "pair": sec_pair, "heads": sec_heads, "gemm_perf": sec_gemm_perf, "mel": sec_mel, "gemm_nt": sec_gemm_nt, "gemm_mn": sec_gemm_mn, "ln": sec_ln, "attn": sec_attn,
+SECTIONS = {"umma_probe": sec_umma_probe, "attn_tc": sec_attn_tc, "pair": sec_pair, "heads": sec_heads, "gemm_perf": sec_gemm_perf, "mel": sec_mel, "gemm_nt": sec_gemm_nt, "gemm_mn": sec_gemm_mn, "ln": sec_ln, "attn": sec_attn,
             "bn": sec_bn, "loss": sec_loss, "optim": sec_optim, "tokens": sec_tokens}
 
 if __name__ == "__main__":
