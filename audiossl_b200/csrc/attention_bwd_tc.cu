@@ -15,12 +15,14 @@
 // compute warps overwrite the S / dP quarter in tensor memory with tf32(P) / tf32(dS) (tcgen05.st) and the second
 // stage MMAs take that as their TMEM A operand.
 //
-// Shared memory (193 KB): R1, R2 = the row tile's two operands [2 k-chunks][128 rows][128 B]; Y1, Y2 = the column
-// operands [4 quarters][2 k-chunks][64 rows][128 B]; per-column lse / delta for MODE 1.
+// Shared memory (226 KB): R1, R2 = the row tile's two operands [2 k-chunks][128 rows][128 B]; Y1, Y2 = the column
+// operands [4 quarters][2 k-chunks][64 rows][128 B]; a 32 KB staging tile for the TMA store of the results; per-column
+// lse / delta for MODE 1.
 // Tensor memory (512 columns): accumulators acc1 [0,64) (dQ | dK), acc2 [64,128) (dV); three ring slots of
 // {S quarter, dP quarter} at 128 + 128 s.
-// Warps: 0 TMA producer, 1 MMA issuer (one lane), 2 TMEM allocator, 4-11 compute (thread = row = TMEM lane; the two
-// warps of a lane quadrant split each quarter's 64 columns).
+// Warps: 0 TMA producer, 1 MMA issuer for S / dP, 3 MMA issuer for the second stage, 2 TMEM allocator, 4-11 compute (thread = row = TMEM lane; the two
+// warps of a lane quadrant split each quarter's 64 columns), 12-15 epilogue (accumulators -> swizzled staging tile ->
+// one TMA store per result, clipped at the sequence end by the 4-D tensor map).
 #include "common.cuh"
 
 namespace atst {
@@ -31,9 +33,10 @@ constexpr int kR1 = 0;
 constexpr int kR2 = 32 * 1024;
 constexpr int kY1 = 64 * 1024;
 constexpr int kY2 = 128 * 1024;
-constexpr int kStat = 192 * 1024;          // [2][256] floats
+constexpr int kStage = 192 * 1024;         // [2 chunks][128 rows][128 B] result tile for the TMA store
+constexpr int kStat = 224 * 1024;          // [2][256] floats
 constexpr int kBars = kStat + 2 * 256 * 4;  // mbarriers
-constexpr int kSmemBwd = 1024 + kBars + 256;
+constexpr int kSmemBwd = kBars + 256;       // no alignment slack: the dynamic segment is declared 1024-byte aligned
 constexpr int kSlots = 3;
 constexpr uint32_t kKLbo = 4096, kSbo = 512, kLayout = 1;  // 32B-atom 128B swizzle (see the operand probe)
 
@@ -44,16 +47,26 @@ struct BwdTcParams {
   const int* lengths;
   int N, H, D;
   float scale;
+  long long* trace;  // bring-up: clock64() timeline of one CTA (tools/bringup.py attn_trace), or null
+  int trace_seq;
 };
 
 }  // namespace
 
+// timeline slots: 0 start | 1+4i.. MMA warp {produce ready, produce issued, consume ready, consume issued} of work
+// quarter i | 40+2i.. compute warp 0 {quarter ready, quarter handed back} | 60+2t.. {accumulator ready, tile stored}
+#define ATTN_TRACE(idx)                                       \
+  do {                                                        \
+    if (tracing && lane == 0) p.trace[(idx)] = clock64();     \
+  } while (0)
+
 template <int MODE>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(512, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvR, const __grid_constant__ CUtensorMap tmQkvY,
-                   const __grid_constant__ CUtensorMap tmDoR, const __grid_constant__ CUtensorMap tmDoY, BwdTcParams p) {
-  extern __shared__ uint8_t smem_raw_bwd[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_bwd) + 1023) & ~uintptr_t(1023));
+                   const __grid_constant__ CUtensorMap tmDoR, const __grid_constant__ CUtensorMap tmDoY,
+                   const __grid_constant__ CUtensorMap tmOut, BwdTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // the swizzled tiles need 1024-byte alignment
   float* sL = reinterpret_cast<float*>(smem + kStat);
   float* sD = sL + 256;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBars);
@@ -69,6 +82,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvR, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x, s = blockIdx.y;
+  const bool tracing = p.trace != nullptr && h == 0 && s == p.trace_seq;
   const int N = p.N, D = p.D;
   int len = p.lengths ? p.lengths[s] : N;
   if (len <= 0 || len > N) len = N;  // see attention.cu
@@ -85,12 +99,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvR, const __grid_cons
     tma_prefetch_desc(&tmQkvY);
     tma_prefetch_desc(&tmDoR);
     tma_prefetch_desc(&tmDoY);
+    tma_prefetch_desc(&tmOut);
   }
   if (warp == 1 && lane == 0) {
     mbar_init(bar_r, 1);
     mbar_init(bar_rfree, 1);
     mbar_init(bar_acc, 1);
-    mbar_init(bar_accfree, 256);
+    mbar_init(bar_accfree, 128);
     for (int i = 0; i < 4; ++i) mbar_init(&bar_y[i], 1);
     for (int i = 0; i < kSlots; ++i) {
       mbar_init(&bar_full[i], 1);
@@ -105,6 +120,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvR, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tm_acc1 = tmem_base, tm_acc2 = tmem_base + 64;
+  if (warp == 1) ATTN_TRACE(0);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -138,67 +154,70 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvR, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    const uint32_t idesc_s = make_idesc(2u, 128, 64, 0u, 0u);    // A, B K-major
-    const uint32_t idesc_acc = make_idesc(2u, 128, 64, 0u, 1u);  // A in TMEM (K-major), B MN-major
-    const uint32_t r1 = smem_u32(smem + kR1), r2 = smem_u32(smem + kR2);
-    const uint32_t y1 = smem_u32(smem + kY1), y2 = smem_u32(smem + kY2);
-    auto produce = [&](int i) {
+    // ------------------------------------------------------------ MMA issuer 1: S / dP quarters into the ring
+    const uint32_t idesc_s = make_idesc(2u, 128, 64, 0u, 0u);  // A, B K-major
+    const uint32_t hi = smem_desc_hi(kKLbo, kSbo, kLayout);
+    const uint32_t r1 = smem_desc_lo(smem_u32(smem + kR1), kKLbo), r2 = smem_desc_lo(smem_u32(smem + kR2), kKLbo);
+    const uint32_t y1 = smem_desc_lo(smem_u32(smem + kY1), kKLbo), y2 = smem_desc_lo(smem_u32(smem + kY2), kKLbo);
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    for (int i = 0; i < W; ++i) {
       const int t = i / nq, q = i - t * nq, slot = i % kSlots, u = i / kSlots;
       if (q == 0) mbar_wait(bar_r, t & 1);
       if (t == 0) mbar_wait(&bar_y[q], 0);
-      if (u > 0) mbar_wait(&bar_free[slot], (u - 1) & 1);
+      if (u > 0) mbar_wait(&bar_free[slot], (u - 1) & 1);  // the slot's second-stage MMAs have read it
       tc_fence_after();
-      if (lane == 0) {
+      ATTN_TRACE(1 + 4 * i);
+      {
         const uint32_t tm_s = tmem_base + 128 + slot * 128, tm_dp = tm_s + 64;
+        const uint32_t yq = q * (16384 >> 4);
 #pragma unroll
         for (int kc = 0; kc < 2; ++kc)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_tf32(tm_s, make_smem_desc(r1 + kc * 16384 + k * 32, kKLbo, kSbo, kLayout),
-                      make_smem_desc(y1 + q * 16384 + kc * 8192 + k * 32, kKLbo, kSbo, kLayout), idesc_s,
-                      (kc | k) ? 1u : 0u);
+            umma_tf32_ss_p(tm_s, r1 + ((kc * 16384 + k * 32) >> 4), hi, y1 + yq + ((kc * 8192 + k * 32) >> 4), hi,
+                           idesc_s, (kc | k) ? 1u : 0u, leader);
 #pragma unroll
         for (int kc = 0; kc < 2; ++kc)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_tf32(tm_dp, make_smem_desc(r2 + kc * 16384 + k * 32, kKLbo, kSbo, kLayout),
-                      make_smem_desc(y2 + q * 16384 + kc * 8192 + k * 32, kKLbo, kSbo, kLayout), idesc_s,
-                      (kc | k) ? 1u : 0u);
-        umma_commit(&bar_full[slot]);
-        if (q == nq - 1) umma_commit(bar_rfree);
+            umma_tf32_ss_p(tm_dp, r2 + ((kc * 16384 + k * 32) >> 4), hi, y2 + yq + ((kc * 8192 + k * 32) >> 4), hi,
+                           idesc_s, (kc | k) ? 1u : 0u, leader);
+        umma_commit_p(&bar_full[slot], leader);
+        if (q == nq - 1) umma_commit_p(bar_rfree, leader);
       }
+      ATTN_TRACE(2 + 4 * i);
       __syncwarp();
-    };
-    auto consume = [&](int i) {
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------ MMA issuer 2: second-stage MMAs (A operand in TMEM)
+    const uint32_t idesc_acc = make_idesc(2u, 128, 64, 0u, 1u);  // A in TMEM (K-major), B MN-major
+    const uint32_t hi = smem_desc_hi(8192, kSbo, kLayout);
+    const uint32_t y1 = smem_desc_lo(smem_u32(smem + kY1), 8192), y2 = smem_desc_lo(smem_u32(smem + kY2), 8192);
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    for (int i = 0; i < W; ++i) {
       const int t = i / nq, q = i - t * nq, slot = i % kSlots, u = i / kSlots;
       mbar_wait(&bar_ds[slot], u & 1);
       if (q == 0 && t > 0) mbar_wait(bar_accfree, (t - 1) & 1);  // the previous tile's accumulators were read out
       tc_fence_after();
-      if (lane == 0) {
+      ATTN_TRACE(3 + 4 * i);
+      {
         const uint32_t tm_s = tmem_base + 128 + slot * 128, tm_dp = tm_s + 64;
+        const uint32_t yq = q * (16384 >> 4);
+        const uint32_t acc0 = q ? 1u : 0u;
 #pragma unroll
         for (int k8 = 0; k8 < 8; ++k8) {
-          const uint32_t acc = (q | k8) ? 1u : 0u;
           if (MODE == 1)  // dV += P^T dO
-            umma_tf32_ts(tm_acc2, tm_s + k8 * 8, make_smem_desc(y2 + q * 16384 + k8 * 1024, 8192, kSbo, kLayout),
-                         idesc_acc, acc);
+            umma_tf32_ts_p(tm_acc2, tm_s + k8 * 8, y2 + yq + ((k8 * 1024) >> 4), hi, idesc_acc, k8 ? 1u : acc0, leader);
           // dQ += dS K   |   dK += dS^T Q
-          umma_tf32_ts(tm_acc1, tm_dp + k8 * 8, make_smem_desc(y1 + q * 16384 + k8 * 1024, 8192, kSbo, kLayout),
-                       idesc_acc, acc);
+          umma_tf32_ts_p(tm_acc1, tm_dp + k8 * 8, y1 + yq + ((k8 * 1024) >> 4), hi, idesc_acc, k8 ? 1u : acc0, leader);
         }
-        umma_commit(&bar_free[slot]);
-        if (q == nq - 1) umma_commit(bar_acc);
+        umma_commit_p(&bar_free[slot], leader);
+        if (q == nq - 1) umma_commit_p(bar_acc, leader);
       }
+      ATTN_TRACE(4 + 4 * i);
       __syncwarp();
-    };
-    produce(0);
-    if (W > 1) produce(1);
-    for (int i = 0; i < W; ++i) {
-      consume(i);
-      if (i + 2 < W) produce(i + 2);
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 12) {
     // ------------------------------------------------------------ compute warps (thread = row = TMEM lane)
     const int cw = warp - 4;
     const int quad = cw & 3, half = cw >> 2;
@@ -224,6 +243,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvR, const __grid_cons
         const int i = t * nq + q, slot = i % kSlots, u = i / kSlots;
         mbar_wait(&bar_full[slot], u & 1);
         tc_fence_after();
+        if (cw == 0) ATTN_TRACE(40 + 2 * i);
         const uint32_t tm_s = tmem_base + 128 + slot * 128 + lane_addr + half * 32, tm_dp = tm_s + 64;
         uint32_t sv[32], dv[32];
         tmem_ld_32x32(tm_s, sv);
@@ -252,38 +272,63 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvR, const __grid_cons
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&bar_ds[slot]);
-      }
-      // ---- tile epilogue: accumulators -> global (this warp's 32 of the 64 head-dim columns)
-      mbar_wait(bar_acc, t & 1);
-      tc_fence_after();
-      uint32_t a1[32], a2[32];
-      tmem_ld_32x32(tm_acc1 + lane_addr + half * 32, a1);
-      if (MODE == 1) tmem_ld_32x32(tm_acc2 + lane_addr + half * 32, a2);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(bar_accfree);
-      if (row < N) {
-        float* base = p.dqkv + (static_cast<size_t>(row0) + row) * (3 * D) + h * 64 + half * 32;
-        float* d1 = base + (MODE == 0 ? 0 : D);  // dQ | dK
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float o8[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o8[e] = round_tf32(__uint_as_float(a1[8 * j + e]) * p.scale);
-          st_global_v8(d1 + 8 * j, o8);
-        }
-        if (MODE == 1) {
-          float* d2 = base + 2 * D;  // dV
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float o8[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) o8[e] = round_tf32(__uint_as_float(a2[8 * j + e]));
-            st_global_v8(d2 + 8 * j, o8);
-          }
-        }
+        if (cw == 0) ATTN_TRACE(41 + 2 * i);
       }
     }
+  } else if (warp >= 12) {
+    // ------------------------------------------------------------ epilogue warps: accumulators -> staging -> TMA store
+    const int quad = warp & 3;
+    const int rt = quad * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t stage = smem_u32(smem + kStage);
+    const bool leader = threadIdx.x == 12 * 32;
+    // v: the thread's 64 result columns -> staging row rt, 128B-swizzled 16-byte units, both 32-column chunks
+    auto stage_row = [&](const uint32_t (&v0)[32], const uint32_t (&v1)[32], float scale) {
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        const uint32_t dst = stage + ch * 16384 + rt * 128;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const uint32_t* v = ch ? v1 : v0;
+          st_shared_v4(dst + ((j4 ^ (rt & 7)) << 4), round_tf32(__uint_as_float(v[4 * j4]) * scale),
+                       round_tf32(__uint_as_float(v[4 * j4 + 1]) * scale),
+                       round_tf32(__uint_as_float(v[4 * j4 + 2]) * scale),
+                       round_tf32(__uint_as_float(v[4 * j4 + 3]) * scale));
+        }
+      }
+    };
+    bool pending = false;  // a bulk store may still be reading the staging tile
+    for (int t = 0; t < tiles; ++t) {
+      mbar_wait(bar_acc, t & 1);
+      tc_fence_after();
+      if (warp == 12) ATTN_TRACE(60 + 2 * t);
+      for (int r = 0; r < (MODE == 1 ? 2 : 1); ++r) {
+        uint32_t a0[32], a1[32];
+        const uint32_t tm_acc = (r == 0 ? tm_acc1 : tm_acc2) + lane_addr;
+        tmem_ld_32x32(tm_acc, a0);
+        tmem_ld_32x32(tm_acc + 32, a1);
+        tmem_ld_wait();
+        if (r == (MODE == 1 ? 1 : 0)) {
+          tc_fence_before();
+          mbar_arrive(bar_accfree);  // the next tile's second-stage MMAs may overwrite the accumulators
+        }
+        if (pending) {
+          if (leader) tma_store_wait_read();
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+        }
+        stage_row(a0, a1, r == 0 ? p.scale : 1.0f);  // dQ | dK, then dV
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (leader) {
+          const int chunk = (MODE == 0) ? cq : (r == 0 ? ck : cv);
+          tma_store_4d(&tmOut, smem + kStage, 0, t * 128, chunk, s);
+          tma_store_commit();
+        }
+        pending = true;
+      }
+      if (warp == 12) ATTN_TRACE(61 + 2 * t);
+    }
+    if (leader) tma_store_wait_read();
   }
 
   __syncwarp();
@@ -298,7 +343,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvR, const __grid_cons
 // ---------------------------------------------------------------------------------------------- host side
 int make_map_generic_3d(CUtensorMap* map, const float* ptr, long long rows, int feats, int ld, int box_rows,
                         int box_chunks);
+int make_map_seq4d(CUtensorMap* map, const float* ptr, int S, int N, int feats, int box_rows);
 int attention_delta(const float* o, const float* d_o, float* delta, int S, int N, int H, cudaStream_t stream);
+
+static long long* g_trace = nullptr;
+static int g_trace_seq = 0, g_trace_mode = 0;
+void attention_set_trace(long long* buf, int seq, int mode) { g_trace = buf; g_trace_seq = seq; g_trace_mode = mode; }
 
 int attention_backward_tc(const float* qkv, const float* o, const float* d_o, const float* lse, float* delta_ws,
                           float* dqkv, const int* lengths, int S, int N, int H, cudaStream_t stream) {
@@ -310,7 +360,8 @@ int attention_backward_tc(const float* qkv, const float* o, const float* d_o, co
   int rc = attention_delta(o, d_o, delta_ws, S, N, H, stream);
   if (rc) return rc;
   const long long rows = static_cast<long long>(S) * N;
-  CUtensorMap tqr, tqy, tdr, tdy;
+  CUtensorMap tqr, tqy, tdr, tdy, tout;
+  if ((rc = make_map_seq4d(&tout, dqkv, S, N, 3 * D, 128))) return rc;
   if ((rc = make_map_generic_3d(&tqr, qkv, rows, 3 * D, 3 * D, 128, 2))) return rc;
   if ((rc = make_map_generic_3d(&tqy, qkv, rows, 3 * D, 3 * D, 64, 2))) return rc;
   if ((rc = make_map_generic_3d(&tdr, d_o, rows, D, D, 128, 2))) return rc;
@@ -326,10 +377,13 @@ int attention_backward_tc(const float* qkv, const float* o, const float* d_o, co
   BwdTcParams p{};
   p.dqkv = dqkv; p.lse = lse; p.delta = delta_ws; p.lengths = lengths; p.N = N; p.H = H; p.D = D; p.scale = 0.125f;
   dim3 grid(H, S);
-  attn_bwd_tc_kernel<0><<<grid, 384, kSmemBwd, stream>>>(tqr, tqy, tdr, tdy, p);
+  p.trace_seq = g_trace_seq;
+  p.trace = g_trace_mode == 0 ? g_trace : nullptr;
+  attn_bwd_tc_kernel<0><<<grid, 512, kSmemBwd, stream>>>(tqr, tqy, tdr, tdy, tout, p);
   rc = atst_check_launch("attn_bwd_tc_kernel<dQ>");
   if (rc) return rc;
-  attn_bwd_tc_kernel<1><<<grid, 384, kSmemBwd, stream>>>(tqr, tqy, tdr, tdy, p);
+  p.trace = g_trace_mode == 1 ? g_trace : nullptr;
+  attn_bwd_tc_kernel<1><<<grid, 512, kSmemBwd, stream>>>(tqr, tqy, tdr, tdy, tout, p);
   return atst_check_launch("attn_bwd_tc_kernel<dKdV>");
 }
 

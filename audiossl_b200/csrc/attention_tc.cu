@@ -1,79 +1,93 @@
 // Attention forward on tcgen05 (5th-gen tensor cores) for sequences of up to 256 tokens (every ATST config:
 // N <= 251).  Same math and outputs as attn_kernel<0> in attention.cu: o = softmax(q k^T / 8 + key-padding) v,
-// lse in the log2 domain; TF32 operands, fp32 accumulation in TMEM, fp32 softmax.
+// lse in the log2 domain; TF32 operands, fp32 accumulation in tensor memory, fp32 softmax.
 //
-// One CTA = one (sequence, head, 128-query tile); 224 KB of shared memory, all operands resident:
-//   Q  [2 k-chunks][128 rows][128 B]   K-major, 128B swizzle   (TMA, box {32 floats, 128 rows})
-//   K  [2 k-chunks][256 rows][128 B]   K-major, 128B swizzle
-//   V  [2 key halves][2 dh-chunks][128 keys][128 B]  token-major ("MN-major" B operand), 128B swizzle / 32B atoms
-//   P  [2 buffers][2 key-chunks][128 rows][128 B]    K-major, written by the softmax threads with the swizzle applied
-// TMEM: S = Q K^T in columns [0,256) (one UMMA N=256), O in columns [256,320).
-// Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 softmax + epilogue
-// (thread = query row = TMEM lane, so row max / row sum need no shuffles).  The row maximum is taken over the whole
-// row first (S stays in TMEM and is read twice), so P needs no rescaling: the four 64-key quarters of P stream
-// through two smem buffers while the previous quarter's P V MMAs run.
+// One CTA per (sequence, head), both 128-query tiles; K and V are loaded once.  Operands arrive by TMA in the
+// token-major 32B-atom 128B swizzle: Q and K are read K-major (S = Q K^T), V MN-major (O = P V).  The probabilities
+// never touch shared memory: the compute warps overwrite each 64-key quarter of S in tensor memory with tf32(P)
+// (tcgen05.st) and the P V MMAs take it as their TMEM A operand.
+//
+// Tensor memory (512 columns): a ring of six 64-column quarter slots [0,384) - a tile's S occupies up to four, so the
+// next tile's first quarters are produced while this tile's softmax runs - and the two tiles' O accumulators
+// [384,448), [448,512).
+// The row maximum is taken over the whole row first (S is read twice from tensor memory), so P needs no rescaling.
+// Warps: 0 TMA producer, 1 MMA issuer for S, 3 MMA issuer for P V, 2 TMEM allocator, 4-11 softmax (thread = query row
+// = TMEM lane; the two warps of a lane quadrant split each quarter's 64 columns and exchange their partial row
+// max / row sum through shared memory), 12-15 epilogue (O / l -> the tile's dead Q buffer, 128B-swizzled -> one TMA
+// store, clipped at the sequence end by the 4-D tensor map; lse).
 #include "common.cuh"
 
 namespace atst {
 
 namespace {
 
-constexpr int kQOff = 0;
-constexpr int kKOff = 32 * 1024;
-constexpr int kVOff = 96 * 1024;
-constexpr int kPOff = 160 * 1024;
-constexpr int kBarOff = 224 * 1024;
-constexpr int kSmemTc = 1024 + kBarOff + 256;
+constexpr int kQ = 0;                    // [2 tiles][2 k-chunks][128 rows][128 B]
+constexpr int kK = 64 * 1024;            // [4 quarters][2 k-chunks][64 rows][128 B]
+constexpr int kV = 128 * 1024;           // same, read MN-major
+constexpr int kStatF = 192 * 1024;       // sXm [2 tiles][2 halves][128], sXl [2][2][128]
+constexpr int kBarsF = kStatF + 2 * 2 * 2 * 128 * 4;
+constexpr int kSmemFwd = kBarsF + 512;
+constexpr int kRing = 6;
+constexpr uint32_t kLboK = 4096, kSboF = 512, kLayoutF = 1;  // 32B-atom 128B swizzle (see the operand probe)
 
 struct AttnTcParams {
-  float* o;
   float* lse;
   const int* lengths;
   int N, H, D;
   float scale;
 };
 
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
 }  // namespace
 
-__global__ void __launch_bounds__(256, 1)
-attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV, AttnTcParams p) {
-  extern __shared__ uint8_t smem_raw_tc[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_tc) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBarOff);
-  uint64_t* bar_qk = bars + 0;
-  uint64_t* bar_v = bars + 1;      // [2]
-  uint64_t* bar_s = bars + 3;
-  uint64_t* bar_p = bars + 4;      // [2]
-  uint64_t* bar_pfree = bars + 6;  // [2]
-  uint64_t* bar_o = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+__global__ void __launch_bounds__(512, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmY,
+                   const __grid_constant__ CUtensorMap tmOut, AttnTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // the swizzled tiles need 1024-byte alignment
+  float* sXm = reinterpret_cast<float*>(smem + kStatF);  // [tile][half][row]
+  float* sXl = sXm + 2 * 2 * 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBarsF);
+  uint64_t* bar_q = bars + 0;       // [2]
+  uint64_t* bar_k = bars + 2;       // [4]
+  uint64_t* bar_v = bars + 6;       // [4]
+  uint64_t* bar_full = bars + 10;   // [6]
+  uint64_t* bar_p = bars + 16;      // [6]
+  uint64_t* bar_free = bars + 22;   // [6]
+  uint64_t* bar_o = bars + 28;      // [2]
+  uint64_t* bar_stats = bars + 30;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 128, h = blockIdx.y, s = blockIdx.z;
+  const int h = blockIdx.x, s = blockIdx.y;
   const int N = p.N, D = p.D;
   int len = p.lengths ? p.lengths[s] : N;
   if (len <= 0 || len > N) len = N;  // see attention.cu
+  const int row0 = s * N;
+  const int tiles = (N + 127) >> 7;
   const int nq = (len + 63) >> 6;  // 64-key quarters that contain valid keys
-  const int row0 = s * N;          // first token row of this sequence in the [S*N, 3D] tensor
+  const int W = tiles * nq;
+  const int cq = (h * 64) >> 5, ck = (D + h * 64) >> 5, cv = (2 * D + h * 64) >> 5;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQK);
-    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmR);
+    tma_prefetch_desc(&tmY);
+    tma_prefetch_desc(&tmOut);
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(bar_qk, 1);
-    mbar_init(&bar_v[0], 1);
-    mbar_init(&bar_v[1], 1);
-    mbar_init(bar_s, 1);
-    mbar_init(&bar_p[0], 128);
-    mbar_init(&bar_p[1], 128);
-    mbar_init(&bar_pfree[0], 1);
-    mbar_init(&bar_pfree[1], 1);
-    mbar_init(bar_o, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_q[i], 1);
+      mbar_init(&bar_o[i], 1);
+      mbar_init(&bar_stats[i], 256);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&bar_k[i], 1);
+      mbar_init(&bar_v[i], 1);
+    }
+    for (int i = 0; i < kRing; ++i) {
+      mbar_init(&bar_full[i], 1);
+      mbar_init(&bar_p[i], 256);
+      mbar_init(&bar_free[i], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -81,134 +95,166 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 256;
+  const uint32_t tm_o = tmem_base + 384;  // + 64 * tile
 
   if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer: Q0, K quarters, Q1, V quarters
     if (lane == 0) {
-      // Q (2 boxes) + K (4 boxes of 128 rows) on one barrier, the two key halves of V on their own
-      mbar_expect_tx(bar_qk, 96 * 1024);
-      for (int kc = 0; kc < 2; ++kc) {
-        tma_load_2d(smem + kQOff + kc * 16384, &tmQK, bar_qk, h * 64 + kc * 32, row0 + q0);
-        tma_load_2d(smem + kKOff + kc * 32768, &tmQK, bar_qk, D + h * 64 + kc * 32, row0);
-        tma_load_2d(smem + kKOff + kc * 32768 + 16384, &tmQK, bar_qk, D + h * 64 + kc * 32, row0 + 128);
+      mbar_expect_tx(&bar_q[0], 32 * 1024);
+      tma_load_3d(smem + kQ, &tmR, &bar_q[0], 0, row0, cq);
+      for (int q = 0; q < nq; ++q) {
+        mbar_expect_tx(&bar_k[q], 16 * 1024);
+        tma_load_3d(smem + kK + q * 16384, &tmY, &bar_k[q], 0, row0 + q * 64, ck);
       }
-      for (int hf = 0; hf < 2; ++hf) {
-        if (hf * 2 >= nq) break;
-        mbar_expect_tx(&bar_v[hf], 32 * 1024);
-        tma_load_3d(smem + kVOff + hf * 32768, &tmV, &bar_v[hf], 0, row0 + hf * 128, (2 * D + h * 64) / 32);
+      if (tiles > 1) {
+        mbar_expect_tx(&bar_q[1], 32 * 1024);
+        tma_load_3d(smem + kQ + 32768, &tmR, &bar_q[1], 0, row0 + 128, cq);
+      }
+      for (int q = 0; q < nq; ++q) {
+        mbar_expect_tx(&bar_v[q], 16 * 1024);
+        tma_load_3d(smem + kV + q * 16384, &tmY, &bar_v[q], 0, row0 + q * 64, cv);
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    const uint32_t idesc_s = make_idesc(2u, 128, 256, 0u, 0u);
-    const uint32_t idesc_pv = make_idesc(2u, 128, 64, 0u, 1u);
-    mbar_wait(bar_qk, 0);
-    tc_fence_after();
-    if (lane == 0) {
-      const uint32_t qa = smem_u32(smem + kQOff), ka = smem_u32(smem + kKOff);
+    // ------------------------------------------------------------ MMA issuer 1: S quarters into the ring
+    const uint32_t idesc_s = make_idesc(2u, 128, 64, 0u, 0u);
+    const uint32_t hi = smem_desc_hi(kLboK, kSboF, kLayoutF);
+    const uint32_t qd = smem_desc_lo(smem_u32(smem + kQ), kLboK), kd = smem_desc_lo(smem_u32(smem + kK), kLboK);
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    for (int i = 0; i < W; ++i) {
+      const int t = i / nq, q = i - t * nq, slot = i % kRing, u = i / kRing;
+      if (q == 0) mbar_wait(&bar_q[t], 0);
+      if (t == 0) mbar_wait(&bar_k[q], 0);
+      if (u > 0) mbar_wait(&bar_free[slot], (u - 1) & 1);  // the slot's P V MMAs have read it
+      tc_fence_after();
+      const uint32_t tm_s = tmem_base + slot * 64;
+      const uint32_t qa = qd + t * (32768 >> 4), ka = kd + q * (16384 >> 4);
 #pragma unroll
       for (int kc = 0; kc < 2; ++kc)
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_tf32(tmem_s, make_smem_desc(qa + kc * 16384 + k * 32, 16, 1024, 2),
-                    make_smem_desc(ka + kc * 32768 + k * 32, 16, 1024, 2), idesc_s, (kc | k) ? 1u : 0u);
-      umma_commit(bar_s);
-    }
-    __syncwarp();
-    for (int q = 0; q < nq; ++q) {
-      const int b = q & 1, hf = q >> 1;
-      if ((q & 1) == 0) {
-        mbar_wait(&bar_v[hf], 0);
-      }
-      mbar_wait(&bar_p[b], (q >> 1) & 1);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t pa = smem_u32(smem + kPOff + b * 32768);
-        const uint32_t va = smem_u32(smem + kVOff + hf * 32768) + (q & 1) * 64 * 128;  // 64 key rows into the half
-#pragma unroll
-        for (int kc = 0; kc < 2; ++kc)
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_tf32(tmem_o, make_smem_desc(pa + kc * 16384 + k * 32, 16, 1024, 2),
-                      make_smem_desc(va + (kc * 32 + k * 8) * 128, 16384, 512, 1), idesc_pv,
-                      (q | kc | k) ? 1u : 0u);
-        umma_commit(&bar_pfree[b]);
-        if (q == nq - 1) umma_commit(bar_o);
-      }
+          umma_tf32_ss_p(tm_s, qa + ((kc * 16384 + k * 32) >> 4), hi, ka + ((kc * 8192 + k * 32) >> 4), hi, idesc_s,
+                         (kc | k) ? 1u : 0u, leader);
+      umma_commit_p(&bar_full[slot], leader);
       __syncwarp();
     }
-  } else if (warp >= 4) {
-    // ------------------------------------------------------------ softmax + epilogue (thread = query row)
-    const int ew = warp - 4;
-    const int r = ew * 32 + lane;  // row inside the tile == TMEM lane
-    const uint32_t lane_addr = static_cast<uint32_t>(ew * 32) << 16;
-    const float c = p.scale * 1.4426950408889634f;
-    mbar_wait(bar_s, 0);
-    tc_fence_after();
-    // pass 1: row maximum over the valid keys
-    float m = -INFINITY;
-    const int nchunks = (len + 31) >> 5;
-    for (int ch = 0; ch < nchunks; ++ch) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_s + lane_addr + ch * 32, v);
-      tmem_ld_wait();
+  } else if (warp == 3) {
+    // ------------------------------------------------------------ MMA issuer 2: O += P V (P in tensor memory)
+    const uint32_t idesc_pv = make_idesc(2u, 128, 64, 0u, 1u);
+    const uint32_t hi = smem_desc_hi(8192, kSboF, kLayoutF);
+    const uint32_t vd = smem_desc_lo(smem_u32(smem + kV), 8192);
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    for (int i = 0; i < W; ++i) {
+      const int t = i / nq, q = i - t * nq, slot = i % kRing, u = i / kRing;
+      mbar_wait(&bar_p[slot], u & 1);
+      if (t == 0) mbar_wait(&bar_v[q], 0);
+      tc_fence_after();
+      const uint32_t tm_p = tmem_base + slot * 64;
+      const uint32_t va = vd + q * (16384 >> 4);
+      const uint32_t acc0 = q ? 1u : 0u;
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (ch * 32 + j < len) m = fmaxf(m, __uint_as_float(v[j]));
+      for (int k8 = 0; k8 < 8; ++k8)
+        umma_tf32_ts_p(tm_o + t * 64, tm_p + k8 * 8, va + ((k8 * 1024) >> 4), hi, idesc_pv, k8 ? 1u : acc0, leader);
+      umma_commit_p(&bar_free[slot], leader);
+      if (q == nq - 1) umma_commit_p(&bar_o[t], leader);
+      __syncwarp();
     }
-    // pass 2: probabilities, quarter by quarter through the two P buffers
-    float l = 0.f;
-    const uint32_t p_base = smem_u32(smem + kPOff);
-    for (int q = 0; q < nq; ++q) {
-      const int b = q & 1;
-      if (q >= 2) {
-        mbar_wait(&bar_pfree[b], 0);  // the P V MMAs of quarter q-2 have consumed this buffer
-      }
-#pragma unroll
-      for (int c32 = 0; c32 < 2; ++c32) {
+  } else if (warp >= 4 && warp < 12) {
+    // ------------------------------------------------------------ softmax warps (thread = query row = TMEM lane)
+    const int cw = warp - 4;
+    const int quad = cw & 3, half = cw >> 2;
+    const int rt = quad * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+    const float c = p.scale * 1.4426950408889634f;
+    for (int t = 0; t < tiles; ++t) {
+      // pass 1: row maximum over this warp's half of every quarter
+      float m = -INFINITY;
+      for (int q = 0; q < nq; ++q) {
+        const int i = t * nq + q, slot = i % kRing, u = i / kRing;
+        mbar_wait(&bar_full[slot], u & 1);
+        tc_fence_after();
         uint32_t v[32];
-        const int col0 = q * 64 + c32 * 32;
-        tmem_ld_32x32(tmem_s + lane_addr + col0, v);
+        tmem_ld_32x32(tmem_base + slot * 64 + half * 32 + lane_addr, v);
         tmem_ld_wait();
-        const uint32_t dst = p_base + b * 32768 + c32 * 16384 + r * 128;
+        const int col0 = q * 64 + half * 32;
+        if (col0 + 32 <= len) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < len) m = fmaxf(m, __uint_as_float(v[j]));
+        }
+      }
+      float* xm = sXm + t * 256;
+      xm[half * 128 + rt] = m;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      m = fmaxf(xm[rt], xm[128 + rt]);  // at least one valid key per row (len >= 1) lies in half 0 of quarter 0
+      const float mc = m * c;
+      // pass 2: probabilities, written back over S as the TMEM operand of the P V MMAs
+      float l = 0.f;
+      for (int q = 0; q < nq; ++q) {
+        const int i = t * nq + q, slot = i % kRing;
+        const uint32_t ta = tmem_base + slot * 64 + half * 32 + lane_addr;
+        uint32_t v[32];
+        tmem_ld_32x32(ta, v);
+        tmem_ld_wait();
+        const int col0 = q * 64 + half * 32;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float pv = (col0 + j < len) ? ex2_approx(fmaf(__uint_as_float(v[j]), c, -mc)) : 0.f;
+          l += pv;
+          v[j] = __float_as_uint(round_tf32(pv));
+        }
+        tmem_st_32x32(ta, v);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&bar_p[slot]);
+      }
+      sXl[t * 256 + half * 128 + rt] = l;
+      mbar_arrive(&bar_stats[t]);  // publishes this tile's sXm / sXl to the epilogue warps
+    }
+  } else if (warp >= 12) {
+    // ------------------------------------------------------------ epilogue warps: O / l -> staging -> TMA store, lse
+    const int quad = warp & 3;
+    const int rt = quad * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+    const bool leader = threadIdx.x == 12 * 32;
+    const float c = p.scale * 1.4426950408889634f;
+    for (int t = 0; t < tiles; ++t) {
+      mbar_wait(&bar_stats[t], 0);
+      const float m = fmaxf(sXm[t * 256 + rt], sXm[t * 256 + 128 + rt]);
+      const float l = sXl[t * 256 + rt] + sXl[t * 256 + 128 + rt];
+      const float inv = l > 0.f ? 1.0f / l : 0.f;
+      const int row = t * 128 + rt;
+      if (row < N) p.lse[(static_cast<size_t>(s) * p.H + h) * N + row] = m * c + log2f(l);
+      mbar_wait(&bar_o[t], 0);
+      tc_fence_after();
+      uint32_t a0[32], a1[32];
+      tmem_ld_32x32(tm_o + t * 64 + lane_addr, a0);
+      tmem_ld_32x32(tm_o + t * 64 + lane_addr + 32, a1);
+      tmem_ld_wait();
+      // staging = this tile's Q buffer: every S MMA that read it completed before the tile's first P V MMA
+      const uint32_t stage = smem_u32(smem + kQ + t * 32768);
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        const uint32_t dst = stage + ch * 16384 + rt * 128;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          float e[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int col = col0 + j4 * 4 + i;
-            const float pv = col < len ? exp2f((__uint_as_float(v[j4 * 4 + i]) - m) * c) : 0.f;
-            l += pv;
-            e[i] = round_tf32(pv);
-          }
-          st_shared_v4(dst + ((j4 ^ (r & 7)) << 4), e[0], e[1], e[2], e[3]);
+          const uint32_t* v = ch ? a1 : a0;
+          st_shared_v4(dst + ((j4 ^ (rt & 7)) << 4), round_tf32(__uint_as_float(v[4 * j4]) * inv),
+                       round_tf32(__uint_as_float(v[4 * j4 + 1]) * inv), round_tf32(__uint_as_float(v[4 * j4 + 2]) * inv),
+                       round_tf32(__uint_as_float(v[4 * j4 + 3]) * inv));
         }
       }
-      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      mbar_arrive(&bar_p[b]);
-    }
-    // epilogue: O / l -> global, lse
-    mbar_wait(bar_o, 0);
-    tc_fence_after();
-    const int qrow = q0 + r;
-    const float inv = l > 0.f ? 1.0f / l : 0.f;
-    float* op = p.o + (static_cast<size_t>(row0) + qrow) * D + h * 64;
-#pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_o + lane_addr + ch * 32, v);
-      tmem_ld_wait();
-      if (qrow < N) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float o8[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o8[e] = round_tf32(__uint_as_float(v[8 * j + e]) * inv);
-          st_global_v8(op + ch * 32 + 8 * j, o8);
-        }
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (leader) {
+        tma_store_4d(&tmOut, smem + kQ + t * 32768, 0, t * 128, cq, s);
+        tma_store_commit();
       }
     }
-    if (qrow < N) p.lse[(static_cast<size_t>(s) * p.H + h) * N + qrow] = m * c + log2f(l);
+    if (leader) tma_store_wait_read();
   }
 
   __syncwarp();
@@ -221,11 +267,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-int make_map_generic_2d(CUtensorMap* map, const float* ptr, long long rows, int cols, int ld, int box_rows);
 int make_map_generic_3d(CUtensorMap* map, const float* ptr, long long rows, int feats, int ld, int box_rows,
                         int box_chunks);
+int make_map_seq4d(CUtensorMap* map, const float* ptr, int S, int N, int feats, int box_rows);
 
-static int g_attn_tc = 0;
+static int g_attn_tc = 3;  // bit 0: forward, bit 1: backward on tcgen05 (N <= 256); 0 = the mma.sync kernels
 void attention_set_tc(int on) { g_attn_tc = on; }
 int attention_tc_enabled() { return g_attn_tc; }
 
@@ -233,23 +279,24 @@ int attention_forward_tc(const float* qkv, float* o, float* lse, const int* leng
                          cudaStream_t stream) {
   const int D = H * 64;
   ATST_REQUIRE(N <= 256, "attention_forward_tc: N=%d > 256", N);
-  ATST_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(o) & 31) == 0,
-               "attention_forward_tc: qkv must be 16-byte and o 32-byte aligned");
-  CUtensorMap tq, tv;
-  int rc = make_map_generic_2d(&tq, qkv, static_cast<long long>(S) * N, 3 * D, 3 * D, 128);
-  if (rc) return rc;
-  rc = make_map_generic_3d(&tv, qkv, static_cast<long long>(S) * N, 3 * D, 3 * D, 128, 2);
-  if (rc) return rc;
+  ATST_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0,
+               "attention_forward_tc: qkv and o must be 16-byte aligned");
+  CUtensorMap tr, ty, tout;
+  const long long rows = static_cast<long long>(S) * N;
+  int rc;
+  if ((rc = make_map_generic_3d(&tr, qkv, rows, 3 * D, 3 * D, 128, 2))) return rc;
+  if ((rc = make_map_generic_3d(&ty, qkv, rows, 3 * D, 3 * D, 64, 2))) return rc;
+  if ((rc = make_map_seq4d(&tout, o, S, N, D, 128))) return rc;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTc);
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFwd);
     if (e != cudaSuccess) { atst_set_error("attn_fwd_tc smem attr: %s", cudaGetErrorString(e)); return ATST_ERR_CUDA; }
     configured = true;
   }
   AttnTcParams p{};
-  p.o = o; p.lse = lse; p.lengths = lengths; p.N = N; p.H = H; p.D = D; p.scale = 0.125f;
-  dim3 grid((N + 127) / 128, H, S);
-  attn_fwd_tc_kernel<<<grid, 256, kSmemTc, stream>>>(tq, tv, p);
+  p.lse = lse; p.lengths = lengths; p.N = N; p.H = H; p.D = D; p.scale = 0.125f;
+  dim3 grid(H, S);
+  attn_fwd_tc_kernel<<<grid, 512, kSmemFwd, stream>>>(tr, ty, tout, p);
   return atst_check_launch("attn_fwd_tc_kernel");
 }
 

@@ -7,6 +7,7 @@
 
 namespace atst {
 void attention_set_tc(int on);
+void attention_set_trace(long long* buf, int seq, int mode);
 int umma_probe(int mode, const float* A, const float* B, float* D, unsigned layout, unsigned lbo, unsigned sbo,
                unsigned kstep, cudaStream_t stream);
 }
@@ -90,6 +91,11 @@ int atst_gemm_mn_debug(int nn, const float* A, int lda, const float* B, int ldb,
 int atst_umma_probe(int mode, const float* A, const float* B, float* D, unsigned layout, unsigned lbo, unsigned sbo,
                     unsigned kstep, void* stream) {
   return umma_probe(mode, A, B, D, layout, lbo, sbo, kstep, ST(stream));
+}
+
+int atst_attention_trace(long long* buf, int seq, int mode) {
+  attention_set_trace(buf, seq, mode);
+  return ATST_OK;
 }
 
 int atst_layernorm_forward(const float* x, long long x_stride, const float* gamma, const float* beta, float* y,

@@ -113,6 +113,20 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// shared -> global tile store (bulk async group); rows / chunks outside the tensor are clipped
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk stores have finished READING shared memory (the source may be overwritten)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // L2 prefetch of a tensor tile (no smem destination, no barrier): hides HBM latency behind the smem ring
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)),
@@ -219,6 +233,68 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t m, uint
                                                   uint32_t b_major) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | (a_major << 15) | (b_major << 16) | ((n >> 3) << 17) |
          ((m >> 4) << 24);
+}
+
+// one lane of a converged warp (elect.sync): the compiler keeps the guarded tcgen05 issue on the uniform datapath
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// descriptor halves: hi is constant per operand layout, lo = (address >> 4) and advances by (bytes >> 4)
+__device__ __forceinline__ uint32_t smem_desc_hi(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  return static_cast<uint32_t>(make_smem_desc(0, lbo_bytes, sbo_bytes, layout_type) >> 32);
+}
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+// Predicated issue forms for a CONVERGED warp: every lane executes the statement with warp-uniform operands and only
+// the lane whose `leader` flag (elect_one(), taken once per role) is set issues.  Keeping the control flow uniform lets
+// the compiler hold descriptors in uniform registers instead of serialising a divergent region per instruction.
+__device__ __forceinline__ void umma_tf32_ss_p(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate, uint32_t leader) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, L;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.ne.b32 L, %7, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "@L tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts_p(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate, uint32_t leader) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, L;\n\t"
+      ".reg .b64 db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "setp.ne.b32 L, %6, 0;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "@L tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %4, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_p(uint64_t* bar, uint32_t leader) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred L;\n\t"
+      "setp.ne.b32 L, %1, 0;\n\t"
+      "@L tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(leader)
+      : "memory");
 }
 
 }  // namespace atst

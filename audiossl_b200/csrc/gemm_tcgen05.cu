@@ -431,6 +431,23 @@ int make_map_generic_3d(CUtensorMap* map, const float* ptr, long long rows, int 
   return ATST_OK;
 }
 
+// [S, N, feats] fp32 (contiguous) viewed as {32 floats, N rows, feats/32 chunks, S}: a box {32, box_rows, 2, 1} is one
+// head's 64 columns of up to box_rows tokens of ONE sequence - rows past N are clipped on store and zero-filled on load,
+// so a 128-row tile never touches the next sequence.  Standard 128B swizzle ([chunk][row][128 B] in shared memory).
+int make_map_seq4d(CUtensorMap* map, const float* ptr, int S, int N, int feats, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { atst_set_error("cuTensorMapEncodeTiled entry point not available"); return ATST_ERR_CUDA; }
+  cuuint64_t dims[4] = {32, static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(feats / 32), static_cast<cuuint64_t>(S)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(feats) * 4, 128, static_cast<cuuint64_t>(N) * feats * 4};
+  cuuint32_t box[4] = {32, static_cast<cuuint32_t>(box_rows), 2, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { atst_set_error("cuTensorMapEncodeTiled(4d) failed: %d", (int)r); return ATST_ERR_CUDA; }
+  return ATST_OK;
+}
+
 template <int BLOCK_N, bool A_MN, bool B_MN>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;

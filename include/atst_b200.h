@@ -81,6 +81,10 @@ int atst_attention_forward(const float* qkv, float* o, float* lse, const int* le
 int atst_attention_backward(const float* qkv, const float* o, const float* d_o, const float* lse, float* delta_ws,
                             float* dqkv, const int* lengths, int S, int N, int H, void* stream);
 
+/* bring-up: record a clock64() timeline (80 slots, device buffer) of the CTA of head 0 / sequence seq in the tcgen05
+ * backward kernel `mode` (0 dQ, 1 dK dV) on subsequent atst_attention_backward calls; buf = NULL switches it off */
+int atst_attention_trace(long long* buf, int seq, int mode);
+
 /* ---- patch embedding plumbing (audiossl/models/atst/audio_transformer.py:56-75,153-186;
  *      frame model: audiossl/methods/atstframe/audio_transformer.py:161-181) */
 int atst_patchify(const float* mel, long long clip_stride, int S, int T, float* patches, void* stream);

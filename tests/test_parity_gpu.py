@@ -93,25 +93,45 @@ def test_gemm_wgrad_dgrad(T, M, N):
     assert rel(ops.gemm_nn(A, W), A @ W) < 2e-5
 
 
-def test_attention_matches_reference_formula():
-    from audiossl_b200 import ops
+@pytest.mark.parametrize("tc", [3, 0])  # tcgen05 kernels (default, N <= 256) / mma.sync kernels
+@pytest.mark.parametrize("S,N,H,lens", [
+    (3, 151, 6, [191, 77, 0]),      # beyond the sequence / ragged / fully masked
+    (2, 26, 2, None),               # 1 s clips: one tile, one quarter
+    (5, 251, 12, [251, 1, 64, 65, 200]),  # config-2 shape with quarter-boundary lengths
+    (2, 128, 1, [128, 127]),        # exactly one tile
+    (2, 129, 3, [129, 128]),        # one row into the second tile
+    (1, 256, 2, None),              # the largest supported sequence
+])
+def test_attention_matches_reference_formula(tc, S, N, H, lens):
+    from audiossl_b200 import _lib, ops
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.manual_seed(0)
-    S, N, H = 3, 151, 6
     D = H * 64
     qkv = ops.round_tf32(torch.randn(S * N, 3 * D, device="cuda"))
-    lengths = torch.tensor([N + 40, 77, 0], dtype=torch.int32, device="cuda")  # beyond the sequence / fully masked
+    lengths = None if lens is None else torch.tensor(lens, dtype=torch.int32, device="cuda")
     q = qkv.clone().requires_grad_(True)
     t = q.reshape(S, N, 3, H, 64).permute(2, 0, 3, 1, 4)
     att = (t[0] @ t[1].transpose(-2, -1)) * 0.125
-    att = att + ((torch.arange(N, device="cuda")[None] >= lengths[:, None]) * -10000.0)[:, None, None, :]
+    if lengths is not None:
+        att = att + ((torch.arange(N, device="cuda")[None] >= lengths[:, None]) * -10000.0)[:, None, None, :]
+    lse_ref = torch.logsumexp(att, -1) * 1.4426950408889634  # [S,H,N], log2 domain
     o_ref = (att.softmax(-1) @ t[2]).transpose(1, 2).reshape(S * N, D)
     d_o = ops.round_tf32(torch.randn(S * N, D, device="cuda"))
     o_ref.backward(d_o)
-    o, lse = ops.attention_fwd(qkv, S, N, H, lengths)
-    dqkv = ops.attention_bwd(qkv, o, d_o, lse, S, N, H, lengths)
+    _lib.lib().atst_set_option(b"attn_tcgen05", tc)
+    try:
+        guard = torch.full((S * N + 8, 3 * D), 7.0, device="cuda")  # rows past the last sequence must stay untouched
+        o, lse = ops.attention_fwd(qkv, S, N, H, lengths)
+        dqkv = ops.attention_bwd(qkv, o, d_o, lse, S, N, H, lengths, dqkv=guard[:S * N])
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().atst_set_option(b"attn_tcgen05", 3)
     assert rel(o, o_ref) < 1e-3
+    # a fully masked sequence shifts every score by the same -10000 in the reference: softmax unchanged, lse shifted
+    keep = torch.ones(S, dtype=torch.bool, device="cuda") if lengths is None else lengths > 0
+    assert rel(lse[keep], lse_ref[keep]) < 1e-5
     assert rel(dqkv, q.grad) < 1e-3
+    assert torch.all(guard[S * N:] == 7.0)
 
 
 def test_layernorm_backward_fused_outputs():

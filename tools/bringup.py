@@ -214,6 +214,36 @@ def sec_umma_probe():
         print("%s mode 0 layout=%d lbo=%5d sbo=%4d kstep=%3d rel=%.3e" % ("OK " if err < 2e-3 else "   ", layout, lbo, sbo, kstep, err))
 
 
+def sec_attn_trace():
+    """clock64 timeline of one CTA of the tcgen05 attention backward kernels at the config-2 shape."""
+    import torch
+    from audiossl_b200 import _lib, ops
+    from audiossl_b200._lib import ptr
+    L = _lib.lib()
+    L.atst_set_option(b"attn_tcgen05", 3)
+    S, N, H = 512, 251, 12
+    qkv = torch.randn(S * N, 3 * H * 64, device="cuda")
+    o, lse = ops.attention_fwd(qkv, S, N, H)
+    d_o = torch.randn_like(o)
+    dqkv = torch.empty_like(qkv)
+    ops.attention_bwd(qkv, o, d_o, lse, S, N, H, dqkv=dqkv)
+    for mode in (0, 1):
+        buf = torch.zeros(80, dtype=torch.int64, device="cuda")
+        L.atst_attention_trace(ptr(buf), S // 2, mode)
+        ops.attention_bwd(qkv, o, d_o, lse, S, N, H, dqkv=dqkv)
+        torch.cuda.synchronize()
+        L.atst_attention_trace(None, 0, 0)
+        tr = buf.cpu().tolist()
+        t0 = tr[0]
+        rel = [x - t0 if x else -1 for x in tr]
+        print("mode %d (%s) cycles since CTA start" % (mode, "dQ" if mode == 0 else "dK dV"))
+        for i in range(8):
+            print("  q%d  mma: P ready %6d issued %6d | C ready %6d issued %6d || compute: ready %6d done %6d" %
+                  (i, rel[1 + 4 * i], rel[2 + 4 * i], rel[3 + 4 * i], rel[4 + 4 * i], rel[40 + 2 * i], rel[41 + 2 * i]))
+        for t in range(2):
+            print("  tile %d acc ready %6d stored %6d" % (t, rel[60 + 2 * t], rel[61 + 2 * t]))
+
+
 def sec_attn_tc():
     from audiossl_b200 import _lib
     _lib.lib().atst_set_option(b"attn_tcgen05", int(os.environ.get("ATTN_TC", "3")))
@@ -515,7 +545,7 @@ def sec_pair():
         L.atst_set_option(b"gemm_cta_pair", 0)
 
 
-SECTIONS = {"umma_probe": sec_umma_probe, "attn_tc": sec_attn_tc, "pair": sec_pair, "heads": sec_heads, "gemm_perf": sec_gemm_perf, "mel": sec_mel, "gemm_nt": sec_gemm_nt, "gemm_mn": sec_gemm_mn, "ln": sec_ln, "attn": sec_attn,
+SECTIONS = {"attn_trace": sec_attn_trace, "umma_probe": sec_umma_probe, "attn_tc": sec_attn_tc, "pair": sec_pair, "heads": sec_heads, "gemm_perf": sec_gemm_perf, "mel": sec_mel, "gemm_nt": sec_gemm_nt, "gemm_mn": sec_gemm_mn, "ln": sec_ln, "attn": sec_attn,
             "bn": sec_bn, "loss": sec_loss, "optim": sec_optim, "tokens": sec_tokens}
 
 if __name__ == "__main__":
