@@ -56,7 +56,7 @@ int atst_gemm_nt(const float* A, int lda, const float* B, int ldb, float* C, int
   ATST_REQUIRE((epi >= EPI_STORE && epi <= EPI_RELU) || epi == EPI_DBG_NOSTORE || epi == EPI_DBG_NOLOAD,
                "atst_gemm_nt: bad epilogue %d", epi);
   ATST_REQUIRE(!(epi == EPI_RESID && resid == nullptr), "atst_gemm_nt: EPI_RESID needs resid");
-  ATST_REQUIRE(!((epi == EPI_GELU || epi == EPI_DGELU) && aux == nullptr), "atst_gemm_nt: GELU epilogues need aux");
+  ATST_REQUIRE(!(epi == EPI_DGELU && aux == nullptr), "atst_gemm_nt: EPI_DGELU needs aux");
   return gemm_nt(A, lda, B, ldb, p, ST(stream));
 }
 

@@ -6,10 +6,10 @@
 // two SMs read the other half from the peer's shared memory.  Per CTA: 64 B/clk of TMA fill, 64 B/clk of UMMA
 // reads, 64 B/clk of L2 traffic, and the 32 KB stages make the smem ring 6 deep instead of 4.
 //
-// Roles per CTA (256 threads): warp 0 TMA producer (both CTAs; transactions complete on the LEADER's full
+// Roles per CTA (384 threads): warp 0 TMA producer (both CTAs; transactions complete on the LEADER's full
 // barrier), warp 1 MMA issuer (leader only: tcgen05.mma.cta_group::2, M=256; tcgen05.commit multicast frees the
 // smem slot / publishes the accumulator in both CTAs), warp 2 TMEM allocator (cta_group::2 alloc in both CTAs),
-// warps 4-7 epilogue (own 128 TMEM lanes; the accumulator stage is handed back on the leader's barrier, remotely
+// warps 4-11 epilogue (own 128 TMEM lanes, two warps per lane quadrant; the accumulator stage is handed back on the leader's barrier, remotely
 // from the follower).  Operand majors as in the 1-CTA kernel (K-major 128B swizzle, or token-major tensors via
 // the 32B-atom swizzle).
 #include <cooperative_groups.h>
@@ -98,7 +98,7 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
 }  // namespace
 
 template <bool A_MN, bool B_MN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
   extern __shared__ uint8_t smem_raw2[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw2) + 1023) & ~uintptr_t(1023));
@@ -136,7 +136,7 @@ gemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 8);
+      mbar_init(&tempty_bar[i], 16);  // 8 epilogue warps x 2 CTAs
     }
     fence_barrier_init();
   }
@@ -220,7 +220,9 @@ gemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
-    const int ew = warp - 4;
+    // eight warps: two per TMEM lane quadrant, each walking one 128-column half of the tile
+    const int ew = (warp - 4) & 3, chalf = (warp - 4) >> 2;
+    const int epi_tid = threadIdx.x - 128;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
@@ -231,10 +233,11 @@ gemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int kb0 = split * kb_per_split;
       const bool empty_split = min(kb0 + kb_per_split, kb_total) <= kb0;
       uint64_t* tempty = &tempty_bar[acc];
-      epilogue_tile<kBN>(p, m0, n0, empty_split, tmem_base + acc * kBN, smem_bias + acc * 256, ew, lane, &tfull_bar[acc],
-                         acc_phase, [&]() {
-                           if (lane == 0) mbar_arrive_leader(tempty);
-                         });
+      auto release = [&]() {
+        if (lane == 0) mbar_arrive_leader(tempty);
+      };
+      epilogue_tile<kBN, 256>(p, m0, n0, empty_split, tmem_base + acc * kBN, smem_bias + acc * 256, ew, lane, epi_tid,
+                              chalf * (kBN / 16), (chalf + 1) * (kBN / 16), &tfull_bar[acc], acc_phase, release);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -269,7 +272,7 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
   const int tiles = m_tiles * n_tiles * (p.splits > 0 ? p.splits : 1);
   const int pairs = gemm_num_sms() / 2;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
-  kfn<<<grid, 256, kSmem2, stream>>>(ta, tb, p);
+  kfn<<<grid, 384, kSmem2, stream>>>(ta, tb, p);
   return atst_check_launch("gemm2_tf32_kernel");
 }
 

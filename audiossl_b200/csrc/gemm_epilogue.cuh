@@ -34,112 +34,108 @@ __device__ __forceinline__ float gelu_grad(float u) {
 }
 
 
-// Thread `lane` of epilogue warp `ew` owns accumulator row 32*ew + lane.  `release()` is called once, right after
-// the last TMEM load of the tile, to hand the accumulator stage back to the MMA issuer.
-template <int BLOCK_N, class Release>
+// Thread `lane` of an epilogue warp of TMEM lane quadrant `ew` owns accumulator row 32*ew + lane and walks the
+// 8-column groups [g0, g1) of the tile (g1 - g0 even; one warp per quadrant: the whole tile, two warps: half each).
+// The loop is deliberately NOT unrolled over the tile: one compact body (TMEM load of the next group and its side
+// input in flight while the current group is computed and stored) instead of a copy of every epilogue variant per
+// column chunk - the unrolled form thrashed the instruction cache (ncu: 23 % of the stall samples were "no
+// instruction" with the GELU epilogue).  `release()` is called once per warp, right after its last TMEM load of the
+// tile, to hand the accumulator stage back to the MMA issuer.  EPI_THREADS = epilogue threads of the CTA.
+template <int BLOCK_N, int EPI_THREADS, class Release>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n0, bool empty_split, uint32_t taddr,
-                                              float* sbias, int ew, int lane, uint64_t* tfull_bar, uint32_t acc_phase,
-                                              Release release) {
+                                              float* sbias, int ew, int lane, int epi_tid, int g0, int g1,
+                                              uint64_t* tfull_bar, uint32_t acc_phase, Release release) {
   const float* side_ptr = (p.epi == EPI_RESID) ? p.resid : ((p.epi == EPI_DGELU) ? p.aux : nullptr);
   const int side_ld = (p.epi == EPI_RESID) ? p.ldr : p.ldaux;
   const int gm = m0 + ew * 32 + lane;
   const bool row_ok = gm < p.M && !empty_split;
   const float rs = (p.rowscale != nullptr && row_ok) ? p.rowscale[gm / p.rows_per_seq] : 1.0f;
-  const float* side_row = side_ptr ? side_ptr + static_cast<size_t>(gm) * side_ld : nullptr;
-  float* c_row = p.C + static_cast<size_t>(gm) * p.ldc;
-  float* aux_row = (p.epi == EPI_GELU) ? p.aux + static_cast<size_t>(gm) * p.ldaux : nullptr;
+  const float* side_row = (side_ptr && row_ok) ? side_ptr + static_cast<size_t>(gm) * side_ld + n0 : nullptr;
+  float* c_row = p.C + static_cast<size_t>(gm) * p.ldc + n0;
+  float* aux_row = (p.epi == EPI_GELU && p.aux != nullptr) ? p.aux + static_cast<size_t>(gm) * p.ldaux + n0 : nullptr;
+  const int ncols = min(BLOCK_N, p.N - n0);  // valid columns of this tile (multiple of 8)
   // while this tile's main loop is still running: pull the side-input rows into L2 and stage the bias slice
-  if (side_row != nullptr && row_ok) {
-#pragma unroll
-    for (int c = 0; c < BLOCK_N / 32; ++c)
-      if (n0 + c * 32 < p.N) prefetch_l2(side_row + n0 + c * 32);
+  if (side_row != nullptr) {
+    for (int g = g0; g < g1; g += 4)
+      if (g * 8 < ncols) prefetch_l2(side_row + g * 8);
   }
   if (p.bias != nullptr) {
-    const int t128 = ew * 32 + lane;
-    for (int j = t128; j < BLOCK_N; j += 128) sbias[j] = (n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
+    for (int j = epi_tid; j < BLOCK_N; j += EPI_THREADS) sbias[j] = (j < ncols) ? __ldg(p.bias + n0 + j) : 0.f;
+    asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");  // epilogue warps only
   }
   mbar_wait(tfull_bar, acc_phase);
   tc_fence_after();
   taddr += static_cast<uint32_t>(ew * 32) << 16;
 
-  auto load_side = [&](int c, float (&sd)[32]) {
-    const int gn = n0 + c * 32;
-    if (side_row == nullptr || !row_ok || gn >= p.N) return;
+  auto fetch = [&](int g, uint32_t (&r)[8], float (&sd)[8]) {
+    tmem_ld_32x8(taddr + g * 8, r);
+    if (side_row != nullptr && g * 8 < ncols) ld_global_v8(side_row + g * 8, sd);
+  };
+  auto finish = [&](int g, const uint32_t (&r)[8], const float (&sd)[8]) {
+    if (!row_ok || g * 8 >= ncols) return;
+    float v[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (gn + 8 * j < p.N) ld_global_v8(side_row + gn + 8 * j, &sd[8 * j]);
+    for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[e]);
+    if (p.bias != nullptr) {
+      const float4 b0 = *reinterpret_cast<const float4*>(sbias + g * 8);  // smem broadcast
+      const float4 b1 = *reinterpret_cast<const float4*>(sbias + g * 8 + 4);
+      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    }
+    switch (p.epi) {
+      case EPI_GELU:  // aux (nullable: the teacher keeps no pre-activation) <- pre-activation, C <- gelu
+        if (aux_row != nullptr) st_global_v8(aux_row + g * 8, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = gelu_exact(v[e]);
+        break;
+      case EPI_DGELU:  // C <- acc * gelu'(aux)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] *= gelu_grad(sd[e]);
+        break;
+      case EPI_RESID:  // C <- resid + rowscale[seq] * (acc + bias)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = fmaf(rs, v[e], sd[e]);
+        break;
+      case EPI_SCALE:  // C <- rowscale[seq] * acc   (dgrad through droppath)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] *= rs;
+        break;
+      case EPI_RELU:
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+        break;
+      default:
+        break;
+    }
+    if (p.round_out) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = round_tf32(v[e]);
+    }
+    float* cp = c_row + g * 8;
+    if (p.epi == EPI_ATOMIC) {
+      red_add_v4(cp, v[0], v[1], v[2], v[3]);
+      red_add_v4(cp + 4, v[4], v[5], v[6], v[7]);
+    } else {
+      st_global_v8(cp, v);
     }
   };
-  auto process = [&](int c, const float (&sd)[32]) {
-    uint32_t r[32];
-    tmem_ld_32x32(taddr + c * 32, r);
+  uint32_t ra[8], rb[8];
+  float sa[8], sb[8];
+  fetch(g0, ra, sa);
+#pragma unroll 1
+  for (int g = g0; g < g1; g += 2) {
     tmem_ld_wait();
-    if (c == BLOCK_N / 32 - 1) {
+    fetch(g + 1, rb, sb);
+    finish(g, ra, sa);
+    tmem_ld_wait();
+    if (g + 2 < g1) {
+      fetch(g + 2, ra, sa);
+    } else {  // this warp's last TMEM load of the tile has completed
       tc_fence_before();
       __syncwarp();
       release();
     }
-    const int gn = n0 + c * 32;
-    if (!row_ok || gn >= p.N) return;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {  // 8 columns at a time
-      if (gn + 8 * j >= p.N) break;
-      float v[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * j + e]);
-      if (p.bias != nullptr) {
-        const float4 b0 = *reinterpret_cast<const float4*>(sbias + c * 32 + 8 * j);  // smem broadcast
-        const float4 b1 = *reinterpret_cast<const float4*>(sbias + c * 32 + 8 * j + 4);
-        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-      }
-      switch (p.epi) {
-        case EPI_GELU:
-          st_global_v8(aux_row + gn + 8 * j, v);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = gelu_exact(v[e]);
-          break;
-        case EPI_DGELU:
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] *= gelu_grad(sd[8 * j + e]);
-          break;
-        case EPI_RESID:
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = fmaf(rs, v[e], sd[8 * j + e]);
-          break;
-        case EPI_SCALE:
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] *= rs;
-          break;
-        case EPI_RELU:
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
-          break;
-        default:
-          break;
-      }
-      if (p.round_out) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = round_tf32(v[e]);
-      }
-      float* cp = c_row + gn + 8 * j;
-      if (p.epi == EPI_ATOMIC) {
-        red_add_v4(cp, v[0], v[1], v[2], v[3]);
-        red_add_v4(cp + 4, v[4], v[5], v[6], v[7]);
-      } else {
-        st_global_v8(cp, v);
-      }
-    }
-  };
-  float side_a[32], side_b[32];
-  load_side(0, side_a);
-#pragma unroll 1
-  for (int c = 0; c < BLOCK_N / 32; c += 2) {
-    load_side(c + 1, side_b);
-    process(c, side_a);
-    if (c + 2 < BLOCK_N / 32) load_side(c + 2, side_a);
-    process(c + 1, side_b);
+    finish(g + 1, rb, sb);
   }
 }
 

@@ -210,7 +210,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const float rs = (p.rowscale != nullptr && row_ok) ? p.rowscale[gm / p.rows_per_seq] : 1.0f;
       const float* side_row = side_ptr ? side_ptr + static_cast<size_t>(gm) * side_ld : nullptr;
       float* c_row = p.C + static_cast<size_t>(gm) * p.ldc;
-      float* aux_row = (p.epi == EPI_GELU) ? p.aux + static_cast<size_t>(gm) * p.ldaux : nullptr;
+      float* aux_row = (p.epi == EPI_GELU && p.aux != nullptr) ? p.aux + static_cast<size_t>(gm) * p.ldaux : nullptr;
       // while this tile's main loop is still running: pull the side-input rows into L2 and stage the bias slice
       if (side_row != nullptr && row_ok) {
 #pragma unroll
@@ -265,8 +265,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
           }
           switch (p.epi) {
-            case EPI_GELU:  // aux <- pre-activation, C <- gelu
-              st_global_v8(aux_row + gn + 8 * j, v);
+            case EPI_GELU:  // aux (nullable) <- pre-activation, C <- gelu
+              if (aux_row != nullptr) st_global_v8(aux_row + gn + 8 * j, v);
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] = gelu_exact(v[e]);
               break;

@@ -16,8 +16,12 @@ import os
 
 from . import ops
 
-# GELU / GELU' inside the GEMM epilogue (1) or as separate elementwise passes (0); see DESIGN.md "GEMM epilogues"
-FUSE_GELU = os.environ.get("ATST_FUSE_GELU", "0") == "1"
+# GELU / GELU' inside the GEMM epilogue or as separate elementwise passes; see DESIGN.md "GEMM epilogues".
+#   ATST_FUSE_GELU bit 0: forward passes that keep no activations (teacher, inference) fuse GELU into fc1 and never
+#                         store the pre-activation; bit 1: the student forward fuses it too (epilogue writes u and g);
+#                  bit 2: the backward fuses GELU' into the fc2 dgrad epilogue
+_FG = int(os.environ.get("ATST_FUSE_GELU", "3"))
+FUSE_GELU_NOSAVE, FUSE_GELU, FUSE_DGELU = bool(_FG & 1), bool(_FG & 2), bool(_FG & 4)
 
 
 class Workspace:
@@ -111,11 +115,16 @@ class EncoderEngine:
                              resid=x, rowscale=s_attn, rows_per_seq=N, out=lt("x1", (M, D)))
             h2, mean2, rstd2 = self._ln(x1, fp.p(b + "norm2.weight"), fp.p(b + "norm2.bias"), M, lt("h2", (M, D)),
                                         lt("mean2", (M,)), lt("rstd2", (M,)))
-            u = lt("u", (M, 4 * D))
-            if FUSE_GELU:
+            u = None
+            if not save and FUSE_GELU_NOSAVE:
+                g = ops.gemm_nt(h2, fp.c(b + "mlp.fc1.weight"), bias=fp.p(b + "mlp.fc1.bias"), epi=ops.EPI_GELU,
+                                aux=None, round_out=True, out=lt("g", (M, 4 * D)))
+            elif save and FUSE_GELU:
+                u = lt("u", (M, 4 * D))
                 g = ops.gemm_nt(h2, fp.c(b + "mlp.fc1.weight"), bias=fp.p(b + "mlp.fc1.bias"), epi=ops.EPI_GELU,
                                 aux=u, round_out=True, out=lt("g", (M, 4 * D)))
             else:
+                u = lt("u", (M, 4 * D))
                 ops.gemm_nt(h2, fp.c(b + "mlp.fc1.weight"), bias=fp.p(b + "mlp.fc1.bias"), out=u)
                 g = ops.gelu_fwd(u, lt("g", (M, 4 * D)))
             x2 = ops.gemm_nt(g, fp.c(b + "mlp.fc2.weight"), bias=fp.p(b + "mlp.fc2.bias"), epi=ops.EPI_RESID,
@@ -187,7 +196,7 @@ class EncoderEngine:
             s_attn = scales[i][0]
             # ---- MLP branch: x2 = x1 + s * (g W2^T + b2); dys = tf32(s * dx), fc2.bias gradient already accumulated
             ops.gemm_tn_acc(dys, L["g"], fp.g(b + "mlp.fc2.weight"))
-            if FUSE_GELU:
+            if FUSE_DGELU:
                 du = ops.gemm_nn(dys, fp.c(b + "mlp.fc2.weight"), epi=ops.EPI_DGELU, aux=L["u"], round_out=True,
                                  out=t("du", (M, 4 * D)))
                 ops.colsum_acc(du, fp.g(b + "mlp.fc1.bias"))
