@@ -102,6 +102,41 @@ __global__ void colsum_kernel(const float* __restrict__ X, long long ld, int row
   }
 }
 
+// same, 128 columns per CTA (float4 per lane), four rows in flight per thread; cols and ld multiples of 4
+__global__ void __launch_bounds__(256)
+colsum4_kernel(const float* __restrict__ X, long long ld, int rows, int cols, float* __restrict__ out) {
+  __shared__ float red[8][128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c4 = blockIdx.x * 32 + lane;
+  const int rows_per = (rows + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per, r1 = min(r0 + rows_per, rows);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c4 * 4 < cols) {
+    for (int r = r0 + warp; r < r1; r += 32) {
+      float4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const bool ok = r + 8 * k < r1;
+        v[k] = ok ? __ldcs(reinterpret_cast<const float4*>(X + static_cast<long long>(r + 8 * k) * ld) + c4)
+                  : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
+    }
+  }
+  *reinterpret_cast<float4*>(&red[warp][lane * 4]) = acc;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int col = blockIdx.x * 128 + threadIdx.x;
+    if (col < cols) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+      atomicAdd(out + col, s);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ BatchNorm1d (train mode) + ReLU
 // pass 1: per-column mean and M2 = sum (x - mean)^2 over the local rows (two-pass, like ATen)
 __global__ void bn_stats_kernel(const float* __restrict__ X, int rows, int cols, float* __restrict__ mean,
@@ -260,17 +295,29 @@ gelu_bwd_kernel(float* __restrict__ d, const float* __restrict__ u, int rows, in
   const int r0 = blockIdx.y * rows_per, r1 = min(r0 + rows_per, rows);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (c4 < cols4) {
-    for (int r = r0 + warp; r < r1; r += 8) {
-      const size_t i = static_cast<size_t>(r) * cols4 + c4;
-      const float4 v = __ldcs(reinterpret_cast<const float4*>(u) + i);
-      float4 o = reinterpret_cast<float4*>(d)[i];
-      float c, p;
-      gelu_cdf_pdf(v.x, c, p); o.x = round_tf32(o.x * fmaf(v.x, p, c));
-      gelu_cdf_pdf(v.y, c, p); o.y = round_tf32(o.y * fmaf(v.y, p, c));
-      gelu_cdf_pdf(v.z, c, p); o.z = round_tf32(o.z * fmaf(v.z, p, c));
-      gelu_cdf_pdf(v.w, c, p); o.w = round_tf32(o.w * fmaf(v.w, p, c));
-      reinterpret_cast<float4*>(d)[i] = o;
-      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    // four rows per trip: eight independent 16-byte loads in flight per thread (the row stride defeats the
+    // hardware's sequential prefetch, so memory-level parallelism has to come from the unroll)
+    for (int r = r0 + warp; r < r1; r += 32) {
+      float4 v[4], o[4];
+      bool ok[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        ok[k] = r + 8 * k < r1;
+        const size_t i = static_cast<size_t>(ok[k] ? r + 8 * k : r) * cols4 + c4;
+        v[k] = __ldcs(reinterpret_cast<const float4*>(u) + i);
+        o[k] = reinterpret_cast<float4*>(d)[i];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (!ok[k]) continue;
+        float c, p;
+        gelu_cdf_pdf(v[k].x, c, p); o[k].x = round_tf32(o[k].x * fmaf(v[k].x, p, c));
+        gelu_cdf_pdf(v[k].y, c, p); o[k].y = round_tf32(o[k].y * fmaf(v[k].y, p, c));
+        gelu_cdf_pdf(v[k].z, c, p); o[k].z = round_tf32(o[k].z * fmaf(v[k].z, p, c));
+        gelu_cdf_pdf(v[k].w, c, p); o[k].w = round_tf32(o[k].w * fmaf(v[k].w, p, c));
+        reinterpret_cast<float4*>(d)[static_cast<size_t>(r + 8 * k) * cols4 + c4] = o[k];
+        acc.x += o[k].x; acc.y += o[k].y; acc.z += o[k].z; acc.w += o[k].w;
+      }
     }
   }
   if (colsum_out == nullptr) return;
@@ -358,6 +405,14 @@ int colsum_accumulate(const float* X, long long ld, int rows, int cols, float* o
   int gy = (rows + 2047) / 2048;
   if (gy > 64) gy = 64;
   if (gy < 1) gy = 1;
+  if (cols % 4 == 0 && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0) {
+    const int gx = (cols / 4 + 31) / 32;
+    int gy4 = (148 * 8 + gx - 1) / gx;
+    if (gy4 > (rows + 63) / 64) gy4 = (rows + 63) / 64;
+    if (gy4 < 1) gy4 = 1;
+    colsum4_kernel<<<dim3(gx, gy4), 256, 0, st>>>(X, ld, rows, cols, out);
+    return atst_check_launch("colsum4_kernel");
+  }
   colsum_kernel<<<dim3((cols + 31) / 32, gy), 256, 0, st>>>(X, ld, rows, cols, out);
   return atst_check_launch("colsum_kernel");
 }

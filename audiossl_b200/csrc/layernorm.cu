@@ -52,8 +52,10 @@ ln_fwd_kernel(const float* __restrict__ x, long long x_stride, const float* __re
 
 // dx = dres + rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
 // dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy   (per-lane register partials -> smem -> atomics)
-template <int NV>
-__global__ void __launch_bounds__(256)
+// WPR warps share a row (WPR = 2 for the wide rows: half the per-lane state, so two CTAs fit per SM and twice as
+// many loads are in flight; the two warps exchange their partial row sums through shared memory).
+template <int NV, int WPR>
+__global__ void __launch_bounds__(256, WPR == 2 ? 2 : 1)
 ln_bwd_kernel(const float* __restrict__ dy, long long dy_stride, const float* __restrict__ x, long long x_stride,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
               const float* __restrict__ dres, long long dres_stride, float* __restrict__ dx, long long dx_stride,
@@ -63,26 +65,34 @@ ln_bwd_kernel(const float* __restrict__ dy, long long dy_stride, const float* __
   // optional second output for the consumer branch of dx: dys = tf32(rowscale[row / rows_per_seq] * dx) (the
   // DropPath-scaled, GEMM-ready copy) and colsum_out += column sums of dys (= the consumer Linear's bias gradient)
   constexpr int D = NV * 128;
-  __shared__ float red[3][8][32 * 4];  // [dgamma|dbeta|colsum][warp][lane*4] for one i at a time
+  constexpr int NW = NV / WPR;  // float4 slabs per lane
+  static_assert(NV % WPR == 0, "row slabs must split evenly over the warps of a row");
+  __shared__ float red[3][8][32 * 4];  // [dgamma|dbeta|colsum][warp][lane*4] for one slab at a time
+  __shared__ float xch[2][8][2];       // [parity][warp][s1, s2] partial row sums (WPR == 2)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int warps_per_cta = blockDim.x >> 5;
-  float4 pg[NV], pb[NV], pc[NV];
+  const int sub = warp % WPR, slot = warp / WPR;  // this warp's part of the row / row slot inside the CTA
+  constexpr int kRowsPerCta = 8 / WPR;
+  float4 pg[NW], pb[NW], pc[NW];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) pg[i] = pb[i] = pc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 gm[NV];
+  for (int i = 0; i < NW; ++i) pg[i] = pb[i] = pc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 gm[NW];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) gm[i] = reinterpret_cast<const float4*>(gamma)[lane + 32 * i];
+  for (int i = 0; i < NW; ++i) gm[i] = reinterpret_cast<const float4*>(gamma)[lane + 32 * (sub * NW + i)];
 
-  for (int row = blockIdx.x * warps_per_cta + warp; row < rows; row += gridDim.x * warps_per_cta) {
-    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * x_stride);
-    const float4* dr = reinterpret_cast<const float4*>(dy + static_cast<long long>(row) * dy_stride);
+  int it = 0;
+  // every warp of a row slot runs the same number of iterations (the pair barrier below needs both warps)
+  for (int row = blockIdx.x * kRowsPerCta + slot; row < rows; row += gridDim.x * kRowsPerCta, ++it) {
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * x_stride) + 32 * sub * NW;
+    const float4* dr = reinterpret_cast<const float4*>(dy + static_cast<long long>(row) * dy_stride) + 32 * sub * NW;
     const float mu = mean[row], rs = rstd[row];
-    float4 xh[NV], g[NV];
+    float4 xh[NW], g[NW], rv[NW];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
+    for (int i = 0; i < NW; ++i) {
       const float4 xv = xr[lane + 32 * i];
       const float4 dv = dr[lane + 32 * i];
+      if (dres != nullptr)
+        rv[i] = (reinterpret_cast<const float4*>(dres + static_cast<long long>(row) * dres_stride) + 32 * sub * NW)[lane + 32 * i];
       xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
       g[i] = make_float4(dv.x * gm[i].x, dv.y * gm[i].y, dv.z * gm[i].z, dv.w * gm[i].w);
       s1 += g[i].x + g[i].y + g[i].z + g[i].w;
@@ -90,46 +100,55 @@ ln_bwd_kernel(const float* __restrict__ dy, long long dy_stride, const float* __
       pg[i].x += dv.x * xh[i].x; pg[i].y += dv.y * xh[i].y; pg[i].z += dv.z * xh[i].z; pg[i].w += dv.w * xh[i].w;
       pb[i].x += dv.x; pb[i].y += dv.y; pb[i].z += dv.z; pb[i].w += dv.w;
     }
-    s1 = warp_sum(s1) * (1.0f / D);
-    s2 = warp_sum(s2) * (1.0f / D);
-    float4* ox = reinterpret_cast<float4*>(dx + static_cast<long long>(row) * dx_stride);
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (WPR == 2) {
+      float* xc = &xch[it & 1][0][0];
+      if (lane == 0) { xc[warp * 2] = s1; xc[warp * 2 + 1] = s2; }
+      asm volatile("bar.sync %0, 64;" ::"r"(slot + 1) : "memory");  // the two warps of this row
+      s1 += xc[(warp ^ 1) * 2];
+      s2 += xc[(warp ^ 1) * 2 + 1];
+    }
+    s1 *= (1.0f / D);
+    s2 *= (1.0f / D);
+    float4* ox = reinterpret_cast<float4*>(dx + static_cast<long long>(row) * dx_stride) + 32 * sub * NW;
+    const float sc = (dys != nullptr && rowscale != nullptr) ? rowscale[row / rows_per_seq] : 1.0f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
+    for (int i = 0; i < NW; ++i) {
       float4 o;
       o.x = rs * (g[i].x - s1 - xh[i].x * s2);
       o.y = rs * (g[i].y - s1 - xh[i].y * s2);
       o.z = rs * (g[i].z - s1 - xh[i].z * s2);
       o.w = rs * (g[i].w - s1 - xh[i].w * s2);
-      if (dres != nullptr) {
-        const float4 r = reinterpret_cast<const float4*>(dres + static_cast<long long>(row) * dres_stride)[lane + 32 * i];
-        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-      }
+      if (dres != nullptr) { o.x += rv[i].x; o.y += rv[i].y; o.z += rv[i].z; o.w += rv[i].w; }
       ox[lane + 32 * i] = o;
       if (dys != nullptr) {
-        const float sc = rowscale != nullptr ? rowscale[row / rows_per_seq] : 1.0f;
         float4 y = make_float4(round_tf32(sc * o.x), round_tf32(sc * o.y), round_tf32(sc * o.z), round_tf32(sc * o.w));
-        reinterpret_cast<float4*>(dys + static_cast<long long>(row) * dys_stride)[lane + 32 * i] = y;
+        (reinterpret_cast<float4*>(dys + static_cast<long long>(row) * dys_stride) + 32 * sub * NW)[lane + 32 * i] = y;
         pc[i].x += y.x; pc[i].y += y.y; pc[i].z += y.z; pc[i].w += y.w;
       }
     }
   }
-  // cross-warp reduction of the parameter-gradient partials, one 128-column slab at a time
+  // cross-warp reduction of the parameter-gradient partials, one 128-column slab per `sub` at a time
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
+  for (int i = 0; i < NW; ++i) {
     *reinterpret_cast<float4*>(&red[0][warp][lane * 4]) = pg[i];
     *reinterpret_cast<float4*>(&red[1][warp][lane * 4]) = pb[i];
     *reinterpret_cast<float4*>(&red[2][warp][lane * 4]) = pc[i];
     __syncthreads();
     {
       const int which = threadIdx.x >> 7, col = threadIdx.x & 127;  // 256 threads: dgamma | dbeta
-      float acc = 0.f;
-      for (int w = 0; w < warps_per_cta; ++w) acc += red[which][w][col];
-      // column of this slab: float4 index (lane + 32 i) -> element (lane*4 + j) + 128 i
-      atomicAdd((which ? dbeta : dgamma) + 128 * i + col, acc);
-      if (colsum_out != nullptr && which == 0) {
-        float c = 0.f;
-        for (int w = 0; w < warps_per_cta; ++w) c += red[2][w][col];
-        atomicAdd(colsum_out + 128 * i + col, c);
+#pragma unroll
+      for (int sb = 0; sb < WPR; ++sb) {
+        float acc = 0.f;
+        for (int w = sb; w < 8; w += WPR) acc += red[which][w][col];
+        // column of this slab: float4 index (lane + 32 (sb NW + i)) -> element (lane*4 + j) + 128 (sb NW + i)
+        atomicAdd((which ? dbeta : dgamma) + 128 * (sb * NW + i) + col, acc);
+        if (colsum_out != nullptr && which == 0) {
+          float c = 0.f;
+          for (int w = sb; w < 8; w += WPR) c += red[2][w][col];
+          atomicAdd(colsum_out + 128 * (sb * NW + i) + col, c);
+        }
       }
     }
     __syncthreads();
@@ -149,10 +168,12 @@ static int ln_bwd_launch(const float* dy, long long dys, const float* x, long lo
                          const float* rstd, const float* g, const float* dres, long long drs, float* dx,
                          long long dxs, float* dg, float* db, int rows, float* dys2, long long dys2s,
                          const float* rowscale, int rps, float* colsum_out, cudaStream_t st) {
-  int grid = (rows + 7) / 8;
+  constexpr int WPR = (NV % 2 == 0 && NV >= 6) ? 2 : 1;
+  constexpr int kRowsPerCta = 8 / WPR;
+  int grid = (rows + kRowsPerCta - 1) / kRowsPerCta;
   if (grid > 148 * 2) grid = 148 * 2;
-  ln_bwd_kernel<NV><<<grid, 256, 0, st>>>(dy, dys, x, xs, mean, rstd, g, dres, drs, dx, dxs, dg, db, rows, dys2, dys2s,
-                                         rowscale, rps > 0 ? rps : 1, colsum_out);
+  ln_bwd_kernel<NV, WPR><<<grid, 256, 0, st>>>(dy, dys, x, xs, mean, rstd, g, dres, drs, dx, dxs, dg, db, rows, dys2,
+                                              dys2s, rowscale, rps > 0 ? rps : 1, colsum_out);
   return atst_check_launch("ln_bwd_kernel");
 }
 

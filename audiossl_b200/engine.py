@@ -20,7 +20,7 @@ from . import ops
 #   ATST_FUSE_GELU bit 0: forward passes that keep no activations (teacher, inference) fuse GELU into fc1 and never
 #                         store the pre-activation; bit 1: the student forward fuses it too (epilogue writes u and g);
 #                  bit 2: the backward fuses GELU' into the fc2 dgrad epilogue
-_FG = int(os.environ.get("ATST_FUSE_GELU", "3"))
+_FG = int(os.environ.get("ATST_FUSE_GELU", "7"))
 FUSE_GELU_NOSAVE, FUSE_GELU, FUSE_DGELU = bool(_FG & 1), bool(_FG & 2), bool(_FG & 4)
 
 

@@ -170,6 +170,42 @@ def test_gelu_passes_match_torch():
     assert (g - gref).abs().max().item() < 5e-3  # tf32 rounding of outputs up to |u| ~ 8 (8 * 2^-11)
 
 
+@pytest.mark.parametrize("M,N,K", [(300, 512, 128), (1000, 1024, 256), (515, 256, 64)])
+def test_gelu_fused_epilogues_match_torch(M, N, K):
+    """fc1 with the GELU epilogue (with and without the stored pre-activation) and the fc2 dgrad with the GELU'
+    epilogue against torch; the CTA-pair kernel serves N % 256 == 0."""
+    from audiossl_b200 import ops
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(1)
+    A = ops.round_tf32(torch.randn(M, K, device="cuda"))
+    W = ops.round_tf32(torch.randn(N, K, device="cuda") * 0.1)
+    b = torch.randn(N, device="cuda")
+    u_ref = A @ W.t() + b
+    g_ref = torch.nn.functional.gelu(u_ref)
+    u = torch.empty(M, N, device="cuda")
+    g = ops.gemm_nt(A, W, bias=b, epi=ops.EPI_GELU, aux=u, round_out=True)
+    g2 = ops.gemm_nt(A, W, bias=b, epi=ops.EPI_GELU, aux=None, round_out=True)
+    assert rel(u, u_ref) < 1e-5 and rel(g, g_ref) < 1e-3 and torch.equal(g, g2)
+    # dgrad: du = (dy W2) * gelu'(u), W2 [out=K2, in=N]
+    K2 = 128
+    dy = ops.round_tf32(torch.randn(M, K2, device="cuda"))
+    W2 = ops.round_tf32(torch.randn(K2, N, device="cuda") * 0.1)
+    ur = u_ref.clone().requires_grad_(True)
+    torch.nn.functional.gelu(ur).backward(dy @ W2)
+    du = ops.gemm_nn(dy, W2, epi=ops.EPI_DGELU, aux=u_ref.contiguous(), round_out=True)
+    assert rel(du, ur.grad) < 1e-3
+
+
+@pytest.mark.parametrize("rows,cols", [(1000, 3072), (77, 130), (129, 4), (5000, 768)])
+def test_colsum_accumulates(rows, cols):
+    from audiossl_b200 import ops
+    torch.manual_seed(2)
+    X = torch.randn(rows, cols, device="cuda")
+    out = torch.ones(cols, device="cuda")
+    ops.colsum_acc(X, out)
+    assert rel(out, 1.0 + X.double().sum(0)) < 1e-5
+
+
 # --------------------------------------------------------------------------- full model vs oracle / golden
 def build_cuda_model(case):
     from audiossl_b200.models.atst import ATST

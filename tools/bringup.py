@@ -214,6 +214,47 @@ def sec_umma_probe():
         print("%s mode 0 layout=%d lbo=%5d sbo=%4d kstep=%3d rel=%.3e" % ("OK " if err < 2e-3 else "   ", layout, lbo, sbo, kstep, err))
 
 
+def sec_ew_perf():
+    """HBM-bound passes at the config-2 shape: time and achieved algorithmic GB/s."""
+    import torch
+    from audiossl_b200 import ops
+    M, D = 128512, 768
+    x = torch.randn(M, D, device="cuda")
+    g = torch.randn(D, device="cuda")
+    b = torch.randn(D, device="cuda")
+    y, mean, rstd = ops.layernorm_fwd(x, g, b, M, D)
+    dy = torch.randn(M, D, device="cuda")
+    dres = torch.randn(M, D, device="cuda")
+    dx = torch.empty(M, D, device="cuda")
+    dys = torch.empty(M, D, device="cuda")
+    dg, db, cs = (torch.zeros(D, device="cuda") for _ in range(3))
+    sc = torch.rand(512, device="cuda") + 0.5
+    u = torch.randn(M, 4 * D, device="cuda")
+    gg = torch.empty(M, 4 * D, device="cuda")
+    cs4 = torch.zeros(4 * D, device="cuda")
+    flush = torch.empty(64 * 1024 * 1024, device="cuda")  # 256 MB > L2
+
+    def tm(fn, nbytes, name):
+        ts = []
+        for _ in range(5):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        t = sorted(ts)[len(ts) // 2]
+        print("%-44s %.3f ms  %7.1f GB/s" % (name, t, nbytes / t / 1e6))
+
+    tm(lambda: ops.layernorm_fwd(x, g, b, M, D, out=y, mean=mean, rstd=rstd), 8.0 * M * D, "ln_fwd [M,768]")
+    tm(lambda: ops.layernorm_bwd(dy, x, mean, rstd, g, dg, db, M, D, dres=dres, dx=dx, dys=dys, rowscale=sc,
+                                 rows_per_seq=251, colsum_out=cs), 20.0 * M * D, "ln_bwd (+dres, dys, colsum) [M,768]")
+    tm(lambda: ops.gelu_fwd(u, gg), 32.0 * M * D, "gelu_fwd [M,3072]")
+    tm(lambda: ops.gelu_bwd_(gg, u, colsum_out=cs4), 48.0 * M * D, "gelu_bwd + colsum [M,3072]")
+    tm(lambda: ops.colsum_acc(gg, cs4), 16.0 * M * D, "colsum [M,3072]")
+
+
 def sec_attn_trace():
     """clock64 timeline of one CTA of the tcgen05 attention backward kernels at the config-2 shape."""
     import torch
@@ -545,7 +586,7 @@ def sec_pair():
         L.atst_set_option(b"gemm_cta_pair", 0)
 
 
-SECTIONS = {"attn_trace": sec_attn_trace, "umma_probe": sec_umma_probe, "attn_tc": sec_attn_tc, "pair": sec_pair, "heads": sec_heads, "gemm_perf": sec_gemm_perf, "mel": sec_mel, "gemm_nt": sec_gemm_nt, "gemm_mn": sec_gemm_mn, "ln": sec_ln, "attn": sec_attn,
+SECTIONS = {"ew_perf": sec_ew_perf, "attn_trace": sec_attn_trace, "umma_probe": sec_umma_probe, "attn_tc": sec_attn_tc, "pair": sec_pair, "heads": sec_heads, "gemm_perf": sec_gemm_perf, "mel": sec_mel, "gemm_nt": sec_gemm_nt, "gemm_mn": sec_gemm_mn, "ln": sec_ln, "attn": sec_attn,
             "bn": sec_bn, "loss": sec_loss, "optim": sec_optim, "tokens": sec_tokens}
 
 if __name__ == "__main__":
