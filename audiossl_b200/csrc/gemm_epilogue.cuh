@@ -11,19 +11,26 @@ namespace atst {
 // one MUFU.RCP + one MUFU.EX2 + 7 FMA instead of libdevice erff's ~25 instructions.  The exp(-u^2/2) factor is
 // shared between the cdf and the pdf, so gelu'(u) costs no second exponential.
 struct GeluParts { float cdf, pdf; };
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ GeluParts gelu_parts(float u) {
   const float x = u * 0.70710678118654752f;
   const float ax = fabsf(x);
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));  // MUFU.RCP, branch-free (keeps the 8 chains interleaved)
+  // raw MUFU.RCP / MUFU.EX2 (flush-to-zero forms): the argument of the reciprocal is >= 1 and a flushed exp(-x^2)
+  // only occurs where erf has long saturated, so the denormal fix-ups of __fdividef / __expf buy nothing here
+  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
   poly *= t;
-  const float e = __expf(-ax * ax);            // exp(-u^2 / 2)
-  const float erf_abs = fmaf(-poly, e, 1.0f);  // erf(|x|)
+  const float e = ex2_approx(-1.4426950408889634f * ax * ax);  // exp(-u^2 / 2)
+  const float erf_abs = fmaf(-poly, e, 1.0f);                  // erf(|x|)
   GeluParts g;
-  g.cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+  g.cdf = fmaf(0.5f, copysignf(erf_abs, x), 0.5f);
   g.pdf = 0.3989422804014327f * e;
   return g;
 }

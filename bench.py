@@ -300,6 +300,30 @@ def run_ours(args):
         step(args.warmup, False)
         torch.cuda.synchronize()
         return
+    if args.gaps:  # in-situ kernel timeline of one step (CUPTI through torch.profiler): busy vs idle GPU time
+        from torch.profiler import profile, ProfilerActivity
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step(args.warmup, False)
+            torch.cuda.synchronize()
+        ks = sorted(((e.time_range.start, e.time_range.end, e.name) for e in prof.events()
+                     if e.device_type == torch.autograd.DeviceType.CUDA), key=lambda t: t[0])
+        busy = sum(b - a for a, b, _ in ks)
+        span = ks[-1][1] - ks[0][0]
+        agg = {}
+        for a, b, nm in ks:
+            d = agg.setdefault(nm[:60], [0, 0.0])
+            d[0] += 1
+            d[1] += (b - a) / 1e3
+        gaps = sorted(((ks[i + 1][0] - ks[i][1], ks[i][2][:40], ks[i + 1][2][:40]) for i in range(len(ks) - 1)),
+                      reverse=True)
+        print("kernels %d  span %.2f ms  busy %.2f ms  idle %.2f ms" % (len(ks), span / 1e3, busy / 1e3, (span - busy) / 1e3))
+        for nm, (n_, ms_) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:25]:
+            print("  %-60s n=%4d %8.3f ms" % (nm, n_, ms_))
+        print("largest gaps (us):")
+        for g_, a_, b_ in gaps[:15]:
+            print("  %8.1f  %s -> %s" % (g_, a_, b_))
+        return
     sampler = ClockSampler(local)
     sampler.start()
     ops.reset_stats()
@@ -403,9 +427,10 @@ if __name__ == "__main__":
     ap.add_argument("--arch", default="", help="override the config's architecture")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="warm-up + one step only (for ncu captures)")
+    ap.add_argument("--gaps", action="store_true", help="in-situ kernel timeline of one step: busy / idle GPU time")
     ap.add_argument("--breakdown", default="", help="write a per-GEMM-shape timing table to this file")
     a = ap.parse_args()
-    if a.warmup < 3 and a.impl == "ours" and not a.profile:
+    if a.warmup < 3 and a.impl == "ours" and not a.profile and not a.gaps:
         a.warmup = 3
     if a.impl == "reference":
         run_reference(a)
