@@ -47,6 +47,7 @@ struct BwdTcParams {
   const int* lengths;
   int N, H, D;
   float scale;
+  int prefetch_dist, num_items;  // see attention_tc.cu
   long long* trace;  // bring-up: clock64() timeline of one CTA (tools/bringup.py attn_trace), or null
   int trace_seq;
 };
@@ -146,6 +147,22 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvR, const __grid_cons
         } else {
           tma_load_3d(smem + kY1 + q * 16384, &tmQkvY, &bar_y[q], 0, r, cq);
           tma_load_3d(smem + kY2 + q * 16384, &tmDoY, &bar_y[q], 0, r, cdo);
+        }
+      }
+      // pull the operands of the CTA that will follow this one on the SM into L2 (see attention_tc.cu)
+      const int nxt = (s * p.H + h) + p.prefetch_dist;
+      if (p.prefetch_dist > 0 && nxt < p.num_items) {
+        const int s2 = nxt / p.H, h2 = nxt - s2 * p.H;
+        const int r2 = s2 * N, c2 = (h2 * 64) >> 5;
+        for (int t = 0; t < tiles; ++t) {
+          tma_prefetch_3d(&tmQkvR, 0, r2 + t * 128, MODE == 0 ? c2 : c2 + (D >> 5));
+          if (MODE == 0) tma_prefetch_3d(&tmDoR, 0, r2 + t * 128, c2);
+          else           tma_prefetch_3d(&tmQkvR, 0, r2 + t * 128, c2 + (D >> 4));
+        }
+        for (int q = 0; q < ((N + 63) >> 6); ++q) {
+          tma_prefetch_3d(&tmQkvY, 0, r2 + q * 64, MODE == 0 ? c2 + (D >> 5) : c2);
+          if (MODE == 0) tma_prefetch_3d(&tmQkvY, 0, r2 + q * 64, c2 + (D >> 4));
+          else           tma_prefetch_3d(&tmDoY, 0, r2 + q * 64, c2);
         }
       }
       for (int t = 1; t < tiles; ++t) {
@@ -344,6 +361,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvR, const __grid_cons
 int make_map_generic_3d(CUtensorMap* map, const float* ptr, long long rows, int feats, int ld, int box_rows,
                         int box_chunks);
 int make_map_seq4d(CUtensorMap* map, const float* ptr, int S, int N, int feats, int box_rows);
+int attention_l2_prefetch_enabled();
+int gemm_num_sms();
 int attention_delta(const float* o, const float* d_o, float* delta, int S, int N, int H, cudaStream_t stream);
 
 static long long* g_trace = nullptr;
@@ -377,6 +396,8 @@ int attention_backward_tc(const float* qkv, const float* o, const float* d_o, co
   BwdTcParams p{};
   p.dqkv = dqkv; p.lse = lse; p.delta = delta_ws; p.lengths = lengths; p.N = N; p.H = H; p.D = D; p.scale = 0.125f;
   dim3 grid(H, S);
+  p.prefetch_dist = attention_l2_prefetch_enabled() ? gemm_num_sms() : 0;
+  p.num_items = S * H;
   p.trace_seq = g_trace_seq;
   p.trace = g_trace_mode == 0 ? g_trace : nullptr;
   attn_bwd_tc_kernel<0><<<grid, 512, kSmemBwd, stream>>>(tqr, tqy, tdr, tdy, tout, p);

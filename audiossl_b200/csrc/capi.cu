@@ -7,6 +7,7 @@
 
 namespace atst {
 void attention_set_tc(int on);
+void attention_set_l2_prefetch(int on);
 void attention_set_trace(long long* buf, int seq, int mode);
 int umma_probe(int mode, const float* A, const float* B, float* D, unsigned layout, unsigned lbo, unsigned sbo,
                unsigned kstep, cudaStream_t stream);
@@ -22,6 +23,7 @@ int atst_set_option(const char* name, int value) {
   if (name != nullptr && strcmp(name, "gemm_l2_prefetch") == 0) { gemm_set_l2_prefetch(value); return ATST_OK; }
   if (name != nullptr && strcmp(name, "gemm_cta_pair") == 0) { gemm_set_cta_pair(value); return ATST_OK; }
   if (name != nullptr && strcmp(name, "attn_tcgen05") == 0) { attention_set_tc(value); return ATST_OK; }
+  if (name != nullptr && strcmp(name, "attn_l2_prefetch") == 0) { attention_set_l2_prefetch(value); return ATST_OK; }
   atst_set_error("atst_set_option: unknown option '%s'", name ? name : "(null)");
   return ATST_ERR_ARG;
 }

@@ -6,10 +6,10 @@
 // two SMs read the other half from the peer's shared memory.  Per CTA: 64 B/clk of TMA fill, 64 B/clk of UMMA
 // reads, 64 B/clk of L2 traffic, and the 32 KB stages make the smem ring 6 deep instead of 4.
 //
-// Roles per CTA (384 threads): warp 0 TMA producer (both CTAs; transactions complete on the LEADER's full
+// Roles per CTA (640 threads): warp 0 TMA producer (both CTAs; transactions complete on the LEADER's full
 // barrier), warp 1 MMA issuer (leader only: tcgen05.mma.cta_group::2, M=256; tcgen05.commit multicast frees the
 // smem slot / publishes the accumulator in both CTAs), warp 2 TMEM allocator (cta_group::2 alloc in both CTAs),
-// warps 4-11 epilogue (own 128 TMEM lanes, two warps per lane quadrant; the accumulator stage is handed back on the leader's barrier, remotely
+// warps 4-19 epilogue (own 128 TMEM lanes, four warps per lane quadrant; the accumulator stage is handed back on the leader's barrier, remotely
 // from the follower).  Operand majors as in the 1-CTA kernel (K-major 128B swizzle, or token-major tensors via
 // the 32B-atom swizzle).
 #include <cooperative_groups.h>
@@ -26,6 +26,8 @@ constexpr int kBN = 256;       // N columns per pair tile
 constexpr int kBNHalf = 128;   // B rows staged per CTA
 constexpr int kBK = 32;        // tf32 elements per k-block (128 B)
 constexpr int kStages2 = 6;
+constexpr int kEpiWarps2 = 16;                 // four per TMEM lane quadrant, each walking a 64-column quarter of the tile
+constexpr int kThreads2 = 128 + 32 * kEpiWarps2;
 constexpr int kA2 = kBM * 128;       // 16 KB
 constexpr int kB2 = kBNHalf * 128;   // 16 KB
 constexpr int kStage2 = kA2 + kB2;   // 32 KB
@@ -98,7 +100,7 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
 }  // namespace
 
 template <bool A_MN, bool B_MN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 gemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
   extern __shared__ uint8_t smem_raw2[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw2) + 1023) & ~uintptr_t(1023));
@@ -136,7 +138,7 @@ gemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 16);  // 8 epilogue warps x 2 CTAs
+      mbar_init(&tempty_bar[i], 2 * kEpiWarps2);  // every epilogue warp of both CTAs
     }
     fence_barrier_init();
   }
@@ -220,7 +222,8 @@ gemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
-    // eight warps: two per TMEM lane quadrant, each walking one 128-column half of the tile
+    // kEpiWarps2 / 4 warps per TMEM lane quadrant, each walking one column slice of the tile
+    constexpr int kGroupsPerWarp = (kBN / 8) / (kEpiWarps2 / 4);
     const int ew = (warp - 4) & 3, chalf = (warp - 4) >> 2;
     const int epi_tid = threadIdx.x - 128;
     int acc = 0;
@@ -236,8 +239,9 @@ gemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       auto release = [&]() {
         if (lane == 0) mbar_arrive_leader(tempty);
       };
-      epilogue_tile<kBN, 256>(p, m0, n0, empty_split, tmem_base + acc * kBN, smem_bias + acc * 256, ew, lane, epi_tid,
-                              chalf * (kBN / 16), (chalf + 1) * (kBN / 16), &tfull_bar[acc], acc_phase, release);
+      epilogue_tile<kBN, 32 * kEpiWarps2>(p, m0, n0, empty_split, tmem_base + acc * kBN, smem_bias + acc * 256, ew, lane,
+                                          epi_tid, chalf * kGroupsPerWarp, (chalf + 1) * kGroupsPerWarp, &tfull_bar[acc],
+                                          acc_phase, release);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -272,7 +276,7 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
   const int tiles = m_tiles * n_tiles * (p.splits > 0 ? p.splits : 1);
   const int pairs = gemm_num_sms() / 2;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
-  kfn<<<grid, 384, kSmem2, stream>>>(ta, tb, p);
+  kfn<<<grid, kThreads2, kSmem2, stream>>>(ta, tb, p);
   return atst_check_launch("gemm2_tf32_kernel");
 }
 

@@ -288,6 +288,7 @@ def sec_attn_trace():
 def sec_attn_tc():
     from audiossl_b200 import _lib
     _lib.lib().atst_set_option(b"attn_tcgen05", int(os.environ.get("ATTN_TC", "3")))
+    _lib.lib().atst_set_option(b"attn_l2_prefetch", int(os.environ.get("ATTN_PF", "1")))
     sec_attn()
 
 
