@@ -78,6 +78,33 @@ __device__ __forceinline__ void umma2_tf32(uint32_t d_tmem, uint64_t a_desc, uin
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// predicated forms for a converged warp (see common.cuh): only the lane with `lead` set issues
+__device__ __forceinline__ void umma2_tf32_p(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t accumulate, uint32_t lead) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, L;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.ne.b32 L, %7, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "@L tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(lead)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc_p(uint64_t* bar, uint32_t lead) {
+  const uint16_t mask = 3;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred L;\n\t"
+      "setp.ne.b32 L, %2, 0;\n\t"
+      "@L tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "h"(mask), "r"(lead)
+      : "memory");
+}
 // arrive (once the MMAs issued so far have completed) on the barrier at the same smem offset in BOTH CTAs
 __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
   const uint16_t mask = 3;
@@ -180,6 +207,15 @@ gemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ------------------------------------------------------------ MMA issuer (leader CTA only)
     if (leader) {
       const uint32_t idesc = make_idesc(2u, 2 * kBM, kBN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+      // descriptor halves: the high word is fixed per operand layout, the low word is (address >> 4) | LBO and
+      // advances by (bytes >> 4); issue is predicated on one elected lane of the converged warp (uniform datapath,
+      // no per-instruction divergent region)
+      const uint32_t a_hi = A_MN ? smem_desc_hi(p.mn_lbo, p.mn_sbo, p.mn_layout) : smem_desc_hi(16, 1024, 2);
+      const uint32_t b_hi = B_MN ? smem_desc_hi(p.mn_lbo, p.mn_sbo, p.mn_layout) : smem_desc_hi(16, 1024, 2);
+      const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem_a), A_MN ? p.mn_lbo : 16);
+      const uint32_t b_lo0 = smem_desc_lo(smem_u32(smem_b), B_MN ? p.mn_lbo : 16);
+      const uint32_t a_step = (A_MN ? p.mn_kstep : 32) >> 4, b_step = (B_MN ? p.mn_kstep : 32) >> 4;
+      const uint32_t lead = elect_one() ? 1u : 0u;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -194,28 +230,19 @@ gemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t a_addr = smem_u32(smem_a + stage * kA2);
-            const uint32_t b_addr = smem_u32(smem_b + stage * kB2);
+          const uint32_t a_lo = a_lo0 + stage * (kA2 >> 4), b_lo = b_lo0 + stage * (kB2 >> 4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t da = A_MN ? make_smem_desc(a_addr + k * p.mn_kstep, p.mn_lbo, p.mn_sbo, p.mn_layout)
-                                       : make_smem_desc(a_addr + k * 32, 16, 1024, 2);
-              const uint64_t db = B_MN ? make_smem_desc(b_addr + k * p.mn_kstep, p.mn_lbo, p.mn_sbo, p.mn_layout)
-                                       : make_smem_desc(b_addr + k * 32, 16, 1024, 2);
-              umma2_tf32(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            }
-            umma2_commit_mc(&empty_bar[stage]);
-            if (kb == kb1 - 1) umma2_commit_mc(&tfull_bar[acc]);
-          }
-          __syncwarp();
+          for (int k = 0; k < 4; ++k)
+            umma2_tf32_p(d_tmem, a_lo + k * a_step, a_hi, b_lo + k * b_step, b_hi, idesc, (kb > kb0 || k > 0) ? 1u : 0u,
+                         lead);
+          umma2_commit_mc_p(&empty_bar[stage], lead);
+          if (kb == kb1 - 1) umma2_commit_mc_p(&tfull_bar[acc], lead);
           if (++stage == kStages2) {
             stage = 0;
             phase ^= 1;
           }
         }
-        if (kb1 <= kb0 && lane == 0) umma2_commit_mc(&tfull_bar[acc]);
-        __syncwarp();
+        if (kb1 <= kb0) umma2_commit_mc_p(&tfull_bar[acc], lead);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }

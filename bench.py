@@ -304,7 +304,8 @@ def run_ours(args):
         from torch.profiler import profile, ProfilerActivity
         torch.cuda.synchronize()
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
-            step(args.warmup, False)
+            for k_ in range(max(args.steps, 1)):
+                step(args.warmup + k_, False)
             torch.cuda.synchronize()
         ks = sorted(((e.time_range.start, e.time_range.end, e.name) for e in prof.events()
                      if e.device_type == torch.autograd.DeviceType.CUDA), key=lambda t: t[0])
@@ -317,7 +318,8 @@ def run_ours(args):
             d[1] += (b - a) / 1e3
         gaps = sorted(((ks[i + 1][0] - ks[i][1], ks[i][2][:40], ks[i + 1][2][:40]) for i in range(len(ks) - 1)),
                       reverse=True)
-        print("kernels %d  span %.2f ms  busy %.2f ms  idle %.2f ms" % (len(ks), span / 1e3, busy / 1e3, (span - busy) / 1e3))
+        print("steps %d  kernels %d  span %.2f ms  busy %.2f ms  idle %.2f ms" %
+              (max(args.steps, 1), len(ks), span / 1e3, busy / 1e3, (span - busy) / 1e3))
         for nm, (n_, ms_) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:25]:
             print("  %-60s n=%4d %8.3f ms" % (nm, n_, ms_))
         print("largest gaps (us):")
