@@ -75,25 +75,24 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvR, const __grid_cons
   uint64_t* bar_rfree = bars + 1;
   uint64_t* bar_acc = bars + 2;
   uint64_t* bar_accfree = bars + 3;
-  uint64_t* bar_y = bars + 4;      // [4]
-  uint64_t* bar_full = bars + 8;   // [3]
-  uint64_t* bar_ds = bars + 11;    // [3]
-  uint64_t* bar_free = bars + 14;  // [3]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* bar_y = bars + 4;       // [4]
+  uint64_t* bar_full = bars + 8;    // [3]
+  uint64_t* bar_ds = bars + 11;     // [3]
+  uint64_t* bar_free = bars + 14;   // [3]
+  uint64_t* bar_yfree = bars + 17;  // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = blockIdx.x, s = blockIdx.y;
-  const bool tracing = p.trace != nullptr && h == 0 && s == p.trace_seq;
-  const int N = p.N, D = p.D;
-  int len = p.lengths ? p.lengths[s] : N;
-  if (len <= 0 || len > N) len = N;  // see attention.cu
-  const int row0 = s * N;  // first token row of this sequence
+  const int N = p.N, D = p.D, H = p.H;
   const int tiles = (N + 127) >> 7;
-  const int ncols = (MODE == 0) ? len : N;  // dQ only needs keys < len; dK/dV walk every query
-  const int nq = (ncols + 63) >> 6;
-  const int W = tiles * nq;  // work quarters
-  // 32-float chunk index (third TMA coordinate) of this head's q / k / v / dO columns
-  const int cq = (h * 64) >> 5, ck = (D + h * 64) >> 5, cv = (2 * D + h * 64) >> 5, cdo = (h * 64) >> 5;
+  // Persistent CTA: items (sequence, head) blockIdx.x, blockIdx.x + gridDim.x, ...  Every role walks the same item
+  // sequence with running counters (work quarters gi -> ring slot / use count, row tiles gt, per-quarter parity
+  // bits), so the next item's operands stream in while this item's last quarters are still being computed.
+  auto item_len = [&](int s) {
+    int len = p.lengths ? p.lengths[s] : N;
+    return (len <= 0 || len > N) ? N : len;  // see attention.cu
+  };
+  auto item_nq = [&](int len) { return (((MODE == 0) ? len : N) + 63) >> 6; };  // dQ only needs keys < len
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQkvR);
@@ -107,7 +106,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvR, const __grid_cons
     mbar_init(bar_rfree, 1);
     mbar_init(bar_acc, 1);
     mbar_init(bar_accfree, 128);
-    for (int i = 0; i < 4; ++i) mbar_init(&bar_y[i], 1);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&bar_y[i], 1);
+      mbar_init(&bar_yfree[i], 1);
+    }
     for (int i = 0; i < kSlots; ++i) {
       mbar_init(&bar_full[i], 1);
       mbar_init(&bar_ds[i], 256);
@@ -121,53 +123,67 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvR, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tm_acc1 = tmem_base, tm_acc2 = tmem_base + 64;
-  if (warp == 1) ATTN_TRACE(0);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      auto load_rows = [&](int t) {
-        mbar_expect_tx(bar_r, 64 * 1024);
-        const int r = row0 + t * 128;
-        if (MODE == 0) {
-          tma_load_3d(smem + kR1, &tmQkvR, bar_r, 0, r, cq);
-          tma_load_3d(smem + kR2, &tmDoR, bar_r, 0, r, cdo);
-        } else {
-          tma_load_3d(smem + kR1, &tmQkvR, bar_r, 0, r, ck);
-          tma_load_3d(smem + kR2, &tmQkvR, bar_r, 0, r, cv);
+      uint32_t gt = 0, ypar = 0, yused = 0;  // row tiles loaded so far; per column quarter: load-count parity / loaded before
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        const int s = item / H, h = item - s * H;
+        const int row0 = s * N, nq = item_nq(item_len(s));
+        const int cq = (h * 64) >> 5, ck = cq + (D >> 5), cv = cq + (D >> 4), cdo = cq;
+        for (int t = 0; t < tiles; ++t, ++gt) {
+          if (gt > 0) mbar_wait(bar_rfree, (gt - 1) & 1);  // every S / dP MMA of the previous tile has read R1, R2
+          mbar_expect_tx(bar_r, 64 * 1024);
+          const int r = row0 + t * 128;
+          if (MODE == 0) {
+            tma_load_3d(smem + kR1, &tmQkvR, bar_r, 0, r, cq);
+            tma_load_3d(smem + kR2, &tmDoR, bar_r, 0, r, cdo);
+          } else {
+            tma_load_3d(smem + kR1, &tmQkvR, bar_r, 0, r, ck);
+            tma_load_3d(smem + kR2, &tmQkvR, bar_r, 0, r, cv);
+          }
+          // the loads that follow are known exactly (next row tile, then the next item's columns): pull them into
+          // L2 now so that they hit when the buffers free up (their latency sits on the tile-boundary critical path)
+          if (p.prefetch_dist) {
+            int ns = s, nh = h, nt = t + 1;
+            if (nt == tiles) {
+              const int nitem = item + gridDim.x;
+              nt = nitem < p.num_items ? 0 : -1;
+              ns = nitem / H;
+              nh = nitem - ns * H;
+            }
+            if (nt >= 0) {
+              const int nr = ns * N + nt * 128, nc = (nh * 64) >> 5;
+              tma_prefetch_3d(&tmQkvR, 0, nr, MODE == 0 ? nc : nc + (D >> 5));
+              if (MODE == 0) tma_prefetch_3d(&tmDoR, 0, nr, nc);
+              else           tma_prefetch_3d(&tmQkvR, 0, nr, nc + (D >> 4));
+              if (nt == 0) {
+                for (int q = 0; q < ((N + 63) >> 6); ++q) {
+                  tma_prefetch_3d(&tmQkvY, 0, ns * N + q * 64, MODE == 0 ? nc + (D >> 5) : nc);
+                  if (MODE == 0) tma_prefetch_3d(&tmQkvY, 0, ns * N + q * 64, nc + (D >> 4));
+                  else           tma_prefetch_3d(&tmDoY, 0, ns * N + q * 64, nc);
+                }
+              }
+            }
+          }
+          if (t != 0) continue;
+          for (int q = 0; q < nq; ++q) {
+            // k-th load of this quarter: the (k-1)-th use's last second-stage MMAs (previous item) have completed
+            if ((yused >> q) & 1) mbar_wait(&bar_yfree[q], ((ypar >> q) & 1) ^ 1);
+            mbar_expect_tx(&bar_y[q], 32 * 1024);
+            const int ry = row0 + q * 64;
+            if (MODE == 0) {
+              tma_load_3d(smem + kY1 + q * 16384, &tmQkvY, &bar_y[q], 0, ry, ck);
+              tma_load_3d(smem + kY2 + q * 16384, &tmQkvY, &bar_y[q], 0, ry, cv);
+            } else {
+              tma_load_3d(smem + kY1 + q * 16384, &tmQkvY, &bar_y[q], 0, ry, cq);
+              tma_load_3d(smem + kY2 + q * 16384, &tmDoY, &bar_y[q], 0, ry, cdo);
+            }
+            ypar ^= 1u << q;
+            yused |= 1u << q;
+          }
         }
-      };
-      load_rows(0);
-      for (int q = 0; q < nq; ++q) {
-        mbar_expect_tx(&bar_y[q], 32 * 1024);
-        const int r = row0 + q * 64;
-        if (MODE == 0) {
-          tma_load_3d(smem + kY1 + q * 16384, &tmQkvY, &bar_y[q], 0, r, ck);
-          tma_load_3d(smem + kY2 + q * 16384, &tmQkvY, &bar_y[q], 0, r, cv);
-        } else {
-          tma_load_3d(smem + kY1 + q * 16384, &tmQkvY, &bar_y[q], 0, r, cq);
-          tma_load_3d(smem + kY2 + q * 16384, &tmDoY, &bar_y[q], 0, r, cdo);
-        }
-      }
-      // pull the operands of the CTA that will follow this one on the SM into L2 (see attention_tc.cu)
-      const int nxt = (s * p.H + h) + p.prefetch_dist;
-      if (p.prefetch_dist > 0 && nxt < p.num_items) {
-        const int s2 = nxt / p.H, h2 = nxt - s2 * p.H;
-        const int r2 = s2 * N, c2 = (h2 * 64) >> 5;
-        for (int t = 0; t < tiles; ++t) {
-          tma_prefetch_3d(&tmQkvR, 0, r2 + t * 128, MODE == 0 ? c2 : c2 + (D >> 5));
-          if (MODE == 0) tma_prefetch_3d(&tmDoR, 0, r2 + t * 128, c2);
-          else           tma_prefetch_3d(&tmQkvR, 0, r2 + t * 128, c2 + (D >> 4));
-        }
-        for (int q = 0; q < ((N + 63) >> 6); ++q) {
-          tma_prefetch_3d(&tmQkvY, 0, r2 + q * 64, MODE == 0 ? c2 + (D >> 5) : c2);
-          if (MODE == 0) tma_prefetch_3d(&tmQkvY, 0, r2 + q * 64, c2 + (D >> 4));
-          else           tma_prefetch_3d(&tmDoY, 0, r2 + q * 64, c2);
-        }
-      }
-      for (int t = 1; t < tiles; ++t) {
-        mbar_wait(bar_rfree, (t - 1) & 1);  // every S / dP MMA of tile t-1 has read R1, R2
-        load_rows(t);
       }
     }
   } else if (warp == 1) {
@@ -177,33 +193,44 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvR, const __grid_cons
     const uint32_t r1 = smem_desc_lo(smem_u32(smem + kR1), kKLbo), r2 = smem_desc_lo(smem_u32(smem + kR2), kKLbo);
     const uint32_t y1 = smem_desc_lo(smem_u32(smem + kY1), kKLbo), y2 = smem_desc_lo(smem_u32(smem + kY2), kKLbo);
     const uint32_t leader = elect_one() ? 1u : 0u;
-    for (int i = 0; i < W; ++i) {
-      const int t = i / nq, q = i - t * nq, slot = i % kSlots, u = i / kSlots;
-      if (q == 0) mbar_wait(bar_r, t & 1);
-      if (t == 0) mbar_wait(&bar_y[q], 0);
-      if (u > 0) mbar_wait(&bar_free[slot], (u - 1) & 1);  // the slot's second-stage MMAs have read it
-      tc_fence_after();
-      ATTN_TRACE(1 + 4 * i);
-      {
-        const uint32_t tm_s = tmem_base + 128 + slot * 128, tm_dp = tm_s + 64;
-        const uint32_t yq = q * (16384 >> 4);
+    uint32_t gi = 0, gt = 0, ypar = 0;
+    int iter = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++iter) {
+      const int nq = item_nq(item_len(item / H));
+      const bool tracing = p.trace != nullptr && blockIdx.x == 0 && iter == p.trace_seq;
+      ATTN_TRACE(0);
+      for (int t = 0; t < tiles; ++t, ++gt) {
+        for (int q = 0; q < nq; ++q, ++gi) {
+          const int i = t * nq + q;
+          const uint32_t slot = gi % kSlots, u = gi / kSlots;
+          if (q == 0) mbar_wait(bar_r, gt & 1);
+          if (t == 0) {
+            mbar_wait(&bar_y[q], (ypar >> q) & 1);
+            ypar ^= 1u << q;
+          }
+          if (u > 0) mbar_wait(&bar_free[slot], (u - 1) & 1);  // the slot's second-stage MMAs have read it
+          tc_fence_after();
+          ATTN_TRACE(1 + 4 * i);
+          const uint32_t tm_s = tmem_base + 128 + slot * 128, tm_dp = tm_s + 64;
+          const uint32_t yq = q * (16384 >> 4);
 #pragma unroll
-        for (int kc = 0; kc < 2; ++kc)
+          for (int kc = 0; kc < 2; ++kc)
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_tf32_ss_p(tm_s, r1 + ((kc * 16384 + k * 32) >> 4), hi, y1 + yq + ((kc * 8192 + k * 32) >> 4), hi,
-                           idesc_s, (kc | k) ? 1u : 0u, leader);
+            for (int k = 0; k < 4; ++k)
+              umma_tf32_ss_p(tm_s, r1 + ((kc * 16384 + k * 32) >> 4), hi, y1 + yq + ((kc * 8192 + k * 32) >> 4), hi,
+                             idesc_s, (kc | k) ? 1u : 0u, leader);
 #pragma unroll
-        for (int kc = 0; kc < 2; ++kc)
+          for (int kc = 0; kc < 2; ++kc)
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_tf32_ss_p(tm_dp, r2 + ((kc * 16384 + k * 32) >> 4), hi, y2 + yq + ((kc * 8192 + k * 32) >> 4), hi,
-                           idesc_s, (kc | k) ? 1u : 0u, leader);
-        umma_commit_p(&bar_full[slot], leader);
-        if (q == nq - 1) umma_commit_p(bar_rfree, leader);
+            for (int k = 0; k < 4; ++k)
+              umma_tf32_ss_p(tm_dp, r2 + ((kc * 16384 + k * 32) >> 4), hi, y2 + yq + ((kc * 8192 + k * 32) >> 4), hi,
+                             idesc_s, (kc | k) ? 1u : 0u, leader);
+          umma_commit_p(&bar_full[slot], leader);
+          if (q == nq - 1) umma_commit_p(bar_rfree, leader);
+          ATTN_TRACE(2 + 4 * i);
+          __syncwarp();
+        }
       }
-      ATTN_TRACE(2 + 4 * i);
-      __syncwarp();
     }
   } else if (warp == 3) {
     // ------------------------------------------------------------ MMA issuer 2: second-stage MMAs (A operand in TMEM)
@@ -211,28 +238,36 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvR, const __grid_cons
     const uint32_t hi = smem_desc_hi(8192, kSbo, kLayout);
     const uint32_t y1 = smem_desc_lo(smem_u32(smem + kY1), 8192), y2 = smem_desc_lo(smem_u32(smem + kY2), 8192);
     const uint32_t leader = elect_one() ? 1u : 0u;
-    for (int i = 0; i < W; ++i) {
-      const int t = i / nq, q = i - t * nq, slot = i % kSlots, u = i / kSlots;
-      mbar_wait(&bar_ds[slot], u & 1);
-      if (q == 0 && t > 0) mbar_wait(bar_accfree, (t - 1) & 1);  // the previous tile's accumulators were read out
-      tc_fence_after();
-      ATTN_TRACE(3 + 4 * i);
-      {
-        const uint32_t tm_s = tmem_base + 128 + slot * 128, tm_dp = tm_s + 64;
-        const uint32_t yq = q * (16384 >> 4);
-        const uint32_t acc0 = q ? 1u : 0u;
+    uint32_t gi = 0, gt = 0;
+    int iter = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++iter) {
+      const int nq = item_nq(item_len(item / H));
+      const bool tracing = p.trace != nullptr && blockIdx.x == 0 && iter == p.trace_seq;
+      for (int t = 0; t < tiles; ++t, ++gt) {
+        for (int q = 0; q < nq; ++q, ++gi) {
+          const int i = t * nq + q;
+          const uint32_t slot = gi % kSlots, u = gi / kSlots;
+          mbar_wait(&bar_ds[slot], u & 1);
+          if (q == 0 && gt > 0) mbar_wait(bar_accfree, (gt - 1) & 1);  // the previous tile's accumulators were read out
+          tc_fence_after();
+          ATTN_TRACE(3 + 4 * i);
+          const uint32_t tm_s = tmem_base + 128 + slot * 128, tm_dp = tm_s + 64;
+          const uint32_t yq = q * (16384 >> 4);
+          const uint32_t acc0 = q ? 1u : 0u;
 #pragma unroll
-        for (int k8 = 0; k8 < 8; ++k8) {
-          if (MODE == 1)  // dV += P^T dO
-            umma_tf32_ts_p(tm_acc2, tm_s + k8 * 8, y2 + yq + ((k8 * 1024) >> 4), hi, idesc_acc, k8 ? 1u : acc0, leader);
-          // dQ += dS K   |   dK += dS^T Q
-          umma_tf32_ts_p(tm_acc1, tm_dp + k8 * 8, y1 + yq + ((k8 * 1024) >> 4), hi, idesc_acc, k8 ? 1u : acc0, leader);
+          for (int k8 = 0; k8 < 8; ++k8) {
+            if (MODE == 1)  // dV += P^T dO
+              umma_tf32_ts_p(tm_acc2, tm_s + k8 * 8, y2 + yq + ((k8 * 1024) >> 4), hi, idesc_acc, k8 ? 1u : acc0, leader);
+            // dQ += dS K   |   dK += dS^T Q
+            umma_tf32_ts_p(tm_acc1, tm_dp + k8 * 8, y1 + yq + ((k8 * 1024) >> 4), hi, idesc_acc, k8 ? 1u : acc0, leader);
+          }
+          umma_commit_p(&bar_free[slot], leader);
+          if (t == tiles - 1) umma_commit_p(&bar_yfree[q], leader);  // the item's last reader of this column quarter
+          if (q == nq - 1) umma_commit_p(bar_acc, leader);
+          ATTN_TRACE(4 + 4 * i);
+          __syncwarp();
         }
-        umma_commit_p(&bar_free[slot], leader);
-        if (q == nq - 1) umma_commit_p(bar_acc, leader);
       }
-      ATTN_TRACE(4 + 4 * i);
-      __syncwarp();
     }
   } else if (warp >= 4 && warp < 12) {
     // ------------------------------------------------------------ compute warps (thread = row = TMEM lane)
@@ -241,55 +276,65 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvR, const __grid_cons
     const int rt = quad * 32 + lane;  // row inside the tile
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     const float c = p.scale * 1.4426950408889634f;
-    const size_t stat_base = (static_cast<size_t>(s) * p.H + h) * N;
-    if (MODE == 1) {
-      const int i = threadIdx.x - 128;  // 0..255
-      sL[i] = i < N ? p.lse[stat_base + i] : 0.f;
-      sD[i] = i < N ? p.delta[stat_base + i] : 0.f;
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // compute warps only
-    }
-    for (int t = 0; t < tiles; ++t) {
-      const int row = t * 128 + rt;
-      float Lr = 0.f, dr = 0.f;
-      if (MODE == 0 && row < N) {
-        Lr = p.lse[stat_base + row];
-        dr = p.delta[stat_base + row];
+    uint32_t gi = 0;
+    int iter = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++iter) {
+      const int s = item / H, h = item - s * H;
+      const int len = item_len(s), nq = item_nq(len);
+      const bool tracing = p.trace != nullptr && blockIdx.x == 0 && iter == p.trace_seq;
+      const size_t stat_base = (static_cast<size_t>(s) * H + h) * N;
+      if (MODE == 1) {
+        const int i = threadIdx.x - 128;  // 0..255
+        const float lv = i < N ? p.lse[stat_base + i] : 0.f, dv0 = i < N ? p.delta[stat_base + i] : 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // every compute warp is done with the previous item's stats
+        sL[i] = lv;
+        sD[i] = dv0;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      const bool row_ok = (MODE == 0) ? (row < N) : (row < len);
-      for (int q = 0; q < nq; ++q) {
-        const int i = t * nq + q, slot = i % kSlots, u = i / kSlots;
-        mbar_wait(&bar_full[slot], u & 1);
-        tc_fence_after();
-        if (cw == 0) ATTN_TRACE(40 + 2 * i);
-        const uint32_t tm_s = tmem_base + 128 + slot * 128 + lane_addr + half * 32, tm_dp = tm_s + 64;
-        uint32_t sv[32], dv[32];
-        tmem_ld_32x32(tm_s, sv);
-        tmem_ld_32x32(tm_dp, dv);
-        tmem_ld_wait();
-        const int col0 = q * 64 + half * 32;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = col0 + j;
-          float Lc, dc;
-          bool ok;
-          if (MODE == 0) {
-            Lc = Lr; dc = dr;
-            ok = row_ok && col < len;
-          } else {
-            Lc = sL[col]; dc = sD[col];  // warp-uniform address: shared-memory broadcast
-            ok = row_ok && col < N;
-          }
-          const float pv = ok ? ex2_approx(fmaf(__uint_as_float(sv[j]), c, -Lc)) : 0.f;
-          const float ds = pv * (__uint_as_float(dv[j]) - dc);
-          if (MODE == 1) sv[j] = __float_as_uint(round_tf32(pv));
-          dv[j] = __float_as_uint(round_tf32(ds));
+      for (int t = 0; t < tiles; ++t) {
+        const int row = t * 128 + rt;
+        float Lr = 0.f, dr = 0.f;
+        if (MODE == 0 && row < N) {
+          Lr = p.lse[stat_base + row];
+          dr = p.delta[stat_base + row];
         }
-        if (MODE == 1) tmem_st_32x32(tm_s, sv);
-        tmem_st_32x32(tm_dp, dv);
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&bar_ds[slot]);
-        if (cw == 0) ATTN_TRACE(41 + 2 * i);
+        const bool row_ok = (MODE == 0) ? (row < N) : (row < len);
+        for (int q = 0; q < nq; ++q, ++gi) {
+          const int i = t * nq + q;
+          const uint32_t slot = gi % kSlots, u = gi / kSlots;
+          mbar_wait(&bar_full[slot], u & 1);
+          tc_fence_after();
+          if (cw == 0) ATTN_TRACE(40 + 2 * i);
+          const uint32_t tm_s = tmem_base + 128 + slot * 128 + lane_addr + half * 32, tm_dp = tm_s + 64;
+          uint32_t sv[32], dv[32];
+          tmem_ld_32x32(tm_s, sv);
+          tmem_ld_32x32(tm_dp, dv);
+          tmem_ld_wait();
+          const int col0 = q * 64 + half * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = col0 + j;
+            float Lc, dc;
+            bool ok;
+            if (MODE == 0) {
+              Lc = Lr; dc = dr;
+              ok = row_ok && col < len;
+            } else {
+              Lc = sL[col]; dc = sD[col];  // warp-uniform address: shared-memory broadcast
+              ok = row_ok && col < N;
+            }
+            const float pv = ok ? ex2_approx(fmaf(__uint_as_float(sv[j]), c, -Lc)) : 0.f;
+            const float ds = pv * (__uint_as_float(dv[j]) - dc);
+            if (MODE == 1) sv[j] = __float_as_uint(round_tf32(pv));
+            dv[j] = __float_as_uint(round_tf32(ds));
+          }
+          if (MODE == 1) tmem_st_32x32(tm_s, sv);
+          tmem_st_32x32(tm_dp, dv);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&bar_ds[slot]);
+          if (cw == 0) ATTN_TRACE(41 + 2 * i);
+        }
       }
     }
   } else if (warp >= 12) {
@@ -315,35 +360,42 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvR, const __grid_cons
       }
     };
     bool pending = false;  // a bulk store may still be reading the staging tile
-    for (int t = 0; t < tiles; ++t) {
-      mbar_wait(bar_acc, t & 1);
-      tc_fence_after();
-      if (warp == 12) ATTN_TRACE(60 + 2 * t);
-      for (int r = 0; r < (MODE == 1 ? 2 : 1); ++r) {
-        uint32_t a0[32], a1[32];
-        const uint32_t tm_acc = (r == 0 ? tm_acc1 : tm_acc2) + lane_addr;
-        tmem_ld_32x32(tm_acc, a0);
-        tmem_ld_32x32(tm_acc + 32, a1);
-        tmem_ld_wait();
-        if (r == (MODE == 1 ? 1 : 0)) {
-          tc_fence_before();
-          mbar_arrive(bar_accfree);  // the next tile's second-stage MMAs may overwrite the accumulators
-        }
-        if (pending) {
-          if (leader) tma_store_wait_read();
+    uint32_t gt = 0;
+    int iter = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++iter) {
+      const int s = item / H, h = item - s * H;
+      const int cq = (h * 64) >> 5, ck = cq + (D >> 5), cv = cq + (D >> 4);
+      const bool tracing = p.trace != nullptr && blockIdx.x == 0 && iter == p.trace_seq;
+      for (int t = 0; t < tiles; ++t, ++gt) {
+        mbar_wait(bar_acc, gt & 1);
+        tc_fence_after();
+        if (warp == 12) ATTN_TRACE(60 + 2 * t);
+        for (int r = 0; r < (MODE == 1 ? 2 : 1); ++r) {
+          uint32_t a0[32], a1[32];
+          const uint32_t tm_acc = (r == 0 ? tm_acc1 : tm_acc2) + lane_addr;
+          tmem_ld_32x32(tm_acc, a0);
+          tmem_ld_32x32(tm_acc + 32, a1);
+          tmem_ld_wait();
+          if (r == (MODE == 1 ? 1 : 0)) {
+            tc_fence_before();
+            mbar_arrive(bar_accfree);  // the next tile's second-stage MMAs may overwrite the accumulators
+          }
+          if (pending) {
+            if (leader) tma_store_wait_read();
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+          }
+          stage_row(a0, a1, r == 0 ? p.scale : 1.0f);  // dQ | dK, then dV
+          fence_proxy_async_smem();
           asm volatile("bar.sync 2, 128;" ::: "memory");
+          if (leader) {
+            const int chunk = (MODE == 0) ? cq : (r == 0 ? ck : cv);
+            tma_store_4d(&tmOut, smem + kStage, 0, t * 128, chunk, s);
+            tma_store_commit();
+          }
+          pending = true;
         }
-        stage_row(a0, a1, r == 0 ? p.scale : 1.0f);  // dQ | dK, then dV
-        fence_proxy_async_smem();
-        asm volatile("bar.sync 2, 128;" ::: "memory");
-        if (leader) {
-          const int chunk = (MODE == 0) ? cq : (r == 0 ? ck : cv);
-          tma_store_4d(&tmOut, smem + kStage, 0, t * 128, chunk, s);
-          tma_store_commit();
-        }
-        pending = true;
+        if (warp == 12) ATTN_TRACE(61 + 2 * t);
       }
-      if (warp == 12) ATTN_TRACE(61 + 2 * t);
     }
     if (leader) tma_store_wait_read();
   }
@@ -395,9 +447,9 @@ int attention_backward_tc(const float* qkv, const float* o, const float* d_o, co
   }
   BwdTcParams p{};
   p.dqkv = dqkv; p.lse = lse; p.delta = delta_ws; p.lengths = lengths; p.N = N; p.H = H; p.D = D; p.scale = 0.125f;
-  dim3 grid(H, S);
-  p.prefetch_dist = attention_l2_prefetch_enabled() ? gemm_num_sms() : 0;
+  p.prefetch_dist = attention_l2_prefetch_enabled();  // L2 prefetch of the CTA's next loads
   p.num_items = S * H;
+  const int grid = p.num_items < gemm_num_sms() ? p.num_items : gemm_num_sms();  // persistent: one CTA per SM
   p.trace_seq = g_trace_seq;
   p.trace = g_trace_mode == 0 ? g_trace : nullptr;
   attn_bwd_tc_kernel<0><<<grid, 512, kSmemBwd, stream>>>(tqr, tqy, tdr, tdy, tout, p);

@@ -270,7 +270,7 @@ def sec_attn_trace():
     ops.attention_bwd(qkv, o, d_o, lse, S, N, H, dqkv=dqkv)
     for mode in (0, 1):
         buf = torch.zeros(80, dtype=torch.int64, device="cuda")
-        L.atst_attention_trace(ptr(buf), S // 2, mode)
+        L.atst_attention_trace(ptr(buf), 20, mode)  # the CTA's 21st item (steady state)
         ops.attention_bwd(qkv, o, d_o, lse, S, N, H, dqkv=dqkv)
         torch.cuda.synchronize()
         L.atst_attention_trace(None, 0, 0)
