@@ -101,6 +101,8 @@ def test_gemm_wgrad_dgrad(T, M, N):
     (2, 128, 1, [128, 127]),        # exactly one tile
     (2, 129, 3, [129, 128]),        # one row into the second tile
     (1, 256, 2, None),              # the largest supported sequence
+    (40, 251, 12, "ragged"),        # 480 (sequence, head) items > SM count: every persistent CTA walks several items
+    (70, 100, 6, "ragged"),         # with a different number of key quarters each (the barrier parities must track)
 ])
 def test_attention_matches_reference_formula(tc, S, N, H, lens):
     from audiossl_b200 import _lib, ops
@@ -108,6 +110,9 @@ def test_attention_matches_reference_formula(tc, S, N, H, lens):
     torch.manual_seed(0)
     D = H * 64
     qkv = ops.round_tf32(torch.randn(S * N, 3 * D, device="cuda"))
+    if lens == "ragged":
+        lens = torch.randint(1, N + 1, (S,), generator=torch.Generator().manual_seed(S)).tolist()
+        lens[0], lens[1] = N, 1
     lengths = None if lens is None else torch.tensor(lens, dtype=torch.int32, device="cuda")
     q = qkv.clone().requires_grad_(True)
     t = q.reshape(S, N, 3, H, 64).permute(2, 0, 3, 1, 4)
