@@ -13,11 +13,26 @@ EPI_STORE, EPI_GELU, EPI_DGELU, EPI_RESID, EPI_SCALE, EPI_RELU = 0, 1, 2, 3, 4, 
 # launch accounting for bench.py: kernels launched through the C ABI, algorithmic GEMM flops, and (optionally)
 # a CUDA-event pair around every GEMM launch to measure the dominant kernel in place
 STATS = {"launches": 0, "gemm_flops": 0.0, "gemm_bytes": 0.0, "gemm_launches": 0, "time_gemms": False,
-         "gemm_events": []}
+         "gemm_events": [], "attn_events": []}
 
 
 def reset_stats():
-    STATS.update(launches=0, gemm_flops=0.0, gemm_bytes=0.0, gemm_launches=0, gemm_events=[])
+    STATS.update(launches=0, gemm_flops=0.0, gemm_bytes=0.0, gemm_launches=0, gemm_events=[], attn_events=[])
+
+
+class _AttnTimer:
+    """CUDA-event pair around an attention call when bench.py measures kernels in place (algorithmic bytes)."""
+
+    def __init__(self, nbytes, tag):
+        self.ev = None
+        if STATS["time_gemms"]:
+            self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), nbytes, tag)
+            self.ev[0].record()
+
+    def done(self):
+        if self.ev is not None:
+            self.ev[1].record()
+            STATS["attn_events"].append(self.ev)
 
 
 class _GemmTimer:
@@ -150,8 +165,10 @@ def attention_fwd(qkv, S, N, H, lengths=None, out=None, lse=None):
         out = torch.empty((S * N, D), device=qkv.device, dtype=torch.float32)
     if lse is None:
         lse = torch.empty((S, H, N), device=qkv.device, dtype=torch.float32)
+    _t = _AttnTimer(4.0 * S * N * 4 * D, "fwd")  # qkv read once, o written once
     check(_lib.lib().atst_attention_forward(ptr(qkv), ptr(out), ptr(lse), ptr(lengths), S, N, H, _lib.stream()),
           "atst_attention_forward")
+    _t.done()
     _count(1)
     return out, lse
 
@@ -161,8 +178,11 @@ def attention_bwd(qkv, o, d_o, lse, S, N, H, lengths=None, dqkv=None, delta_ws=N
         dqkv = torch.empty_like(qkv)
     if delta_ws is None:
         delta_ws = torch.empty((S, H, N), device=qkv.device, dtype=torch.float32)
+    D = H * 64
+    _t = _AttnTimer(4.0 * S * N * 8 * D, "bwd")  # qkv, o, dO read once, dqkv written once
     check(_lib.lib().atst_attention_backward(ptr(qkv), ptr(o), ptr(d_o), ptr(lse), ptr(delta_ws), ptr(dqkv),
                                              ptr(lengths), S, N, H, _lib.stream()), "atst_attention_backward")
+    _t.done()
     _count(3)
     return dqkv
 

@@ -359,6 +359,12 @@ def run_ours(args):
                 fh.write("%-28s n=%3d  %8.3f ms  %7.1f TFLOP/s\n" % (tag, cnt, t_ms, fl / t_ms / 1e9))
 
     mel_ms = sum(a.elapsed_time(b2) for a, b2 in mel_events)
+    attn = {}
+    for a_, b_, nb_, tag_ in ops.STATS["attn_events"]:
+        d_ = attn.setdefault(tag_, [0, 0.0, 0.0])
+        d_[0] += 1
+        d_[1] += a_.elapsed_time(b_)
+        d_[2] += nb_
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -387,7 +393,7 @@ def run_ours(args):
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_val, "unit": "clips/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
-        "roofline": {"bound": "tensor", "kernel": "gemm_tf32_kernel (tcgen05 kind::tf32)", "achieved": achieved,
+        "roofline": {"bound": "tensor", "kernel": "gemm2_tf32_kernel (CTA pair, tcgen05 kind::tf32)", "achieved": achieved,
                      "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": traffic,
                      "algorithmic_bytes_per_launch": gemm_bytes_launch,
                      "peak_source": pk["src"] + " bf16 cuBLAS sustained; TF32 tensor rate is half of bf16",
@@ -395,6 +401,15 @@ def run_ours(args):
                      "gemm_share_of_step": gemm_ms / ms_step,
                      "algorithmic_gemm_tflop_per_step": gemm_flops_step / 1e12,
                      "model_flops_utilisation_of_step": step_gflop * 1e9 * B / (ms_step / 1e3) / 1e12 / pk["tflops"]},
+        "roofline_attention": {
+            "bound": "hbm", "kernel": "attn_fwd_tc_kernel / attn_bwd_tc_kernel<0,1> + attn_delta_kernel (tcgen05)",
+            "unit": "GB/s", "peak": pk["hbm_gbs"],
+            "note": "algorithmic bytes (qkv, o, dO read once; o / dqkv written once) over the in-place duration; "
+                    "the TMEM read port (64 B/clk/SM) is the co-limiter, DESIGN.md 5.2",
+            **{k_: {"launches_per_step": v_[0], "ms_per_step": v_[1],
+                    "achieved": v_[2] / (v_[1] / 1e3) / 1e9 if v_[1] > 0 else 0.0,
+                    "frac": (v_[2] / (v_[1] / 1e3) / 1e9 / pk["hbm_gbs"]) if v_[1] > 0 else 0.0}
+               for k_, v_ in attn.items()}},
         "roofline_mel": {"bound": "hbm", "kernel": "mel_db_kernel + mel_norm_kernel (fused STFT/mel/dB/MinMax)",
                          "achieved": mel_bytes / (mel_ms / 1e3) / 1e9 if mel_ms > 0 else 0.0, "peak": pk["hbm_gbs"],
                          "unit": "GB/s", "frac": (mel_bytes / (mel_ms / 1e3) / 1e9 / pk["hbm_gbs"]) if mel_ms > 0 else 0.0,
