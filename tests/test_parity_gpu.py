@@ -350,6 +350,66 @@ def test_three_training_steps_follow_the_oracle():
     assert rel(ws_, ref.student.encoder.blocks[3].mlp.fc1.weight.detach()) < 5e-2
 
 
+TWO_RANK_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from tests import util
+from audiossl_b200.models.atst import ATST
+rank = int(os.environ["RANK"])
+torch.cuda.set_device(0)
+c = util.CASES["tiny2b32"]
+def run(lo, hi):
+    m = ATST(arch=dict(embed_dim=c["dim"], depth=c["depth"], num_heads=c["heads"]), ncrops=c["ncrops"], drop_path_rate=0.0)
+    util.load_det(m)
+    m.cuda().train()
+    crops, lengths = util.make_inputs("tiny2b32", c["B"], c["widths"], c["lens"])
+    crops = [x[lo:hi].contiguous().cuda() for x in crops]
+    lengths = [x[lo:hi].contiguous().cuda() for x in lengths]
+    loss, std_s, std_t = m(crops, lengths)
+    loss.backward()
+    torch.cuda.synchronize()
+    g = {k: p.grad.detach().float().cpu().clone() for k, p in m.student.named_parameters() if p.grad is not None}
+    bn = m.student.projector[1].running_mean.detach().cpu().clone()
+    return loss.item(), std_s.item(), g, bn
+ref_loss, ref_std, ref_g, ref_bn = run(0, c["B"])            # one rank, whole batch (no process group yet)
+dist.init_process_group("gloo")
+half = c["B"] // 2
+loss, std, g, bn = run(rank * half, (rank + 1) * half)       # two ranks, half the clips each
+lt = torch.tensor([loss]); dist.all_reduce(lt); mean_loss = lt.item() / 2
+assert abs(mean_loss - ref_loss) < 1e-3 * abs(ref_loss), (mean_loss, ref_loss)
+assert abs(std - ref_std) < 1e-3 * abs(ref_std), (std, ref_std)   # compute_var statistics are global
+assert torch.allclose(bn, ref_bn, rtol=1e-3, atol=1e-5)            # SyncBatchNorm running statistics
+worst = 0.0
+gmax = max(v.norm() for v in ref_g.values())
+for k, rg in ref_g.items():
+    e = ((g[k] - rg).norm() / rg.norm().clamp_min(1e-30)).item()
+    if os.environ.get("ATST_TEST_VERBOSE") and rank == 0:
+        print("%%-50s |g| %%.3e rel %%.3e" %% (k, rg.norm().item(), e))
+    if rg.norm() < 1e-4 * gmax:
+        continue
+    worst = max(worst, e)
+assert worst < 5e-2, worst   # TF32 re-rounding between the two tilings of the same sums
+print("rank", rank, "ok", mean_loss, ref_loss, worst)
+'''
+
+
+def test_two_rank_step_equals_one_rank_on_the_concatenated_batch(tmp_path):
+    """SURVEY 8(e): G ranks on B/G clips each == 1 rank on B clips (SyncBatchNorm statistics, global compute_var,
+    averaged gradients).  Two processes share cuda:0 over a gloo group (NCCL refuses two ranks on one device)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "w2.py"
+    script.write_text(TWO_RANK_WORKER % root)
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29673", str(script)],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("ok") == 2
+
+
 def test_too_long_clip_is_rejected():
     from audiossl_b200.models.atst import ATST
     m = ATST(arch=dict(embed_dim=128, depth=1, num_heads=2)).cuda()
