@@ -42,7 +42,7 @@ __device__ __forceinline__ float gelu_grad(float u) {
 
 
 // Thread `lane` of an epilogue warp of TMEM lane quadrant `ew` owns accumulator row 32*ew + lane and walks the
-// 8-column groups [g0, g1) of the tile (g1 - g0 even; one warp per quadrant: the whole tile, two warps: half each).
+// 8-column groups [g0, g1) of the tile (g1 - g0 a multiple of 4; one warp per quadrant: the whole tile, two warps: half each).
 // The loop is deliberately NOT unrolled over the tile: one compact body (TMEM load of the next group and its side
 // input in flight while the current group is computed and stored) instead of a copy of every epilogue variant per
 // column chunk - the unrolled form thrashed the instruction cache (ncu: 23 % of the stall samples were "no
@@ -74,9 +74,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
   tc_fence_after();
   taddr += static_cast<uint32_t>(ew * 32) << 16;
 
-  auto fetch = [&](int g, uint32_t (&r)[8], float (&sd)[8]) {
-    tmem_ld_32x8(taddr + g * 8, r);
-    if (side_row != nullptr && g * 8 < ncols) ld_global_v8(side_row + g * 8, sd);
+  auto fetch_acc = [&](int g, uint32_t (&r)[8]) { tmem_ld_32x8(taddr + g * 8, r); };
+  auto fetch_side = [&](int g, float (&sd)[8]) {
+    if (side_row != nullptr && g < g1 && g * 8 < ncols) ld_global_v8(side_row + g * 8, sd);
   };
   auto finish = [&](int g, const uint32_t (&r)[8], const float (&sd)[8]) {
     if (!row_ok || g * 8 >= ncols) return;
@@ -126,23 +126,38 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
       st_global_v8(cp, v);
     }
   };
+  // accumulator groups are fetched one ahead (tcgen05.wait::ld waits for every outstanding load, so deeper does not
+  // help), side inputs three ahead (their L2 / HBM latency is several groups long); (g1 - g0) % 4 == 0
   uint32_t ra[8], rb[8];
-  float sa[8], sb[8];
-  fetch(g0, ra, sa);
+  float sd[4][8];
+  fetch_side(g0, sd[0]);
+  fetch_side(g0 + 1, sd[1]);
+  fetch_side(g0 + 2, sd[2]);
+  fetch_acc(g0, ra);
 #pragma unroll 1
-  for (int g = g0; g < g1; g += 2) {
+  for (int g = g0; g < g1; g += 4) {
     tmem_ld_wait();
-    fetch(g + 1, rb, sb);
-    finish(g, ra, sa);
+    fetch_acc(g + 1, rb);
+    fetch_side(g + 3, sd[3]);
+    finish(g, ra, sd[0]);
     tmem_ld_wait();
-    if (g + 2 < g1) {
-      fetch(g + 2, ra, sa);
+    fetch_acc(g + 2, ra);
+    fetch_side(g + 4, sd[0]);
+    finish(g + 1, rb, sd[1]);
+    tmem_ld_wait();
+    fetch_acc(g + 3, rb);
+    fetch_side(g + 5, sd[1]);
+    finish(g + 2, ra, sd[2]);
+    tmem_ld_wait();
+    if (g + 4 < g1) {
+      fetch_acc(g + 4, ra);
+      fetch_side(g + 6, sd[2]);
     } else {  // this warp's last TMEM load of the tile has completed
       tc_fence_before();
       __syncwarp();
       release();
     }
-    finish(g + 1, rb, sb);
+    finish(g + 3, rb, sd[3]);
   }
 }
 
