@@ -63,10 +63,12 @@ int atst_gemm_nt(const float* A, int lda, const float* B, int ldb, float* C, int
 }
 
 int atst_gemm_nn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K, int epi,
-                 float* aux, int ldaux, const float* rowscale, int rows_per_seq, int round_out, void* stream) {
+                 float* aux, int ldaux, const float* rowscale, int rows_per_seq, int round_out, float* colsum_out,
+                 void* stream) {
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.epi = epi; p.aux = aux; p.ldaux = ldaux;
   p.rowscale = rowscale; p.rows_per_seq = rows_per_seq > 0 ? rows_per_seq : 1; p.round_out = round_out;
+  p.colsum = colsum_out;
   ATST_REQUIRE(epi == EPI_STORE || epi == EPI_DGELU || epi == EPI_SCALE, "atst_gemm_nn: bad epilogue %d", epi);
   ATST_REQUIRE(!(epi == EPI_DGELU && aux == nullptr), "atst_gemm_nn: EPI_DGELU needs aux");
   return gemm_nn(A, lda, B, ldb, p, ST(stream));

@@ -30,6 +30,7 @@ struct GemmParams {
   int rows_per_seq = 1;
   int epi = EPI_STORE;
   int round_out = 0;                // round C to tf32 (it feeds another GEMM)
+  float* colsum = nullptr;          // [N] or null: colsum[n] += sum over rows of the stored C[:, n] (a bias gradient)
   int splits = 0;                   // TN only: split-K factor (0 = auto)
   int l2_prefetch = 1;              // producer prefetches streaming operand tiles into L2 ahead of the smem ring
   // TN (token-major operands) shared-memory descriptor fields; 0 = defaults

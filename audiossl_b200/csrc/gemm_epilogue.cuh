@@ -78,8 +78,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
   auto fetch_side = [&](int g, float (&sd)[8]) {
     if (side_row != nullptr && g < g1 && g * 8 < ncols) ld_global_v8(side_row + g * 8, sd);
   };
+  const bool do_colsum = p.colsum != nullptr;  // warp-uniform
   auto finish = [&](int g, const uint32_t (&r)[8], const float (&sd)[8]) {
-    if (!row_ok || g * 8 >= ncols) return;
+    if (g * 8 >= ncols || (!row_ok && !do_colsum)) return;
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[e]);
@@ -119,11 +120,24 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
       for (int e = 0; e < 8; ++e) v[e] = round_tf32(v[e]);
     }
     float* cp = c_row + g * 8;
-    if (p.epi == EPI_ATOMIC) {
-      red_add_v4(cp, v[0], v[1], v[2], v[3]);
-      red_add_v4(cp + 4, v[4], v[5], v[6], v[7]);
-    } else {
-      st_global_v8(cp, v);
+    if (row_ok) {
+      if (p.epi == EPI_ATOMIC) {
+        red_add_v4(cp, v[0], v[1], v[2], v[3]);
+        red_add_v4(cp + 4, v[4], v[5], v[6], v[7]);
+      } else {
+        st_global_v8(cp, v);
+      }
+    }
+    if (do_colsum) {
+      // column sums of the stored values over this warp's 32 rows (the consumer Linear's bias gradient): a
+      // butterfly per column, then one red.global.add per column from eight different lanes
+      float mine = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float s = warp_sum(row_ok ? v[e] : 0.f);
+        if (lane == e) mine = s;
+      }
+      if (lane < 8) atomicAdd(p.colsum + n0 + g * 8 + lane, mine);
     }
   };
   // accumulator groups are fetched one ahead (tcgen05.wait::ld waits for every outstanding load, so deeper does not

@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "gemm.h"
 #include "gemm_epilogue.cuh"
+#include "ops.h"
 
 namespace atst {
 
@@ -520,12 +521,16 @@ int gemm_nn(const float* A, int lda, const float* B, int ldb, GemmParams p, cuda
   const bool wide = (p.N % 256 == 0) || p.N > 1024;
   p.splits = 1;
   if (wide && g_cta_pair) return gemm2_launch(0, 1, A, lda, p.M, p.K, B, ldb, p.K, p.N, p, stream);
+  float* colsum = p.colsum;  // only the pair kernel's epilogue takes the column sums: separate pass here
+  p.colsum = nullptr;
   CUtensorMap ta, tb;
   int rc = make_map_kmajor(&ta, A, p.M, p.K, lda, kBlockM);
   if (rc) return rc;
   rc = make_map_mnmajor(&tb, B, p.K, p.N, ldb, wide ? 256 : 128, p.mn_tma_swizzle);
   if (rc) return rc;
-  return wide ? launch<256, false, true>(ta, tb, p, stream) : launch<128, false, true>(ta, tb, p, stream);
+  rc = wide ? launch<256, false, true>(ta, tb, p, stream) : launch<128, false, true>(ta, tb, p, stream);
+  if (rc == ATST_OK && colsum != nullptr) rc = colsum_accumulate(p.C, p.ldc, p.M, p.N, colsum, stream);
+  return rc;
 }
 
 int gemm_tn(const float* A, int lda, const float* B, int ldb, int T, GemmParams p, cudaStream_t stream) {

@@ -19,9 +19,11 @@ from . import ops
 # GELU / GELU' inside the GEMM epilogue or as separate elementwise passes; see DESIGN.md "GEMM epilogues".
 #   ATST_FUSE_GELU bit 0: forward passes that keep no activations (teacher, inference) fuse GELU into fc1 and never
 #                         store the pre-activation; bit 1: the student forward fuses it too (epilogue writes u and g);
-#                  bit 2: the backward fuses GELU' into the fc2 dgrad epilogue
+#                  bit 2: the backward fuses GELU' into the fc2 dgrad epilogue; bit 3: that epilogue also takes the
+#                         fc1 bias gradient (column sums) instead of a separate pass over du - measured slower
+#                         (the butterflies + red.global.add cost the dgrad GEMM ~0.9 ms to save a 0.27 ms pass): off
 _FG = int(os.environ.get("ATST_FUSE_GELU", "7"))
-FUSE_GELU_NOSAVE, FUSE_GELU, FUSE_DGELU = bool(_FG & 1), bool(_FG & 2), bool(_FG & 4)
+FUSE_GELU_NOSAVE, FUSE_GELU, FUSE_DGELU, FUSE_COLSUM = bool(_FG & 1), bool(_FG & 2), bool(_FG & 4), bool(_FG & 8)
 
 
 class Workspace:
@@ -198,8 +200,9 @@ class EncoderEngine:
             ops.gemm_tn_acc(dys, L["g"], fp.g(b + "mlp.fc2.weight"))
             if FUSE_DGELU:
                 du = ops.gemm_nn(dys, fp.c(b + "mlp.fc2.weight"), epi=ops.EPI_DGELU, aux=L["u"], round_out=True,
-                                 out=t("du", (M, 4 * D)))
-                ops.colsum_acc(du, fp.g(b + "mlp.fc1.bias"))
+                                 out=t("du", (M, 4 * D)), colsum_out=fp.g(b + "mlp.fc1.bias") if FUSE_COLSUM else None)
+                if not FUSE_COLSUM:
+                    ops.colsum_acc(du, fp.g(b + "mlp.fc1.bias"))
             else:
                 du = ops.gemm_nn(dys, fp.c(b + "mlp.fc2.weight"), out=t("du", (M, 4 * D)))
                 ops.gelu_bwd_(du, L["u"], colsum_out=fp.g(b + "mlp.fc1.bias"))

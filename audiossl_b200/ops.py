@@ -98,8 +98,9 @@ def gemm_nt(A, B, bias=None, epi=EPI_STORE, resid=None, aux=None, rowscale=None,
     return out
 
 
-def gemm_nn(A, W, epi=EPI_STORE, aux=None, rowscale=None, rows_per_seq=1, round_out=False, out=None):
-    """out[M,N] = epi(A[M,K] @ W[K,N])  (dgrad against a Linear weight W[out=K, in=N])."""
+def gemm_nn(A, W, epi=EPI_STORE, aux=None, rowscale=None, rows_per_seq=1, round_out=False, out=None, colsum_out=None):
+    """out[M,N] = epi(A[M,K] @ W[K,N])  (dgrad against a Linear weight W[out=K, in=N]).
+    colsum_out [N] (optional) += column sums of out, taken in the GEMM epilogue."""
     M, K = A.shape
     N = W.shape[1]
     assert W.shape[0] == K
@@ -108,7 +109,7 @@ def gemm_nn(A, W, epi=EPI_STORE, aux=None, rowscale=None, rows_per_seq=1, round_
     _t = _GemmTimer(2.0 * M * N * K, "nn %dx%dx%d e%d" % (M, N, K, epi), 4.0 * (M * K + N * K + M * N * (1 + (aux is not None))))
     check(_lib.lib().atst_gemm_nn(ptr(A), A.stride(0), ptr(W), W.stride(0), ptr(out), out.stride(0), M, N, K, epi,
                                   ptr(aux), aux.stride(0) if aux is not None else 0, ptr(rowscale), rows_per_seq,
-                                  1 if round_out else 0, _lib.stream()), "atst_gemm_nn")
+                                  1 if round_out else 0, ptr(colsum_out), _lib.stream()), "atst_gemm_nn")
     _t.done()
     return out
 

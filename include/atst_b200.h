@@ -45,9 +45,12 @@ int atst_mel_forward(const float* wav, int B, int n, long long wav_stride, int w
 int atst_gemm_nt(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K,
                  const float* bias, int epi, const float* resid, int ldr, float* aux, int ldaux,
                  const float* rowscale, int rows_per_seq, int round_out, void* stream);
-/* C[M,N] = epi(A[M,K] . B[K,N]) : input-gradient of a Linear whose weight is B = W[out=K, in=N] */
+/* C[M,N] = epi(A[M,K] . B[K,N]) : input-gradient of a Linear whose weight is B = W[out=K, in=N].
+ * colsum_out (nullable, [N]) += column sums of the stored C: the bias gradient of the Linear that produced the
+ * forward input of this one (fc1.bias from the GELU' epilogue), taken inside the epilogue. */
 int atst_gemm_nn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K, int epi,
-                 float* aux, int ldaux, const float* rowscale, int rows_per_seq, int round_out, void* stream);
+                 float* aux, int ldaux, const float* rowscale, int rows_per_seq, int round_out, float* colsum_out,
+                 void* stream);
 /* C[M,N] += A[T,M]^T . B[T,N] : weight-gradient (split over T, atomically accumulated into C) */
 int atst_gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int T,
                  void* stream);

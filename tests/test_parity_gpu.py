@@ -175,7 +175,7 @@ def test_gelu_passes_match_torch():
     assert (g - gref).abs().max().item() < 5e-3  # tf32 rounding of outputs up to |u| ~ 8 (8 * 2^-11)
 
 
-@pytest.mark.parametrize("M,N,K", [(300, 512, 128), (1000, 1024, 256), (515, 256, 64)])
+@pytest.mark.parametrize("M,N,K", [(300, 512, 128), (1000, 1024, 256), (515, 256, 64), (200, 384, 128)])
 def test_gelu_fused_epilogues_match_torch(M, N, K):
     """fc1 with the GELU epilogue (with and without the stored pre-activation) and the fc2 dgrad with the GELU'
     epilogue against torch; the CTA-pair kernel serves N % 256 == 0."""
@@ -197,8 +197,10 @@ def test_gelu_fused_epilogues_match_torch(M, N, K):
     W2 = ops.round_tf32(torch.randn(K2, N, device="cuda") * 0.1)
     ur = u_ref.clone().requires_grad_(True)
     torch.nn.functional.gelu(ur).backward(dy @ W2)
-    du = ops.gemm_nn(dy, W2, epi=ops.EPI_DGELU, aux=u_ref.contiguous(), round_out=True)
+    cs = torch.ones(N, device="cuda")
+    du = ops.gemm_nn(dy, W2, epi=ops.EPI_DGELU, aux=u_ref.contiguous(), round_out=True, colsum_out=cs)
     assert rel(du, ur.grad) < 1e-3
+    assert rel(cs, 1.0 + du.double().sum(0)) < 1e-5  # column sums of the stored values, accumulated
 
 
 @pytest.mark.parametrize("rows,cols", [(1000, 3072), (77, 130), (129, 4), (5000, 768)])
