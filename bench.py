@@ -195,6 +195,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL's own log lines (version banner, NCCL_DEBUG=INFO output) go to stderr: stdout carries the JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     cfg = CONFIGS[args.config]
     B = args.batch if args.batch > 0 else cfg["batch"]
