@@ -195,9 +195,20 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL's own log lines (version banner, NCCL_DEBUG=INFO output) go to stderr: stdout carries the JSON line only
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries the JSON line only: NCCL prints its version banner (and any NCCL_DEBUG output) to fd 1 when the
+        # communicator is created, so create it with fd 1 pointed at stderr
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     cfg = CONFIGS[args.config]
     B = args.batch if args.batch > 0 else cfg["batch"]
     arch = args.arch or cfg["arch"]
