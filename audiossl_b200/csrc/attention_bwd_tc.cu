@@ -312,21 +312,23 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvR, const __grid_cons
           tmem_ld_wait();
           const int col0 = q * 64 + half * 32;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = col0 + j;
-            float Lc, dc;
-            bool ok;
-            if (MODE == 0) {
-              Lc = Lr; dc = dr;
-              ok = row_ok && col < len;
-            } else {
-              Lc = sL[col]; dc = sD[col];  // warp-uniform address: shared-memory broadcast
-              ok = row_ok && col < N;
+          for (int j4 = 0; j4 < 8; ++j4) {
+            // MODE 1: per-column lse / delta, four columns per 128-bit shared-memory broadcast load
+            float4 L4 = make_float4(Lr, Lr, Lr, Lr), d4 = make_float4(dr, dr, dr, dr);
+            if (MODE == 1) {
+              L4 = *reinterpret_cast<const float4*>(sL + col0 + 4 * j4);
+              d4 = *reinterpret_cast<const float4*>(sD + col0 + 4 * j4);
             }
-            const float pv = ok ? ex2_approx(fmaf(__uint_as_float(sv[j]), c, -Lc)) : 0.f;
-            const float ds = pv * (__uint_as_float(dv[j]) - dc);
-            if (MODE == 1) sv[j] = __float_as_uint(round_tf32(pv));
-            dv[j] = __float_as_uint(round_tf32(ds));
+            const float Lc4[4] = {L4.x, L4.y, L4.z, L4.w}, dc4[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+              const int j = 4 * j4 + i4, col = col0 + j;
+              const bool ok = row_ok && col < ((MODE == 0) ? len : N);
+              const float pv = ok ? ex2_approx(fmaf(__uint_as_float(sv[j]), c, -Lc4[i4])) : 0.f;
+              const float ds = pv * (__uint_as_float(dv[j]) - dc4[i4]);
+              if (MODE == 1) sv[j] = __float_as_uint(round_tf32(pv));
+              dv[j] = __float_as_uint(round_tf32(ds));
+            }
           }
           if (MODE == 1) tmem_st_32x32(tm_s, sv);
           tmem_st_32x32(tm_dp, dv);
