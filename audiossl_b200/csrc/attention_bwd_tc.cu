@@ -71,8 +71,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvR, const __grid_cons
   float* sL = reinterpret_cast<float*>(smem + kStat);
   float* sD = sL + 256;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBars);
-  uint64_t* bar_r = bars + 0;
-  uint64_t* bar_rfree = bars + 1;
+  uint64_t* bar_r = bars + 0;      // R1 (first row operand) loaded
+  uint64_t* bar_rfree = bars + 1;  // every S MMA of the tile has read R1
   uint64_t* bar_acc = bars + 2;
   uint64_t* bar_accfree = bars + 3;
   uint64_t* bar_y = bars + 4;       // [4]
@@ -80,7 +80,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvR, const __grid_cons
   uint64_t* bar_ds = bars + 11;     // [3]
   uint64_t* bar_free = bars + 14;   // [3]
   uint64_t* bar_yfree = bars + 17;  // [4]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+  uint64_t* bar_r2 = bars + 21;      // R2 (second row operand) loaded
+  uint64_t* bar_r2free = bars + 22;  // every dP MMA of the tile has read R2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = p.N, D = p.D, H = p.H;
@@ -104,6 +106,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvR, const __grid_cons
   if (warp == 1 && lane == 0) {
     mbar_init(bar_r, 1);
     mbar_init(bar_rfree, 1);
+    mbar_init(bar_r2, 1);
+    mbar_init(bar_r2free, 1);
     mbar_init(bar_acc, 1);
     mbar_init(bar_accfree, 128);
     for (int i = 0; i < 4; ++i) {
@@ -128,21 +132,24 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvR, const __grid_cons
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t gt = 0, ypar = 0, yused = 0;  // row tiles loaded so far; per column quarter: load-count parity / loaded before
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      int iter = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++iter) {
+        const bool tracing = p.trace != nullptr && blockIdx.x == 0 && iter == p.trace_seq;
         const int s = item / H, h = item - s * H;
         const int row0 = s * N, nq = item_nq(item_len(s));
         const int cq = (h * 64) >> 5, ck = cq + (D >> 5), cv = cq + (D >> 4), cdo = cq;
         for (int t = 0; t < tiles; ++t, ++gt) {
-          if (gt > 0) mbar_wait(bar_rfree, (gt - 1) & 1);  // every S / dP MMA of the previous tile has read R1, R2
-          mbar_expect_tx(bar_r, 64 * 1024);
+          // the two row operands are refilled separately: R1 as soon as the previous tile's last S MMAs are done,
+          // R2 after its last dP MMAs (the reload sits on the tile-boundary critical path)
           const int r = row0 + t * 128;
-          if (MODE == 0) {
-            tma_load_3d(smem + kR1, &tmQkvR, bar_r, 0, r, cq);
-            tma_load_3d(smem + kR2, &tmDoR, bar_r, 0, r, cdo);
-          } else {
-            tma_load_3d(smem + kR1, &tmQkvR, bar_r, 0, r, ck);
-            tma_load_3d(smem + kR2, &tmQkvR, bar_r, 0, r, cv);
-          }
+          if (gt > 0) mbar_wait(bar_rfree, (gt - 1) & 1);
+          ATTN_TRACE(70 + t);
+          mbar_expect_tx(bar_r, 32 * 1024);
+          tma_load_3d(smem + kR1, &tmQkvR, bar_r, 0, r, MODE == 0 ? cq : ck);
+          if (gt > 0) mbar_wait(bar_r2free, (gt - 1) & 1);
+          mbar_expect_tx(bar_r2, 32 * 1024);
+          if (MODE == 0) tma_load_3d(smem + kR2, &tmDoR, bar_r2, 0, r, cdo);
+          else           tma_load_3d(smem + kR2, &tmQkvR, bar_r2, 0, r, cv);
           // the loads that follow are known exactly (next row tile, then the next item's columns): pull them into
           // L2 now so that they hit when the buffers free up (their latency sits on the tile-boundary critical path)
           if (p.prefetch_dist) {
@@ -219,6 +226,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvR, const __grid_cons
             for (int k = 0; k < 4; ++k)
               umma_tf32_ss_p(tm_s, r1 + ((kc * 16384 + k * 32) >> 4), hi, y1 + yq + ((kc * 8192 + k * 32) >> 4), hi,
                              idesc_s, (kc | k) ? 1u : 0u, leader);
+          if (q == nq - 1) umma_commit_p(bar_rfree, leader);  // R1 may be refilled
+          if (q == 0) {
+            mbar_wait(bar_r2, gt & 1);
+            tc_fence_after();
+          }
 #pragma unroll
           for (int kc = 0; kc < 2; ++kc)
 #pragma unroll
@@ -226,7 +238,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQkvR, const __grid_cons
               umma_tf32_ss_p(tm_dp, r2 + ((kc * 16384 + k * 32) >> 4), hi, y2 + yq + ((kc * 8192 + k * 32) >> 4), hi,
                              idesc_s, (kc | k) ? 1u : 0u, leader);
           umma_commit_p(&bar_full[slot], leader);
-          if (q == nq - 1) umma_commit_p(bar_rfree, leader);
+          if (q == nq - 1) umma_commit_p(bar_r2free, leader);
           ATTN_TRACE(2 + 4 * i);
           __syncwarp();
         }

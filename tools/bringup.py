@@ -282,7 +282,8 @@ def sec_attn_trace():
             print("  q%d  mma: P ready %6d issued %6d | C ready %6d issued %6d || compute: ready %6d done %6d" %
                   (i, rel[1 + 4 * i], rel[2 + 4 * i], rel[3 + 4 * i], rel[4 + 4 * i], rel[40 + 2 * i], rel[41 + 2 * i]))
         for t in range(2):
-            print("  tile %d acc ready %6d stored %6d" % (t, rel[60 + 2 * t], rel[61 + 2 * t]))
+            print("  tile %d acc ready %6d stored %6d | producer: row buffers free, load issued %6d" %
+                  (t, rel[60 + 2 * t], rel[61 + 2 * t], rel[70 + t]))
 
 
 def sec_attn_tc():
