@@ -25,6 +25,39 @@ def test_library_exports_every_declared_symbol():
     assert lib.atst_version() >= 100
 
 
+def test_ctypes_signatures_match_the_header():
+    """every declaration of include/atst_b200.h against the ctypes argtypes of _lib.SIGNATURES: same parameter count
+    and the same pointer / integer / float kind at every position (an ABI drift would otherwise only show on the GPU)."""
+    import ctypes
+    from audiossl_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "atst_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    decls = dict(re.findall(r"\bint\s+(atst_\w+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S))
+    assert set(decls) == set(_lib.SIGNATURES)
+
+    def kind(param):
+        param = param.strip()
+        if "*" in param:
+            return "ptr"
+        if param.startswith("float"):
+            return "float"
+        return "int"  # int, unsigned, long long
+
+    ck = {ctypes.c_void_p: "ptr", ctypes.c_char_p: "ptr", ctypes.c_float: "float", ctypes.c_int: "int",
+          ctypes.c_longlong: "int", ctypes.c_uint: "int"}
+    for name, params in decls.items():
+        plist = [] if params.strip() in ("", "void") else [x for x in params.split(",")]
+        want = [kind(x) for x in plist]
+        have = [ck[a] for a in _lib.SIGNATURES[name]]
+        assert want == have, (name, want, have)
+        # 64-bit integers must be declared as such on both sides
+        for x, a in zip(plist, _lib.SIGNATURES[name]):
+            if "long long" in x and "*" not in x:
+                assert a is ctypes.c_longlong, (name, x)
+            if a is ctypes.c_longlong:
+                assert "long long" in x, (name, x)
+
+
 def test_no_cpu_fallback():
     from audiossl_b200.models.atst import ATST
     from audiossl_b200.transforms import LogMelSpectrogram
