@@ -28,6 +28,8 @@ SIGNATURES = {
     "atst_layernorm_backward": [P, L, P, L, P, P, P, P, L, P, L, P, P, I, I, P, L, P, I, P, P],
     "atst_attention_forward": [P, P, P, P, I, I, I, P],
     "atst_attention_backward": [P, P, P, P, P, P, P, I, I, I, P],
+    "atst_gemm_trace": [P],
+    "atst_copy_pattern": [P, P, I, I, I, P],
     "atst_attention_trace": [P, I, I],
     "atst_patchify": [P, L, I, I, P, P],
     "atst_tokens_forward": [P, P, P, P, P, P, I, I, I, I, P],

@@ -9,6 +9,8 @@ namespace atst {
 void attention_set_tc(int on);
 void attention_set_l2_prefetch(int on);
 void attention_set_trace(long long* buf, int seq, int mode);
+void gemm_set_trace(long long* buf);
+int copy_pattern(const float* src, float* dst, int rows, int cols, int mode, cudaStream_t stream);
 int umma_probe(int mode, const float* A, const float* B, float* D, unsigned layout, unsigned lbo, unsigned sbo,
                unsigned kstep, cudaStream_t stream);
 }
@@ -97,6 +99,13 @@ int atst_umma_probe(int mode, const float* A, const float* B, float* D, unsigned
   return umma_probe(mode, A, B, D, layout, lbo, sbo, kstep, ST(stream));
 }
 
+int atst_gemm_trace(long long* buf) {
+  gemm_set_trace(buf);
+  return ATST_OK;
+}
+int atst_copy_pattern(const float* src, float* dst, int rows, int cols, int mode, void* stream) {
+  return copy_pattern(src, dst, rows, cols, mode, ST(stream));
+}
 int atst_attention_trace(long long* buf, int seq, int mode) {
   attention_set_trace(buf, seq, mode);
   return ATST_OK;

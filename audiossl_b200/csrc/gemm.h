@@ -30,6 +30,7 @@ struct GemmParams {
   int rows_per_seq = 1;
   int epi = EPI_STORE;
   int round_out = 0;                // round C to tf32 (it feeds another GEMM)
+  long long* trace = nullptr;       // bring-up: clock64() timeline of one epilogue warp / the MMA warp of CTA 0
   float* colsum = nullptr;          // [N] or null: colsum[n] += sum over rows of the stored C[:, n] (a bias gradient)
   int splits = 0;                   // TN only: split-K factor (0 = auto)
   int l2_prefetch = 1;              // producer prefetches streaming operand tiles into L2 ahead of the smem ring

@@ -6,10 +6,10 @@
 // two SMs read the other half from the peer's shared memory.  Per CTA: 64 B/clk of TMA fill, 64 B/clk of UMMA
 // reads, 64 B/clk of L2 traffic, and the 32 KB stages make the smem ring 6 deep instead of 4.
 //
-// Roles per CTA (640 threads): warp 0 TMA producer (both CTAs; transactions complete on the LEADER's full
+// Roles per CTA (384 threads): warp 0 TMA producer (both CTAs; transactions complete on the LEADER's full
 // barrier), warp 1 MMA issuer (leader only: tcgen05.mma.cta_group::2, M=256; tcgen05.commit multicast frees the
 // smem slot / publishes the accumulator in both CTAs), warp 2 TMEM allocator (cta_group::2 alloc in both CTAs),
-// warps 4-19 epilogue (own 128 TMEM lanes, four warps per lane quadrant; the accumulator stage is handed back on the leader's barrier, remotely
+// warps 4-11 epilogue (own 128 TMEM lanes, two warps per lane quadrant; the accumulator stage is handed back on the leader's barrier, remotely
 // from the follower).  Operand majors as in the 1-CTA kernel (K-major 128B swizzle, or token-major tensors via
 // the 32B-atom swizzle).
 #include <cooperative_groups.h>
@@ -26,7 +26,7 @@ constexpr int kBN = 256;       // N columns per pair tile
 constexpr int kBNHalf = 128;   // B rows staged per CTA
 constexpr int kBK = 32;        // tf32 elements per k-block (128 B)
 constexpr int kStages2 = 6;
-constexpr int kEpiWarps2 = 16;                 // four per TMEM lane quadrant, each walking a 64-column quarter of the tile
+constexpr int kEpiWarps2 = 8;                  // two per TMEM lane quadrant, each walking a 128-column half of the tile
 constexpr int kThreads2 = 128 + 32 * kEpiWarps2;
 constexpr int kA2 = kBM * 128;       // 16 KB
 constexpr int kB2 = kBNHalf * 128;   // 16 KB
@@ -224,8 +224,12 @@ gemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int split = tile / (m_tiles * n_tiles);
         const int kb0 = split * kb_per_split;
         const int kb1 = min(kb0 + kb_per_split, kb_total);
+        const int tidx = (tile - first_tile) / tile_step;
+        const bool tr = p.trace != nullptr && blockIdx.x == 0 && lane == 0 && tidx >= 8 && tidx < 12;
+        if (tr) p.trace[8 * (tidx - 8) + 4] = clock64();  // MMA warp arrives at the tile
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
+        if (tr) p.trace[8 * (tidx - 8) + 5] = clock64();  // accumulator stage free
         const uint32_t d_tmem = tmem_base + acc * kBN;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
@@ -243,6 +247,7 @@ gemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
         if (kb1 <= kb0) umma2_commit_mc_p(&tfull_bar[acc], lead);
+        if (tr) p.trace[8 * (tidx - 8) + 6] = clock64();  // last MMA of the tile issued
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -266,9 +271,13 @@ gemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       auto release = [&]() {
         if (lane == 0) mbar_arrive_leader(tempty);
       };
+      const int tidx = (tile - first_tile) / tile_step;  // this CTA's tile counter
+      const bool tr = p.trace != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0 && tidx >= 8 && tidx < 12;
+      if (tr) p.trace[8 * (tidx - 8) + 0] = clock64();  // epilogue warp arrives at the tile
       epilogue_tile<kBN, 32 * kEpiWarps2>(p, m0, n0, empty_split, tmem_base + acc * kBN, smem_bias + acc * 256, ew, lane,
                                           epi_tid, chalf * kGroupsPerWarp, (chalf + 1) * kGroupsPerWarp, &tfull_bar[acc],
-                                          acc_phase, release);
+                                          acc_phase, release, tr ? p.trace + 8 * (tidx - 8) : nullptr);
+      if (tr) p.trace[8 * (tidx - 8) + 3] = clock64();  // tile stored
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -288,6 +297,7 @@ int make_map_kmajor_pub(CUtensorMap* map, const float* ptr, int rows, int cols, 
 int make_map_mnmajor_pub(CUtensorMap* map, const float* ptr, int tokens, int feats, int ld, int box_feats,
                          int swizzle_mode);
 int gemm_num_sms();
+long long* gemm_trace_ptr();
 
 template <bool A_MN, bool B_MN>
 static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
@@ -303,7 +313,9 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
   const int tiles = m_tiles * n_tiles * (p.splits > 0 ? p.splits : 1);
   const int pairs = gemm_num_sms() / 2;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
-  kfn<<<grid, kThreads2, kSmem2, stream>>>(ta, tb, p);
+  GemmParams q = p;
+  q.trace = gemm_trace_ptr();
+  kfn<<<grid, kThreads2, kSmem2, stream>>>(ta, tb, q);
   return atst_check_launch("gemm2_tf32_kernel");
 }
 

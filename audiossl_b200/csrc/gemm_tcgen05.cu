@@ -380,6 +380,9 @@ void gemm_set_cta_pair(int on) { g_cta_pair = on; }
 int gemm2_launch(int a_mn, int b_mn, const float* A, int lda, int a_rows, int a_cols, const float* B, int ldb, int b_rows,
                  int b_cols, const GemmParams& p, cudaStream_t stream);
 
+static long long* g_gemm_trace = nullptr;
+void gemm_set_trace(long long* buf) { g_gemm_trace = buf; }
+long long* gemm_trace_ptr() { return g_gemm_trace; }
 static int g_l2_prefetch = 0;  // measured: no gain (the ring is L2-bandwidth, not latency, limited)
 void gemm_set_l2_prefetch(int on) { g_l2_prefetch = on; }
 

@@ -108,6 +108,40 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
+// ---- DRAM access-pattern probe: copy [rows, cols] fp32 the way the GEMM epilogue touches memory (mode 0: a warp owns
+// 32 rows x 64 columns, lane = row, eight 32-byte accesses per lane) or fully coalesced (mode 1: float4 grid-stride)
+__global__ void __launch_bounds__(512) copy_pattern_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                           int rows, int cols, int mode) {
+  if (mode == 1) {
+    const long long n4 = static_cast<long long>(rows) * cols / 4;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+      reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+    return;
+  }
+  // tiles of 128 rows x 256 columns, 16 warps per tile: quadrant = warp & 3 (32 rows), slice = warp >> 2 (64 columns)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (rows + 127) / 128, n_tiles = cols / 256;
+  for (int tile = blockIdx.x; tile < m_tiles * n_tiles; tile += gridDim.x) {
+    const int m0 = (tile / n_tiles) * 128, n0 = (tile % n_tiles) * 256;
+    const int row = m0 + (warp & 3) * 32 + lane;
+    if (row >= rows) continue;
+    const size_t off = static_cast<size_t>(row) * cols + n0 + (warp >> 2) * 64;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      float v[8];
+      ld_global_v8(src + off + g * 8, v);
+      st_global_v8(dst + off + g * 8, v);
+    }
+  }
+}
+
+int copy_pattern(const float* src, float* dst, int rows, int cols, int mode, cudaStream_t stream) {
+  ATST_REQUIRE(cols % 256 == 0, "copy_pattern: cols %% 256 != 0");
+  copy_pattern_kernel<<<148 * (mode == 1 ? 4 : 1), 512, 0, stream>>>(src, dst, rows, cols, mode);
+  return atst_check_launch("copy_pattern_kernel");
+}
+
 int umma_probe(int mode, const float* A, const float* B, float* D, unsigned layout, unsigned lbo, unsigned sbo,
                unsigned kstep, cudaStream_t stream) {
   CUtensorMap ta, tb;

@@ -84,6 +84,13 @@ int atst_attention_forward(const float* qkv, float* o, float* lse, const int* le
 int atst_attention_backward(const float* qkv, const float* o, const float* d_o, const float* lse, float* delta_ws,
                             float* dqkv, const int* lengths, int S, int N, int H, void* stream);
 
+/* bring-up: clock64() timeline (32 slots, device buffer) of tiles 8-11 of CTA 0 of the CTA-pair GEMM on subsequent
+ * GEMM calls: per tile {epilogue warp arrives, bias staged, accumulator complete, tile stored, MMA warp arrives,
+ * accumulator stage free, last MMA issued}; buf = NULL switches it off */
+int atst_gemm_trace(long long* buf);
+/* bring-up: copy [rows, cols] fp32 with the GEMM epilogue's access pattern (mode 0: lane = row, 32-byte accesses) or
+ * fully coalesced (mode 1), to measure what each pattern reaches in DRAM bandwidth */
+int atst_copy_pattern(const float* src, float* dst, int rows, int cols, int mode, void* stream);
 /* bring-up: record a clock64() timeline (80 slots, device buffer) of the CTA of head 0 / sequence seq in the tcgen05
  * backward kernel `mode` (0 dQ, 1 dK dV) on subsequent atst_attention_backward calls; buf = NULL switches it off */
 int atst_attention_trace(long long* buf, int seq, int mode);

@@ -214,6 +214,67 @@ def sec_umma_probe():
         print("%s mode 0 layout=%d lbo=%5d sbo=%4d kstep=%3d rel=%.3e" % ("OK " if err < 2e-3 else "   ", layout, lbo, sbo, kstep, err))
 
 
+def sec_gemm_trace():
+    """per-tile timeline of the CTA-pair GEMM (fc1 shape) for the plain, GELU and GELU+aux epilogues."""
+    import torch
+    from audiossl_b200 import _lib, ops
+    from audiossl_b200._lib import ptr
+    L = _lib.lib()
+    M, D = 128512, 768
+    A = ops.round_tf32(torch.randn(M, D, device="cuda"))
+    W = ops.round_tf32(torch.randn(4 * D, D, device="cuda") * 0.05)
+    b = torch.randn(4 * D, device="cuda")
+    u = torch.empty(M, 4 * D, device="cuda")
+    g = torch.empty(M, 4 * D, device="cuda")
+    x = torch.randn(M, D, device="cuda")
+    W2 = ops.round_tf32(torch.randn(D, D, device="cuda") * 0.05)
+    b2 = torch.randn(D, device="cuda")
+    o2 = torch.empty(M, D, device="cuda")
+    cases = [("fc1 plain", lambda: ops.gemm_nt(A, W, bias=b, out=u)),
+             ("fc1 gelu (no aux)", lambda: ops.gemm_nt(A, W, bias=b, epi=ops.EPI_GELU, aux=None, round_out=True, out=g)),
+             ("fc1 gelu + aux", lambda: ops.gemm_nt(A, W, bias=b, epi=ops.EPI_GELU, aux=u, round_out=True, out=g)),
+             ("proj plain", lambda: ops.gemm_nt(A, W2, bias=b2, out=o2)),
+             ("proj + resid", lambda: ops.gemm_nt(A, W2, bias=b2, epi=ops.EPI_RESID, resid=x, out=o2))]
+    for name, fn in cases:
+        fn()
+        buf = torch.zeros(32, dtype=torch.int64, device="cuda")
+        L.atst_gemm_trace(ptr(buf))
+        fn()
+        torch.cuda.synchronize()
+        L.atst_gemm_trace(None)
+        t = buf.cpu().tolist()
+        t0 = t[0]
+        print(name)
+        for k in range(4):
+            r = [v - t0 for v in t[8 * k:8 * k + 7]]
+            print("  tile %d  epi: arrive %6d bias %6d acc-ready %6d stored %6d | mma: arrive %6d stage-free %6d issued %6d" %
+                  (8 + k, r[0], r[1], r[2], r[3], r[4], r[5], r[6]))
+
+
+def sec_copy_pattern():
+    """DRAM bandwidth of the GEMM epilogue's access pattern against a coalesced copy, [128512, 3072] fp32."""
+    import torch
+    from audiossl_b200 import _lib
+    from audiossl_b200._lib import ptr
+    L = _lib.lib()
+    M, N = 128512, 3072
+    src = torch.randn(M, N, device="cuda")
+    dst = torch.empty_like(src)
+    for mode, name in ((0, "epilogue pattern (lane = row, 32 B accesses)"), (1, "coalesced float4")):
+        ts = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            L.atst_copy_pattern(ptr(src), ptr(dst), M, N, mode, _lib.stream())
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        t = sorted(ts)[2]
+        print("%-46s %.3f ms  %7.1f GB/s (read + write)" % (name, t, 8.0 * M * N / t / 1e6))
+        assert torch.equal(src, dst)
+        dst.zero_()
+
+
 def sec_ew_perf():
     """HBM-bound passes at the config-2 shape: time and achieved algorithmic GB/s."""
     import torch
@@ -588,7 +649,7 @@ def sec_pair():
         L.atst_set_option(b"gemm_cta_pair", 0)
 
 
-SECTIONS = {"ew_perf": sec_ew_perf, "attn_trace": sec_attn_trace, "umma_probe": sec_umma_probe, "attn_tc": sec_attn_tc, "pair": sec_pair, "heads": sec_heads, "gemm_perf": sec_gemm_perf, "mel": sec_mel, "gemm_nt": sec_gemm_nt, "gemm_mn": sec_gemm_mn, "ln": sec_ln, "attn": sec_attn,
+SECTIONS = {"gemm_trace": sec_gemm_trace, "copy_pattern": sec_copy_pattern, "ew_perf": sec_ew_perf, "attn_trace": sec_attn_trace, "umma_probe": sec_umma_probe, "attn_tc": sec_attn_tc, "pair": sec_pair, "heads": sec_heads, "gemm_perf": sec_gemm_perf, "mel": sec_mel, "gemm_nt": sec_gemm_nt, "gemm_mn": sec_gemm_mn, "ln": sec_ln, "attn": sec_attn,
             "bn": sec_bn, "loss": sec_loss, "optim": sec_optim, "tokens": sec_tokens}
 
 if __name__ == "__main__":
