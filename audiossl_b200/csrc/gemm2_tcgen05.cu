@@ -6,10 +6,10 @@
 // two SMs read the other half from the peer's shared memory.  Per CTA: 64 B/clk of TMA fill, 64 B/clk of UMMA
 // reads, 64 B/clk of L2 traffic, and the 32 KB stages make the smem ring 6 deep instead of 4.
 //
-// Roles per CTA (384 threads): warp 0 TMA producer (both CTAs; transactions complete on the LEADER's full
+// Roles per CTA (640 threads): warp 0 TMA producer (both CTAs; transactions complete on the LEADER's full
 // barrier), warp 1 MMA issuer (leader only: tcgen05.mma.cta_group::2, M=256; tcgen05.commit multicast frees the
 // smem slot / publishes the accumulator in both CTAs), warp 2 TMEM allocator (cta_group::2 alloc in both CTAs),
-// warps 4-11 epilogue (own 128 TMEM lanes, two warps per lane quadrant; the accumulator stage is handed back on the leader's barrier, remotely
+// warps 4-19 epilogue (own 128 TMEM lanes, four warps per lane quadrant; the accumulator stage is handed back on the leader's barrier, remotely
 // from the follower).  Operand majors as in the 1-CTA kernel (K-major 128B swizzle, or token-major tensors via
 // the 32B-atom swizzle).
 #include <cooperative_groups.h>
@@ -26,7 +26,7 @@ constexpr int kBN = 256;       // N columns per pair tile
 constexpr int kBNHalf = 128;   // B rows staged per CTA
 constexpr int kBK = 32;        // tf32 elements per k-block (128 B)
 constexpr int kStages2 = 6;
-constexpr int kEpiWarps2 = 8;                  // two per TMEM lane quadrant, each walking a 128-column half of the tile
+constexpr int kEpiWarps2 = 16;                 // four per TMEM lane quadrant, each walking a 64-column quarter of the tile
 constexpr int kThreads2 = 128 + 32 * kEpiWarps2;
 constexpr int kA2 = kBM * 128;       // 16 KB
 constexpr int kB2 = kBNHalf * 128;   // 16 KB

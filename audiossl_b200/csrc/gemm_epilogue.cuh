@@ -42,18 +42,20 @@ __device__ __forceinline__ float gelu_grad(float u) {
 
 
 // Thread `lane` of an epilogue warp of TMEM lane quadrant `ew` owns accumulator row 32*ew + lane and walks the
-// 8-column groups [g0, g1) of the tile (g1 - g0 a multiple of 8: whole pairs of 32-column chunks).
+// 8-column groups [g0, g1) of the tile (g1 - g0 a multiple of 4; four warps per quadrant: a 64-column quarter each).
+// The loop is deliberately NOT unrolled over the tile: one compact body (TMEM load of the next group and its side
+// input in flight while the current group is computed and stored) instead of a copy of every epilogue variant per
+// column chunk - the unrolled form thrashed the instruction cache (ncu: 23 % of the stall samples were "no
+// instruction" with the GELU epilogue).  `release()` is called once per warp, right after its last TMEM load of the
+// tile, to hand the accumulator stage back to the MMA issuer.  EPI_THREADS = epilogue threads of the CTA.
 //
-// Accumulator fetch.  Under a running main loop a tcgen05.ld takes ~1500 cycles (the accumulating MMAs own the
-// tensor-memory port; per-tile clock64 timeline, tools/bringup.py gemm_trace), and the accumulator stage can only go
-// back to the MMA issuer after the warp's LAST load.  Eight dependent 8-column loads per warp therefore held the
-// stage for ~12 000 cycles - longer than the 11 000-cycle main loop, so the MMA issuer waited ~2500 cycles per tile
-// for a free stage in EVERY GEMM.  Now two 32-column loads are in flight at a time, the next pair is issued while
-// the current one is processed from registers, and `release()` follows the last wait: the stage is held for two to
-// three load latencies.
-// The per-group body stays compact (one copy of the epilogue variants per chunk position, not per tile): the fully
-// unrolled form thrashed the instruction cache (ncu: 23 % "no instruction" stall samples with the GELU epilogue).
-// EPI_THREADS = epilogue threads of the CTA.
+// What bounds this epilogue (per-tile clock64 timeline, tools/bringup.py gemm_trace): 128 KB of global
+// traffic per tile take ~11 000 cycles whatever the access shape - the SM's link to L2 is already filled by the main
+// loop's operand fetch (768 KB per tile) - so one output stream hides under the 13 600-cycle main loop and a second
+// one (residual / saved pre-activation in, pre-activation out) does not.  Measured and rejected: 4 lanes per row after
+// a quad transpose (same time), a shared-memory staging tile with TMA loads / stores (slower: the shared-memory port
+// belongs to TMA + UMMA), 32- or 16-column accumulator loads in flight with an early release of the stage (plain
+// shapes +5 %, fused shapes -20 %: the unthrottled main loop takes the link from the epilogue that is the bottleneck).
 template <int BLOCK_N, int EPI_THREADS, class Release>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n0, bool empty_split, uint32_t taddr,
                                               float* sbias, int ew, int lane, int epi_tid, int g0, int g1,
@@ -83,16 +85,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
   if (trace) trace[2] = clock64();  // accumulator complete
   taddr += static_cast<uint32_t>(ew * 32) << 16;
 
+  auto fetch_acc = [&](int g, uint32_t (&r)[8]) { tmem_ld_32x8(taddr + g * 8, r); };
   auto fetch_side = [&](int g, float (&sd)[8]) {
     if (side_row != nullptr && g < g1 && g * 8 < ncols) ld_global_v8(side_row + g * 8, sd);
   };
   const bool do_colsum = p.colsum != nullptr;  // warp-uniform
-  // group g = columns [8g, 8g+8) of the tile; its accumulator values are r[8j .. 8j+7] of a 32-column chunk buffer
-  auto finish = [&](int g, const uint32_t (&r)[32], int j, const float (&sd)[8]) {
+  auto finish = [&](int g, const uint32_t (&r)[8], const float (&sd)[8]) {
     if (g * 8 >= ncols || (!row_ok && !do_colsum)) return;
     float v[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * j + e]);
+    for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[e]);
     if (p.bias != nullptr) {
       const float4 b0 = *reinterpret_cast<const float4*>(sbias + g * 8);  // smem broadcast
       const float4 b1 = *reinterpret_cast<const float4*>(sbias + g * 8 + 4);
@@ -101,7 +103,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
     }
     switch (p.epi) {
       case EPI_GELU:  // aux (nullable: the teacher keeps no pre-activation) <- pre-activation, C <- gelu
-        if (aux_row != nullptr && row_ok) st_global_v8(aux_row + g * 8, v);
+        if (aux_row != nullptr) st_global_v8(aux_row + g * 8, v);
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = gelu_exact(v[e]);
         break;
@@ -149,42 +151,38 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
       if (lane < 8) atomicAdd(p.colsum + n0 + g * 8 + lane, mine);
     }
   };
-  // side inputs run three groups ahead of the group being finished (ring of four 8-float buffers, static indices
-  // because a chunk pair is eight groups)
-  uint32_t ra[32], rb[32];
+  // accumulator groups are fetched one ahead (tcgen05.wait::ld waits for every outstanding load, so deeper does not
+  // help), side inputs three ahead (their L2 / HBM latency is several groups long); (g1 - g0) % 4 == 0
+  uint32_t ra[8], rb[8];
   float sd[4][8];
   fetch_side(g0, sd[0]);
   fetch_side(g0 + 1, sd[1]);
   fetch_side(g0 + 2, sd[2]);
-  tmem_ld_32x32(taddr + g0 * 8, ra);
-  tmem_ld_32x32(taddr + g0 * 8 + 32, rb);
-  tmem_ld_wait();
-  auto release_once = [&]() {
-    tc_fence_before();
-    __syncwarp();
-    release();
-  };
-  if (g0 + 8 >= g1) release_once();
-  if (trace) trace[7] = clock64();  // first accumulator chunks in registers
+  fetch_acc(g0, ra);
 #pragma unroll 1
-  for (int g = g0; g < g1; g += 8) {
-    const bool more = g + 8 < g1;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      fetch_side(g + j + 3, sd[(j + 3) & 3]);
-      finish(g + j, ra, j, sd[j & 3]);
+  for (int g = g0; g < g1; g += 4) {
+    tmem_ld_wait();
+    fetch_acc(g + 1, rb);
+    fetch_side(g + 3, sd[3]);
+    finish(g, ra, sd[0]);
+    tmem_ld_wait();
+    fetch_acc(g + 2, ra);
+    fetch_side(g + 4, sd[0]);
+    finish(g + 1, rb, sd[1]);
+    tmem_ld_wait();
+    fetch_acc(g + 3, rb);
+    fetch_side(g + 5, sd[1]);
+    finish(g + 2, ra, sd[2]);
+    tmem_ld_wait();
+    if (g + 4 < g1) {
+      fetch_acc(g + 4, ra);
+      fetch_side(g + 6, sd[2]);
+    } else {  // this warp's last TMEM load of the tile has completed
+      tc_fence_before();
+      __syncwarp();
+      release();
     }
-    if (more) tmem_ld_32x32(taddr + (g + 8) * 8, ra);  // next pair, first chunk: in flight while rb is processed
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      fetch_side(g + 4 + j + 3, sd[(j + 3) & 3]);
-      finish(g + 4 + j, rb, j, sd[j & 3]);
-    }
-    if (more) {
-      tmem_ld_32x32(taddr + (g + 8) * 8 + 32, rb);
-      tmem_ld_wait();
-      if (g + 16 >= g1) release_once();  // this warp's last TMEM load of the tile has completed
-    }
+    finish(g + 3, rb, sd[3]);
   }
 }
 

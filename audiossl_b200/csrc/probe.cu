@@ -119,8 +119,28 @@ __global__ void __launch_bounds__(512) copy_pattern_kernel(const float* __restri
       reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
     return;
   }
-  // tiles of 128 rows x 256 columns, 16 warps per tile: quadrant = warp & 3 (32 rows), slice = warp >> 2 (64 columns)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (mode == 2) {
+    // same tiles, but a warp instruction covers 8 rows x 128 contiguous bytes (4 lanes per row) instead of 32 rows x 32 B
+    const int m_tiles2 = (rows + 127) / 128, n_tiles2 = cols / 256;
+    for (int tile = blockIdx.x; tile < m_tiles2 * n_tiles2; tile += gridDim.x) {
+      const int m0 = (tile / n_tiles2) * 128, n0 = (tile % n_tiles2) * 256;
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {      // 4 x 8 rows of this warp's 32
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {    // 2 x 32 columns of this warp's 64
+          const int row = m0 + (warp & 3) * 32 + rr * 8 + (lane >> 2);
+          if (row >= rows) continue;
+          const size_t off = static_cast<size_t>(row) * cols + n0 + (warp >> 2) * 64 + cc * 32 + (lane & 3) * 8;
+          float v[8];
+          ld_global_v8(src + off, v);
+          st_global_v8(dst + off, v);
+        }
+      }
+    }
+    return;
+  }
+  // tiles of 128 rows x 256 columns, 16 warps per tile: quadrant = warp & 3 (32 rows), slice = warp >> 2 (64 columns)
   const int m_tiles = (rows + 127) / 128, n_tiles = cols / 256;
   for (int tile = blockIdx.x; tile < m_tiles * n_tiles; tile += gridDim.x) {
     const int m0 = (tile / n_tiles) * 128, n0 = (tile % n_tiles) * 256;

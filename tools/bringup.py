@@ -252,27 +252,30 @@ def sec_gemm_trace():
 
 
 def sec_copy_pattern():
-    """DRAM bandwidth of the GEMM epilogue's access pattern against a coalesced copy, [128512, 3072] fp32."""
+    """bandwidth of the GEMM epilogue's access pattern (lane = row, 32 B) against 4 lanes per row (128 B) and a
+    coalesced copy: DRAM-sized [128512, 3072] and L2-resident [8192, 1024] (repeated), fp32."""
     import torch
     from audiossl_b200 import _lib
     from audiossl_b200._lib import ptr
     L = _lib.lib()
-    M, N = 128512, 3072
-    src = torch.randn(M, N, device="cuda")
-    dst = torch.empty_like(src)
-    for mode, name in ((0, "epilogue pattern (lane = row, 32 B accesses)"), (1, "coalesced float4")):
-        ts = []
-        for _ in range(5):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            L.atst_copy_pattern(ptr(src), ptr(dst), M, N, mode, _lib.stream())
-            e1.record()
-            torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        t = sorted(ts)[2]
-        print("%-46s %.3f ms  %7.1f GB/s (read + write)" % (name, t, 8.0 * M * N / t / 1e6))
-        assert torch.equal(src, dst)
-        dst.zero_()
+    for (M, N, reps) in ((128512, 3072, 1), (8192, 1024, 20)):
+        src = torch.randn(M, N, device="cuda")
+        dst = torch.empty_like(src)
+        for mode, name in ((0, "lane = row, 32 B per lane (epilogue today)"), (2, "4 lanes per row, 128 B per row"),
+                           (1, "coalesced float4")):
+            ts = []
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    L.atst_copy_pattern(ptr(src), ptr(dst), M, N, mode, _lib.stream())
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1) / reps)
+            t = sorted(ts)[2]
+            print("[%6d x %4d] %-46s %.4f ms  %7.1f GB/s (read + write)" % (M, N, name, t, 8.0 * M * N / t / 1e6))
+            assert torch.equal(src, dst)
+            dst.zero_()
 
 
 def sec_ew_perf():
