@@ -20,6 +20,8 @@ from .byol import ByolLoss, MultiCropWrapper
 
 
 class _FrameRuntime(_Runtime):
+    never_used = ()  # the student blends mask_embed into the masked patches
+
     def _make_encoder(self, enc):
         return EncoderEngine(enc.embed_dim, enc.depth, enc.num_heads, use_cls=False, norm_name="norm_frame",
                              max_frames=enc.spec_w)
@@ -87,7 +89,7 @@ class _FrameRuntime(_Runtime):
         dxn.zero_()
         ops.scatter_rows(drows, idx, dxn)
         self.enc.backward(fs, self.ws, enc_ctx, dxn)
-        allreduce_avg_(fs.grad)
+        allreduce_avg_(fs.exchanged_grad())
         fs.attach_grads()
 
 

@@ -38,14 +38,19 @@ class _StepFn(torch.autograd.Function):
 
 
 class _Runtime:
+    # parameters the forward pass never reads: they keep grad None and are never stepped / decayed (the reference's
+    # AdamW skips them).  The frame runtime uses mask_embed and overrides this.
+    never_used = ("encoder.mask_embed",)
+
     def __init__(self, model, device):
         self.model = model
         self.device = device
         model.student.to(device)   # BN buffers must live next to the parameters
         model.teacher.to(device)
         enc = model.student.encoder
-        self.fs = FlatParams(list(model.student.named_parameters()), device)
-        self.ft = FlatParams(list(model.teacher.named_parameters()), device)
+        frozen = set(self.never_used) | {n for n, p in model.student.named_parameters() if not p.requires_grad}
+        self.fs = FlatParams(list(model.student.named_parameters()), device, frozen=frozen)
+        self.ft = FlatParams(list(model.teacher.named_parameters()), device, frozen=frozen)
         assert self.ft.total == self.fs.ema_count and self.ft.order == self.fs.order[:len(self.ft.order)], \
             "teacher layout must be the encoder+projector prefix of the student layout"
         self.enc = self._make_encoder(enc)
@@ -132,7 +137,7 @@ class _Runtime:
             S = ctx["S"]
             self.enc.backward(fs, self.ws, ctx, dcls[row:row + S])
             row += S
-        allreduce_avg_(fs.grad)
+        allreduce_avg_(fs.exchanged_grad())
         fs.attach_grads()
 
 

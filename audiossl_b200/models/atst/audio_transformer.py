@@ -126,6 +126,12 @@ class AST(_EncoderInference, nn.Module):
             raise NotImplementedError('pos_type="interpolate" is not used by any ATST recipe')
         if mlp_ratio != 4.:
             raise NotImplementedError("mlp_ratio != 4")
+        if not use_cls:
+            # the reference's AST(use_cls=False) adds pos_embed[:, :T] and returns the length-masked token mean
+            # (audio_transformer.py:180-186, 211-221); the engine's no-CLS path is FrameAST's (positions from 1,
+            # per-token output, norm_frame) - a different function, so refuse instead of computing that silently
+            raise NotImplementedError("AST(use_cls=False) is not used by any ATST recipe; the no-CLS encoder on the "
+                                      "CUDA engine is audiossl_b200.methods.atstframe.audio_transformer.FrameAST")
         self.num_features = self.embed_dim = embed_dim
         self.spec_w, self.spec_h, self.patch_w, self.patch_h = spec_w, spec_h, patch_w, patch_h
         self.depth, self.num_heads, self.drop_path_rate = depth, num_heads, drop_path_rate

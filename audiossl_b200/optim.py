@@ -1,11 +1,17 @@
 """Fused AdamW with the semantics of transformers-4.x ``AdamW`` (the optimizer of
 audiossl/methods/atst/model.py:44-48): betas (0.9, 0.999), eps 1e-6 added to sqrt(v) before bias
-correction, ``correct_bias=True``, decoupled weight decay applied after the Adam update.
+correction, ``correct_bias=True``, decoupled weight decay applied after the Adam update, and - like its
+``if p.grad is None: continue`` - no update and no decay for a parameter that never receives a gradient
+(ATST-clip's ``encoder.mask_embed``, frozen tensors): those sit outside ``FlatParams.wd_segments()``.
 
 It is a regular ``torch.optim.Optimizer`` (param_groups with ``lr`` / ``weight_decay`` that the
 Lightning module's ``schedule()`` overwrites every step), but ``step()`` is a handful of launches of one
 multi-tensor kernel over the flat parameter / gradient / moment buffers instead of a Python loop over
 ~150 tensors.
+
+Checkpoints: ``state_dict()`` carries the per-parameter layout of transformers' AdamW (``state[i] = {step,
+exp_avg, exp_avg_sq}``, views of the flat moment buffers), so a reference optimizer checkpoint loads here and
+vice versa.
 """
 import torch
 
@@ -23,20 +29,22 @@ class FusedHFAdamW(torch.optim.Optimizer):
         self._m = self._v = None
         self._step = 0
 
+    def _moments(self, fp):
+        if self._m is None or self._m.numel() != fp.total or self._m.device != fp.data.device:
+            self._m = torch.zeros_like(fp.data)
+            self._v = torch.zeros_like(fp.data)
+        return self._m, self._v
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
         fp = self.flat_provider()
-        if self._m is None or self._m.numel() != fp.total:
-            self._m = torch.zeros_like(fp.data)
-            self._v = torch.zeros_like(fp.data)
+        m, v = self._moments(fp)
         self._step += 1
         g_reg, g_noreg = self.param_groups[0], self.param_groups[1]
         for (a, b, reg) in fp.wd_segments():
-            if b <= a:
-                continue
             grp = g_reg if reg else g_noreg
-            ops.adamw_step(fp.data[a:b], fp.grad[a:b], self._m[a:b], self._v[a:b], self._step, grp["lr"],
+            ops.adamw_step(fp.data[a:b], fp.grad[a:b], m[a:b], v[a:b], self._step, grp["lr"],
                            grp["weight_decay"], grp["betas"][0], grp["betas"][1], grp["eps"])
         return loss
 
@@ -47,13 +55,55 @@ class FusedHFAdamW(torch.optim.Optimizer):
                 if set_to_none:
                     p.grad = None
 
+    # ------------------------------------------------------------------ checkpoints (transformers-AdamW layout)
+    def _indexed_names(self, fp):
+        """[(index in the param_groups numbering, flat-buffer name)] of the parameters this optimizer owns."""
+        by_ptr = {p.data_ptr(): n for n, p in fp.params.items()}
+        out, i = [], 0
+        for group in self.param_groups:
+            for p in group["params"]:
+                out.append((i, by_ptr.get(p.data_ptr())))
+                i += 1
+        return out
+
     def state_dict(self):
         sd = super().state_dict()
-        sd["flat_state"] = {"step": self._step, "m": self._m, "v": self._v}
+        state = {}
+        if self._m is not None and self._step > 0:
+            fp = self.flat_provider()
+            for i, name in self._indexed_names(fp):
+                if name is None or name in fp.frozen:
+                    continue  # never stepped: transformers' AdamW holds no state for it either
+                state[i] = {"step": self._step, "exp_avg": fp.view(self._m, name).clone(),
+                            "exp_avg_sq": fp.view(self._v, name).clone()}
+        sd["state"] = state
         return sd
 
     def load_state_dict(self, sd):
-        flat = sd.pop("flat_state", None)
+        sd = dict(sd)
+        flat = sd.pop("flat_state", None)  # round-1 checkpoints of this class
+        state = sd.get("state", {})
+        sd["state"] = {}
         super().load_state_dict(sd)
         if flat is not None:
             self._step, self._m, self._v = flat["step"], flat["m"], flat["v"]
+            return
+        if not state:
+            return
+        fp = self.flat_provider()
+        m, v = self._moments(fp)
+        m.zero_()
+        v.zero_()
+        steps = set()
+        for i, name in self._indexed_names(fp):
+            st = state.get(i, state.get(str(i)))
+            if st is None:
+                continue
+            if name is None:
+                raise RuntimeError("optimizer state for parameter %d cannot be mapped onto the flat buffers" % i)
+            fp.view(m, name).copy_(st["exp_avg"])
+            fp.view(v, name).copy_(st["exp_avg_sq"])
+            steps.add(int(st["step"]))
+        if len(steps) > 1:
+            raise RuntimeError("per-parameter step counts differ (%s): the fused kernel keeps one step count" % steps)
+        self._step = steps.pop() if steps else 0

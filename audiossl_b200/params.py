@@ -6,6 +6,10 @@ All parameters of a network live in ONE contiguous device buffer so that
   * the TF32 compute copy of the GEMM weights is one rounding pass.
 Segments: [regularised (>=2-D, non-bias) of encoder+projector | non-regularised of encoder+projector |
            regularised of predictor | non-regularised of predictor]   (utils/common.py:41-68 grouping).
+Tensors that never receive a gradient ("frozen": requires_grad=False, or ATST-clip's encoder.mask_embed, which the
+clip forward never reads - the reason the reference recipe needs find_unused_parameters, methods/atst/train.py:19)
+sit at the head of their segment and are excluded from the optimizer ranges and from the gradient exchange:
+transformers' AdamW skips a parameter whose .grad is None (no update, no weight decay), so must this.
 The nn.Parameters of the module tree are re-pointed at views of this buffer, so state_dict(),
 load_state_dict() and checkpoints keep the reference's key layout.
 """
@@ -19,24 +23,30 @@ def _is_regularized(name, p):
 
 
 class FlatParams:
-    def __init__(self, named_params, device, ema_prefixes=("encoder.", "projector.")):
-        """named_params: list of (name, nn.Parameter) in module order."""
+    def __init__(self, named_params, device, ema_prefixes=("encoder.", "projector."), frozen=()):
+        """named_params: list of (name, nn.Parameter) in module order; frozen: names that never get a gradient."""
+        self.frozen = frozenset(frozen)
         groups = [[], [], [], []]
         for name, p in named_params:
             in_ema = name.startswith(ema_prefixes)
             reg = _is_regularized(name, p)
             groups[(0 if in_ema else 2) + (0 if reg else 1)].append((name, p))
         self.offsets, self.shapes, self.order = {}, {}, []
-        self.seg_bounds = []
+        self.seg_bounds, self.seg_trainable = [], []
         off = 0
         for g in groups:
             start = off
+            g = [x for x in g if x[0] in self.frozen] + [x for x in g if x[0] not in self.frozen]
+            first_trainable = None
             for name, p in g:
+                if first_trainable is None and name not in self.frozen:
+                    first_trainable = off
                 self.offsets[name] = off
                 self.shapes[name] = tuple(p.shape)
                 self.order.append(name)
                 off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
             self.seg_bounds.append((start, off))
+            self.seg_trainable.append(off if first_trainable is None else first_trainable)
         self.total = off
         self.ema_count = self.seg_bounds[1][1]  # encoder+projector prefix of the buffer
         self.data = torch.zeros(self.total, device=device, dtype=torch.float32)
@@ -74,9 +84,12 @@ class FlatParams:
     def attach_grads(self):
         for name, p in self.params.items():
             if p.requires_grad:
-                p.grad = self.g(name)
+                p.grad = None if name in self.frozen else self.g(name)
 
     def wd_segments(self):
-        """[(start, end, regularised?)] for the fused optimizer."""
-        (a0, a1), (b0, b1), (c0, c1), (d0, d1) = self.seg_bounds
-        return [(a0, a1, True), (b0, b1, False), (c0, c1, True), (d0, d1, False)]
+        """[(start, end, regularised?)] for the fused optimizer: the trainable tail of every segment."""
+        return [(t, e, i % 2 == 0) for i, ((_, e), t) in enumerate(zip(self.seg_bounds, self.seg_trainable)) if e > t]
+
+    def exchanged_grad(self):
+        """the slice of the flat gradient that the data-parallel all-reduce carries (frozen head excluded)."""
+        return self.grad[self.seg_trainable[0]:] if self.seg_trainable[0] < self.seg_bounds[0][1] else self.grad

@@ -119,6 +119,125 @@ def mel_feature(wav, win_length=N_FFT, dtype=np.float32):
 
 
 # --------------------------------------------------------------------------------------
+# TF32 operand emulation (test infrastructure for the tcgen05 kind::tf32 kernels)
+# --------------------------------------------------------------------------------------
+# The CUDA path multiplies on the tensor cores with TF32 operands (fp32 containers, 10-bit mantissa, fp32
+# accumulation).  Its producers round every GEMM operand with ``cvt.rna.tf32.f32`` (nearest, ties away from zero).
+# A product of two TF32 numbers is exact in fp32, so an fp32 matmul of operands rounded the same way reproduces the
+# tensor-core result up to accumulation order.  Inside ``with tf32_emulation():`` the oracle rounds at exactly the
+# places the kernels do (DESIGN.md "Precision"):
+#   * every Linear: input, weight and - in the backward pass - the incoming gradient (dgrad and wgrad operands;
+#     bias gradients are column sums of the rounded gradient),
+#   * attention: Q, K, V (the qkv GEMM stores rounded values), the un-normalised probabilities exp(s - max) that
+#     multiply V, the stored output O, and in the backward pass dO, P, dS and the stored dQ / dK / dV.
+# Everything else (LayerNorm, softmax statistics, GELU, BatchNorm, loss, residual stream) stays fp32, as on the GPU.
+# With emulation off nothing below changes the reference arithmetic.
+_EMULATE_TF32 = False
+_EMULATE_HEADS = True
+
+
+class tf32_emulation:
+    """``heads=False`` leaves the projector / predictor Linears in fp32: the CUDA path runs those (< 0.1 % of the
+    flops) as error-compensated 3xTF32 products (hi/lo operand split), i.e. fp32 to ~1e-6."""
+
+    def __init__(self, on=True, heads=True):
+        self.on, self.heads = on, heads
+
+    def __enter__(self):
+        global _EMULATE_TF32, _EMULATE_HEADS
+        self.prev = (_EMULATE_TF32, _EMULATE_HEADS)
+        _EMULATE_TF32, _EMULATE_HEADS = self.on, self.heads
+
+    def __exit__(self, *exc):
+        global _EMULATE_TF32, _EMULATE_HEADS
+        _EMULATE_TF32, _EMULATE_HEADS = self.prev
+
+
+def rna_tf32(x):
+    """cvt.rna.tf32.f32 on an fp32 tensor: keep 10 mantissa bits, round to nearest, ties away from zero."""
+    i = x.detach().contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+class _LinearTF32(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b):
+        xr, wr = rna_tf32(x), rna_tf32(w)
+        ctx.save_for_backward(xr, wr)
+        ctx.has_bias = b is not None
+        y = xr @ wr.t()
+        return y + b if b is not None else y
+
+    @staticmethod
+    def backward(ctx, g):
+        xr, wr = ctx.saved_tensors
+        gr = rna_tf32(g)
+        g2, x2 = gr.reshape(-1, gr.shape[-1]), xr.reshape(-1, xr.shape[-1])
+        return gr @ wr, g2.t() @ x2, (g2.sum(0) if ctx.has_bias else None)
+
+
+def linear(x, w, b=None):
+    if _EMULATE_TF32:
+        return _LinearTF32.apply(x, w, b)
+    return F.linear(x, w, b)
+
+
+class OLinear(nn.Linear):
+    """Linear of the projector / predictor heads."""
+
+    def forward(self, x):
+        if _EMULATE_TF32 and not _EMULATE_HEADS:
+            return F.linear(x, self.weight, self.bias)
+        return linear(x, self.weight, self.bias)
+
+
+class _AttentionTF32(torch.autograd.Function):
+    """softmax(q k^T scale + key mask) v the way attention_tc.cu / attention_bwd_tc.cu compute it."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, scale, valid):
+        # q, k, v [B,H,N,d]; valid [B,1,1,N] bool (keys below the length)
+        q, k, v = rna_tf32(q), rna_tf32(k), rna_tf32(v)
+        s = q @ k.transpose(-2, -1)
+        m = s.masked_fill(~valid, -float("inf")).amax(-1, keepdim=True)
+        pu = torch.where(valid, torch.exp((s - m) * scale), torch.zeros(()))
+        l = pu.sum(-1, keepdim=True)
+        o = rna_tf32((rna_tf32(pu) @ v) * (1.0 / l))
+        ctx.save_for_backward(q, k, v, o, m * scale + torch.log(l), valid)
+        ctx.scale = scale
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        q, k, v, o, lse, valid = ctx.saved_tensors
+        d_o = rna_tf32(d_o)
+        p = torch.where(valid, torch.exp((q @ k.transpose(-2, -1)) * ctx.scale - lse), torch.zeros(()))
+        delta = (d_o * o).sum(-1, keepdim=True)
+        ds = rna_tf32(p * (d_o @ v.transpose(-2, -1) - delta))
+        dq = rna_tf32((ds @ k) * ctx.scale)
+        dk = rna_tf32((ds.transpose(-2, -1) @ q) * ctx.scale)
+        dv = rna_tf32(rna_tf32(p).transpose(-2, -1) @ d_o)
+        return dq, dk, dv, None, None
+
+
+def attention_core(q, k, v, scale, length):
+    """[B,H,N,d] x3 -> [B,H,N,d]; length [B] = number of valid keys (None: all) - modules/transformer.py:111-118."""
+    n_tok = q.shape[-2]
+    if _EMULATE_TF32:
+        if length is None:
+            valid = torch.ones((q.shape[0], 1, 1, n_tok), dtype=torch.bool)
+        else:
+            # a length <= 0 masks every key with the same -10000: the softmax is that of the unmasked row
+            ln = torch.where(length <= 0, torch.full_like(length, n_tok), length)
+            valid = (torch.arange(n_tok)[None, :] < ln[:, None])[:, None, None, :]
+        return _AttentionTF32.apply(q, k, v, scale, valid)
+    att = (q @ k.transpose(-2, -1)) * scale
+    if length is not None:
+        att = att + attention_mask(n_tok, length)
+    return att.softmax(dim=-1) @ v
+
+
+# --------------------------------------------------------------------------------------
 # transformer encoder (torch CPU fp32)
 # --------------------------------------------------------------------------------------
 def _trunc_normal_(t, std=0.02):
@@ -148,18 +267,15 @@ class OracleBlock(nn.Module):
         """dp_scale: optional ([B] attn-branch scale, [B] mlp-branch scale) = mask/keep_prob."""
         B, N, C = x.shape
         h = self.norm1(x)
-        qkv = self.attn.qkv(h).reshape(B, N, 3, self.heads, C // self.heads).permute(2, 0, 3, 1, 4)
-        q, k, v = qkv[0], qkv[1], qkv[2]
-        att = (q @ k.transpose(-2, -1)) * ((C // self.heads) ** -0.5)
-        if length is not None:
-            att = att + attention_mask(N, length)
-        att = att.softmax(dim=-1)
-        y = (att @ v).transpose(1, 2).reshape(B, N, C)
-        y = self.attn.proj(y)
+        qkv = linear(h, self.attn.qkv.weight).reshape(B, N, 3, self.heads, C // self.heads).permute(2, 0, 3, 1, 4)
+        y = attention_core(qkv[0], qkv[1], qkv[2], (C // self.heads) ** -0.5, length)
+        y = y.transpose(1, 2).reshape(B, N, C)
+        y = linear(y, self.attn.proj.weight, self.attn.proj.bias)
         if dp_scale is not None:
             y = y * dp_scale[0][:, None, None]
         x = x + y
-        z = self.mlp.fc2(F.gelu(self.mlp.fc1(self.norm2(x))))
+        z = linear(F.gelu(linear(self.norm2(x), self.mlp.fc1.weight, self.mlp.fc1.bias)), self.mlp.fc2.weight,
+                   self.mlp.fc2.bias)
         if dp_scale is not None:
             z = z * dp_scale[1][:, None, None]
         return x + z
@@ -202,7 +318,8 @@ class OracleAST(nn.Module):
         return x
 
     def tokens(self, mel, length, mask_index=None, mask=True):
-        x = self.patch_embed.patch_embed(self.patchify(mel))
+        pe = self.patch_embed.patch_embed
+        x = linear(self.patchify(mel), pe.weight, pe.bias)
         B, T, C = x.shape
         plen = None
         if length is not None:
@@ -277,8 +394,8 @@ def oracle_log_mixup_exp(x, z, alpha):
 
 
 def build_mlp(in_dim, hidden, out_dim):
-    return nn.Sequential(nn.Linear(in_dim, hidden, bias=False), nn.BatchNorm1d(hidden),
-                         nn.ReLU(inplace=True), nn.Linear(hidden, out_dim, bias=False))
+    return nn.Sequential(OLinear(in_dim, hidden, bias=False), nn.BatchNorm1d(hidden),
+                         nn.ReLU(inplace=True), OLinear(hidden, out_dim, bias=False))
 
 
 class OracleMultiCrop(nn.Module):

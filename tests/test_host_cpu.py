@@ -164,3 +164,58 @@ def test_distributed_helpers_gloo_world2(tmp_path):
                        capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_frozen_tensors_are_outside_the_optimizer_and_exchange_ranges():
+    """ATST-clip never reads encoder.mask_embed: the reference's AdamW skips it (grad is None), so the flat layout
+    keeps it out of the fused-optimizer segments and out of the all-reduced gradient slice; the teacher keeps the
+    same prefix layout for the EMA."""
+    from audiossl_b200.models.atst import ATST
+    from audiossl_b200.params import FlatParams
+    m = ATST(arch=dict(embed_dim=128, depth=2, num_heads=2))
+    m.student.projector[1].bias.requires_grad = False
+    frozen = {"encoder.mask_embed", "projector.1.bias"}
+    fs = FlatParams(list(m.student.named_parameters()), torch.device("cpu"), frozen=frozen)
+    ft = FlatParams(list(m.teacher.named_parameters()), torch.device("cpu"), frozen=frozen)
+    assert ft.total == fs.ema_count and ft.order == fs.order[:len(ft.order)]
+    segs = fs.wd_segments()
+    assert len(segs) == 4
+
+    def covered(name):
+        return any(a <= fs.offsets[name] < b for a, b, _ in segs)
+    assert not covered("encoder.mask_embed") and not covered("projector.1.bias")
+    assert all(covered(n) for n in fs.order if n not in frozen)
+    assert fs.offsets["encoder.mask_embed"] == 0
+    ex = fs.exchanged_grad()
+    assert ex.numel() == fs.total - 128 and ex.data_ptr() == fs.grad.data_ptr() + 4 * 128
+    fs.attach_grads()
+    assert m.student.encoder.mask_embed.grad is None and m.student.encoder.cls_token.grad is not None
+    assert m.student.projector[1].bias.grad is None
+
+
+def test_optimizer_checkpoint_uses_the_transformers_adamw_layout():
+    """state_dict()['state'][i] = {step, exp_avg, exp_avg_sq} per stepped parameter (what transformers' AdamW saves),
+    and such a checkpoint loads back into the flat moment buffers."""
+    from audiossl_b200.models.atst import ATST
+    from audiossl_b200.optim import FusedHFAdamW
+    from audiossl_b200.params import FlatParams
+    from audiossl_b200.utils.common import get_params_groups
+    m = ATST(arch=dict(embed_dim=128, depth=1, num_heads=2))
+    fs = FlatParams(list(m.student.named_parameters()), torch.device("cpu"), frozen={"encoder.mask_embed"})
+    opt = FusedHFAdamW(get_params_groups(m.student), flat=lambda: fs, lr=1e-3)
+    params = [p for g in opt.param_groups for p in g["params"]]
+    ref_state = {i: {"step": 7, "exp_avg": torch.full_like(p, 0.5 + i), "exp_avg_sq": torch.full_like(p, 2.0 + i)}
+                 for i, p in enumerate(params) if p is not m.student.encoder.mask_embed}
+    sd = {"state": ref_state, "param_groups": opt.state_dict()["param_groups"]}
+    keep = dict(sd)
+    opt.load_state_dict(sd)
+    assert sd.keys() == keep.keys()  # the caller's dict is not modified
+    assert opt._step == 7
+    out = opt.state_dict()["state"]
+    assert set(out) == set(ref_state)
+    for i in ref_state:
+        assert torch.equal(out[i]["exp_avg"], ref_state[i]["exp_avg"])
+        assert torch.equal(out[i]["exp_avg_sq"], ref_state[i]["exp_avg_sq"])
+    name = "encoder.blocks.0.mlp.fc1.weight"
+    i = [k for k, p in enumerate(params) if p is m.student.encoder.blocks[0].mlp.fc1.weight][0]
+    assert torch.equal(fs.view(opt._m, name), ref_state[i]["exp_avg"])
