@@ -10,6 +10,9 @@ from ctypes import c_char_p, c_float, c_int, c_longlong, c_uint, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libatst_b200.so")
+# variants of the same sources (audiossl_b200/build.py): "" = the product (TF32 tcgen05 path), "precise" = 3xTF32
+# validation build (fp32-equivalent products, audiossl_b200.set_precision), "debug" = bring-up entry points
+VARIANT_FILES = {"": "libatst_b200.so", "precise": "libatst_b200_precise.so", "debug": "libatst_b200_debug.so"}
 
 P, I, L, F, U = c_void_p, c_int, c_longlong, c_float, c_uint
 
@@ -22,15 +25,10 @@ SIGNATURES = {
     "atst_gemm_nt": [P, I, P, I, P, I, I, I, I, P, I, P, I, P, I, P, I, I, P],
     "atst_gemm_nn": [P, I, P, I, P, I, I, I, I, I, P, I, P, I, I, P, P],
     "atst_gemm_tn": [P, I, P, I, P, I, I, I, I, P],
-    "atst_gemm_mn_debug": [I, P, I, P, I, P, I, I, I, I, U, U, U, U, I, I, P],
-    "atst_umma_probe": [I, P, P, P, U, U, U, U, P],
     "atst_layernorm_forward": [P, L, P, P, P, L, P, P, I, I, F, I, P],
     "atst_layernorm_backward": [P, L, P, L, P, P, P, P, L, P, L, P, P, I, I, P, L, P, I, P, P],
     "atst_attention_forward": [P, P, P, P, I, I, I, P],
     "atst_attention_backward": [P, P, P, P, P, P, P, I, I, I, P],
-    "atst_gemm_trace": [P],
-    "atst_copy_pattern": [P, P, I, I, I, P],
-    "atst_attention_trace": [P, I, I],
     "atst_patchify": [P, L, I, I, P, P],
     "atst_tokens_forward": [P, P, P, P, P, P, I, I, I, I, P],
     "atst_tokens_backward": [P, P, P, P, P, P, I, I, I, I, P],
@@ -51,42 +49,74 @@ SIGNATURES = {
     "atst_gelu_forward": [P, P, L, P],
     "atst_gelu_backward": [P, P, I, I, P, P],
     "atst_round_tf32": [P, P, L, P],
+    "atst_is_precise": [],
+    "atst_split_tf32": [P, L, I, I, P, I, I, P],
     "atst_axpy": [P, P, F, L, P],
 }
 
-_lib = None
-_inited = False
+# bring-up entry points (include/atst_b200_debug.h), present in the "debug" variant only
+DEBUG_SIGNATURES = {
+    "atst_gemm_mn_debug": [I, P, I, P, I, P, I, I, I, I, U, U, U, U, I, I, P],
+    "atst_umma_probe": [I, P, P, P, U, U, U, U, P],
+    "atst_gemm_trace": [P],
+    "atst_copy_pattern": [P, P, I, I, I, P],
+    "atst_attention_trace": [P, I, I],
+}
+
+_libs = {}
+_inited = set()
+_variant = os.environ.get("ATST_LIB_VARIANT", "")
 
 
-def load():
-    """dlopen the library and declare signatures (no GPU needed)."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
+def set_variant(name):
+    """select the library the compute calls go to ("" product, "precise", "debug"); returns the previous one"""
+    global _variant
+    if name not in VARIANT_FILES:
+        raise ValueError("unknown library variant %r" % (name,))
+    prev, _variant = _variant, name
+    return prev
+
+
+def variant():
+    return _variant
+
+
+def load(name=None):
+    """dlopen a library variant and declare signatures (no GPU needed)."""
+    name = _variant if name is None else name
+    if name in _libs:
+        return _libs[name]
+    path = os.path.join(_HERE, VARIANT_FILES[name])
+    if not os.path.exists(path):
         raise RuntimeError("%s not found: run `python -m audiossl_b200.build` (nvcc, sm_100a). "
-                           "There is no CPU fallback." % LIB_PATH)
-    lib = ctypes.CDLL(LIB_PATH)
-    for name, args in SIGNATURES.items():
-        fn = getattr(lib, name)
+                           "There is no CPU fallback." % path)
+    lib = ctypes.CDLL(path)
+    sigs = dict(SIGNATURES)
+    if name == "debug":
+        sigs.update(DEBUG_SIGNATURES)
+    for fn_name, args in sigs.items():
+        fn = getattr(lib, fn_name)
         fn.argtypes = args
         fn.restype = c_int
     lib.atst_last_error.argtypes = []
     lib.atst_last_error.restype = c_char_p
-    _lib = lib
+    _libs[name] = lib
     return lib
 
 
 def lib():
-    """library handle for compute calls: checks the device once."""
-    global _inited
+    """library handle for compute calls: checks the device once per variant."""
     l = load()
-    if not _inited:
+    if _variant not in _inited:
         rc = l.atst_init()
         if rc != 0:
             raise RuntimeError("atst_init failed (%d): %s" % (rc, l.atst_last_error().decode()))
-        _inited = True
+        _inited.add(_variant)
     return l
+
+
+def is_precise():
+    return _variant == "precise"
 
 
 def check(rc, what=""):

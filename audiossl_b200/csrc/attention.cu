@@ -43,6 +43,30 @@ __device__ __forceinline__ uint32_t tf32_bits(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return r;
 }
+// One m16n8k8 product step on fp32 fragment values.
+//  default build: A_ROUNDED operands arrive TF32-rounded from their producer (bits pass through), others are rounded
+//                 here (the probabilities / dS);
+//  -DATST_PRECISE: every operand is split x = hi + lo (hi = tf32(x), lo = tf32(x - hi)) and the product is taken
+//                 as lo*hi + hi*lo + hi*hi (3xTF32, error ~2^-21 relative: fp32-equivalent).
+template <bool A_ROUNDED>
+__device__ __forceinline__ void mma_f(float (&c)[4], float a0, float a1, float a2, float a3, float b0, float b1) {
+#ifdef ATST_PRECISE
+  const uint32_t ah0 = tf32_bits(a0), ah1 = tf32_bits(a1), ah2 = tf32_bits(a2), ah3 = tf32_bits(a3);
+  const uint32_t bh0 = tf32_bits(b0), bh1 = tf32_bits(b1);
+  const uint32_t al0 = tf32_bits(a0 - __uint_as_float(ah0)), al1 = tf32_bits(a1 - __uint_as_float(ah1));
+  const uint32_t al2 = tf32_bits(a2 - __uint_as_float(ah2)), al3 = tf32_bits(a3 - __uint_as_float(ah3));
+  const uint32_t bl0 = tf32_bits(b0 - __uint_as_float(bh0)), bl1 = tf32_bits(b1 - __uint_as_float(bh1));
+  mma_tf32(c, al0, al1, al2, al3, bh0, bh1);
+  mma_tf32(c, ah0, ah1, ah2, ah3, bl0, bl1);
+  mma_tf32(c, ah0, ah1, ah2, ah3, bh0, bh1);
+#else
+  if (A_ROUNDED)
+    mma_tf32(c, __float_as_uint(a0), __float_as_uint(a1), __float_as_uint(a2), __float_as_uint(a3), __float_as_uint(b0),
+             __float_as_uint(b1));
+  else
+    mma_tf32(c, tf32_bits(a0), tf32_bits(a1), tf32_bits(a2), tf32_bits(a3), __float_as_uint(b0), __float_as_uint(b1));
+#endif
+}
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
   const int sz = valid ? 16 : 0;  // src-size 0 => zero fill
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem)), "l"(gmem), "r"(sz) : "memory");
@@ -85,12 +109,10 @@ __device__ __forceinline__ void mma_abt(float (&acc)[8][4], const float* R, int 
     // two passes over the 8 independent accumulators: a dependent mma pair is always 8 issues apart
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
-      mma_tf32(acc[nt], __float_as_uint(x0.x), __float_as_uint(x1.x), __float_as_uint(x0.y), __float_as_uint(x1.y),
-               __float_as_uint(y[nt].x), __float_as_uint(y[nt].y));
+      mma_f<true>(acc[nt], x0.x, x1.x, x0.y, x1.y, y[nt].x, y[nt].y);
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
-      mma_tf32(acc[nt], __float_as_uint(x0.z), __float_as_uint(x1.z), __float_as_uint(x0.w), __float_as_uint(x1.w),
-               __float_as_uint(y[nt].z), __float_as_uint(y[nt].w));
+      mma_f<true>(acc[nt], x0.z, x1.z, x0.w, x1.w, y[nt].z, y[nt].w);
   }
 }
 // acc[dt] += P(16 x 64, C-fragment layout, columns = rows of Y) . Y(64 x 64)
@@ -101,19 +123,18 @@ __device__ __forceinline__ void mma_abt(float (&acc)[8][4], const float* R, int 
 __device__ __forceinline__ void mma_py(float (&acc)[8][4], const float (&P)[8][4], const float* Y, int g, int t) {
 #pragma unroll
   for (int ks = 0; ks < 8; ++ks) {
-    const uint32_t a0 = tf32_bits(P[ks][0]), a1 = tf32_bits(P[ks][2]);
-    const uint32_t a2 = tf32_bits(P[ks][1]), a3 = tf32_bits(P[ks][3]);
+    const float a0 = P[ks][0], a1 = P[ks][2], a2 = P[ks][1], a3 = P[ks][3];
     const int r = 8 * ks + 2 * t;
     const float4 u0 = ld4(Y, r, 2 * g), u1 = ld4(Y, r, 2 * g + 1);
     const float4 v0 = ld4(Y, r + 1, 2 * g), v1 = ld4(Y, r + 1, 2 * g + 1);
-    mma_tf32(acc[0], a0, a1, a2, a3, __float_as_uint(u0.x), __float_as_uint(v0.x));
-    mma_tf32(acc[1], a0, a1, a2, a3, __float_as_uint(u0.y), __float_as_uint(v0.y));
-    mma_tf32(acc[2], a0, a1, a2, a3, __float_as_uint(u0.z), __float_as_uint(v0.z));
-    mma_tf32(acc[3], a0, a1, a2, a3, __float_as_uint(u0.w), __float_as_uint(v0.w));
-    mma_tf32(acc[4], a0, a1, a2, a3, __float_as_uint(u1.x), __float_as_uint(v1.x));
-    mma_tf32(acc[5], a0, a1, a2, a3, __float_as_uint(u1.y), __float_as_uint(v1.y));
-    mma_tf32(acc[6], a0, a1, a2, a3, __float_as_uint(u1.z), __float_as_uint(v1.z));
-    mma_tf32(acc[7], a0, a1, a2, a3, __float_as_uint(u1.w), __float_as_uint(v1.w));
+    mma_f<false>(acc[0], a0, a1, a2, a3, u0.x, v0.x);
+    mma_f<false>(acc[1], a0, a1, a2, a3, u0.y, v0.y);
+    mma_f<false>(acc[2], a0, a1, a2, a3, u0.z, v0.z);
+    mma_f<false>(acc[3], a0, a1, a2, a3, u0.w, v0.w);
+    mma_f<false>(acc[4], a0, a1, a2, a3, u1.x, v1.x);
+    mma_f<false>(acc[5], a0, a1, a2, a3, u1.y, v1.y);
+    mma_f<false>(acc[6], a0, a1, a2, a3, u1.z, v1.z);
+    mma_f<false>(acc[7], a0, a1, a2, a3, u1.w, v1.w);
   }
 }
 // store the permuted accumulator of mma_py: row `row`, 16 contiguous columns starting at 16t
@@ -358,7 +379,9 @@ int attention_delta(const float* o, const float* d_o, float* delta, int S, int N
 int attention_forward(const float* qkv, float* o, float* lse, const int* lengths, int S, int N, int H,
                       cudaStream_t stream) {
   ATST_REQUIRE(S > 0 && N > 0 && H > 0, "attention_forward: bad shape S=%d N=%d H=%d", S, N, H);
+#ifndef ATST_PRECISE  // the validation build stays on these mma.sync kernels (in-register 3xTF32 splits)
   if ((attention_tc_enabled() & 1) && N <= 256) return attention_forward_tc(qkv, o, lse, lengths, S, N, H, stream);
+#endif
   AttnParams p{};
   p.qkv = qkv; p.out_o = o; p.lse = lse; p.lengths = lengths;
   p.N = N; p.H = H; p.D = H * kHd; p.scale = 0.125f;
@@ -368,8 +391,10 @@ int attention_forward(const float* qkv, float* o, float* lse, const int* lengths
 int attention_backward(const float* qkv, const float* o, const float* d_o, const float* lse, float* delta_ws,
                        float* dqkv, const int* lengths, int S, int N, int H, cudaStream_t stream) {
   ATST_REQUIRE(S > 0 && N > 0 && H > 0, "attention_backward: bad shape S=%d N=%d H=%d", S, N, H);
+#ifndef ATST_PRECISE
   if ((attention_tc_enabled() & 2) && N <= 256)
     return attention_backward_tc(qkv, o, d_o, lse, delta_ws, dqkv, lengths, S, N, H, stream);
+#endif
   const int D = H * kHd;
   int rc = attention_delta(o, d_o, delta_ws, S, N, H, stream);
   if (rc) return rc;

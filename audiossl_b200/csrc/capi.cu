@@ -1,5 +1,8 @@
 // extern "C" surface declared in include/atst_b200.h: thin forwarding to the launchers.
 #include "../../include/atst_b200.h"
+#ifdef ATST_DEBUG_ABI
+#include "../../include/atst_b200_debug.h"
+#endif
 #include "common.cuh"
 #include "gemm.h"
 #include "ops.h"
@@ -10,9 +13,11 @@ void attention_set_tc(int on);
 void attention_set_l2_prefetch(int on);
 void attention_set_trace(long long* buf, int seq, int mode);
 void gemm_set_trace(long long* buf);
+#ifdef ATST_DEBUG_ABI
 int copy_pattern(const float* src, float* dst, int rows, int cols, int mode, cudaStream_t stream);
 int umma_probe(int mode, const float* A, const float* B, float* D, unsigned layout, unsigned lbo, unsigned sbo,
                unsigned kstep, cudaStream_t stream);
+#endif
 }
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 using namespace atst;
@@ -83,6 +88,7 @@ int atst_gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int
   return gemm_tn(A, lda, B, ldb, T, p, ST(stream));
 }
 
+#ifdef ATST_DEBUG_ABI  // bring-up entry points: libatst_b200_debug.so only (include/atst_b200_debug.h)
 int atst_gemm_mn_debug(int nn, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K,
                        unsigned lbo, unsigned sbo, unsigned kstep, unsigned layout, int tma_swizzle, int splits,
                        void* stream) {
@@ -110,6 +116,7 @@ int atst_attention_trace(long long* buf, int seq, int mode) {
   attention_set_trace(buf, seq, mode);
   return ATST_OK;
 }
+#endif
 
 int atst_layernorm_forward(const float* x, long long x_stride, const float* gamma, const float* beta, float* y,
                            long long y_stride, float* mean, float* rstd, int rows, int D, float eps, int round_out,
@@ -202,6 +209,17 @@ int atst_gelu_backward(float* d, const float* u, int rows, int cols, float* cols
 }
 int atst_round_tf32(const float* src, float* dst, long long n, void* stream) {
   return round_tf32_copy(src, dst, n, ST(stream));
+}
+int atst_is_precise(void) {
+#ifdef ATST_PRECISE
+  return 1;
+#else
+  return 0;
+#endif
+}
+int atst_split_tf32(const float* src, long long ld, int rows, int cols, float* dst, int pattern, int along_rows,
+                    void* stream) {
+  return split_tf32(src, ld, rows, cols, dst, pattern, along_rows, ST(stream));
 }
 int atst_axpy(float* y, const float* x, float a, long long n, void* stream) { return axpy(y, x, a, n, ST(stream)); }
 

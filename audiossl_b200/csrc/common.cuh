@@ -27,10 +27,23 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
-__device__ __forceinline__ float round_tf32(float x) {
+// cvt.rna.tf32.f32: 10 mantissa bits, nearest, ties away from zero
+__device__ __forceinline__ float cvt_rna_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
+}
+// What a producer applies to a value it hands to a tensor-core product.  Default build: round to TF32.  The
+// validation build (-DATST_PRECISE, libatst_b200_precise.so) keeps fp32 here: its products are error-compensated
+// 3xTF32 (hi/lo operand split: K-concatenated operands for the GEMMs, in-register splits in attention.cu), i.e.
+// the same kernels and the same engine at fp32 accuracy - what tests/test_parity_precise_gpu.py compares with the
+// fp32 reference vectors at tight tolerance.
+__device__ __forceinline__ float round_tf32(float x) {
+#ifdef ATST_PRECISE
+  return x;
+#else
+  return cvt_rna_tf32(x);
+#endif
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -364,6 +364,32 @@ __global__ void round_tf32_kernel(const float* __restrict__ src, float* __restri
   }
 }
 
+// 3xTF32 operand split (validation build's GEMMs): dst block b of element (r, c) = part[b] of src[r, c], where
+// x = hi + lo, hi = tf32(x), lo = tf32(x - hi); parts = {hi, lo, hi} (pattern 0) or {hi, hi, lo} (pattern 1)
+__global__ void split_tf32_kernel(const float* __restrict__ src, long long ld, int rows, int cols,
+                                  float* __restrict__ dst, int pattern, int along_rows) {
+  const long long total = static_cast<long long>(rows) * cols;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cols;
+    const int c = static_cast<int>(i - r * cols);
+    const float x = src[r * ld + c];
+    const float hi = cvt_rna_tf32(x);
+    const float lo = cvt_rna_tf32(x - hi);
+    const float p1 = pattern == 0 ? lo : hi, p2 = pattern == 0 ? hi : lo;
+    if (along_rows) {
+      dst[i] = hi;
+      dst[total + i] = p1;
+      dst[2 * total + i] = p2;
+    } else {
+      float* d = dst + r * 3LL * cols + c;
+      d[0] = hi;
+      d[cols] = p1;
+      d[2 * cols] = p2;
+    }
+  }
+}
+
 __global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, float a, long long n) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
@@ -479,6 +505,13 @@ int round_tf32_copy(const float* src, float* dst, long long n, cudaStream_t st) 
   ATST_REQUIRE(n % 4 == 0, "round_tf32_copy: n %% 4 != 0");
   round_tf32_kernel<<<grid_for(n / 4), 256, 0, st>>>(src, dst, n / 4);
   return atst_check_launch("round_tf32_kernel");
+}
+int split_tf32(const float* src, long long ld, int rows, int cols, float* dst, int pattern, int along_rows,
+               cudaStream_t st) {
+  ATST_REQUIRE(rows > 0 && cols > 0 && ld >= cols && (pattern == 0 || pattern == 1), "split_tf32: bad arguments");
+  split_tf32_kernel<<<grid_for(static_cast<long long>(rows) * cols), 256, 0, st>>>(src, ld, rows, cols, dst, pattern,
+                                                                                     along_rows);
+  return atst_check_launch("split_tf32_kernel");
 }
 int axpy(float* y, const float* x, float a, long long n, cudaStream_t st) {
   axpy_kernel<<<grid_for(n), 256, 0, st>>>(y, x, a, n);

@@ -40,6 +40,8 @@ int scatter_rows(const float* src, const int* idx, float* dst, int rows, int D, 
 int gelu_forward(const float* u, float* g, long long n, cudaStream_t st);
 int gelu_backward(float* d, const float* u, int rows, int cols, float* colsum_out, cudaStream_t st);
 int round_tf32_copy(const float* src, float* dst, long long n, cudaStream_t st);
+int split_tf32(const float* src, long long ld, int rows, int cols, float* dst, int pattern, int along_rows,
+               cudaStream_t st);
 int axpy(float* y, const float* x, float a, long long n, cudaStream_t st);
 int byol_loss(const float* student, const float* teacher, int ncrops, int B, float* dstudent, float* acc_ws,
               cudaStream_t st);

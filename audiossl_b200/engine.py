@@ -69,7 +69,10 @@ class EncoderEngine:
         self.D, self.depth, self.H = embed_dim, depth, num_heads
         self.use_cls, self.norm_name, self.px = use_cls, norm_name, prefix
         self.patch_w, self.max_frames = patch_w, max_frames
-        self.debug = None  # bring-up aid: list collecting (name, layer, tensor clone) during backward
+        # test hook (tests/linkwise.py): a list that collects (name, tag, layer, tensor clone) at every block boundary
+        # of the forward and backward passes, so each link of the chain can be checked against the CPU reference from the
+        # GPU's own inputs to that link
+        self.debug = None
 
     # ------------------------------------------------------------------ forward
     def forward(self, fp, ws, mel, lengths, dp=None, save=True, tag="s", mask=None, mask_input=True, collect=0,
@@ -103,8 +106,10 @@ class EncoderEngine:
                            mask=m8 if mask_input else None, out=t("x0", (M, D)))
         ctx = {"S": S, "P": P, "N": N, "M": M, "key_len": key_len, "dp": dp, "tag": tag, "layers": [],
                "patches": patches, "mask": m8 if mask_input else None}
+        dbg = (lambda name, i, t_: self.debug.append((name, tag, i, t_.clone()))) if self.debug is not None else (lambda *a: None)
         for i in range(self.depth):
             b = "%sblocks.%d." % (px, i)
+            dbg("x_in", i, x)
             lt = (lambda name, shape, i=i: ws.get("%s/L%d/%s" % (tag, i if save else 0, name), shape))
             h, mean1, rstd1 = self._ln(x, fp.p(b + "norm1.weight"), fp.p(b + "norm1.bias"), M, lt("h", (M, D)),
                                        lt("mean1", (M,)), lt("rstd1", (M,)))
@@ -155,6 +160,8 @@ class EncoderEngine:
             rstd = t("rstdf", (M,))
             self._ln(x, fp.p(nm + ".weight"), fp.p(nm + ".bias"), M, out, mean, rstd)
         ctx["meanf"], ctx["rstdf"] = mean, rstd
+        dbg("x_in", self.depth, x)
+        dbg("enc_out", self.depth, out)
         return out, ctx
 
     def _ln(self, x, g, b, rows, out, mean, rstd):
@@ -190,8 +197,9 @@ class EncoderEngine:
                               fp.g(nm + ".weight"), fp.g(nm + ".bias"), M, D, dx=dxa, dys=dys,
                               rowscale=scales[last][1], rows_per_seq=N, colsum_out=fp.g(blk(last) + "mlp.fc2.bias"))
         dx, other = dxa, dxb
-        dbg = (lambda name, i, t_: self.debug.append((name, i, t_.clone()))) if self.debug is not None else (lambda *a: None)
-        dbg("dx_out", self.depth, dx)
+        dbg = (lambda name, i, t_: self.debug.append((name, tag, i, t_.clone()))) if self.debug is not None else (lambda *a: None)
+        dbg("d_enc_out", self.depth, d_out)
+        dbg("dx_in", self.depth, dx)
         for i in reversed(range(self.depth)):
             b = blk(i)
             L = ctx["layers"][i]

@@ -33,6 +33,8 @@ class _FrameRuntime(_Runtime):
             dp = droppath_scales(enc.depth, enc.drop_path_rate, mel.shape[0], mel.device)
         xn, ctx = self.enc.forward(fp, self.ws, mel, ln, dp=dp, save=save, tag=tag, mask=mask, mask_input=mask_input)
         rows = ops.gather_rows(xn, idx, self.ws.get(tag + "/rows", (idx.numel(), self.enc.D)))
+        if self.enc.debug is not None:
+            self.enc.debug.append(("heads_in", tag, -1, rows.clone()))
         return rows, ctx
 
     def step(self, crops, lengths, masks):
@@ -85,6 +87,8 @@ class _FrameRuntime(_Runtime):
         dz = self.pred.backward(fs, self.ws, pred_ctx, d, need_dx=True, sums_sync=sums)
         ops.round_tf32(dz, dz)
         drows = self.proj.backward(fs, self.ws, proj_ctx, dz, need_dx=True, sums_sync=sums)
+        if self.enc.debug is not None:
+            self.enc.debug.append(("d_heads_in", "s", -1, drows.clone()))
         dxn = self.ws.get("s0/bwd/dxn", (enc_ctx["M"], self.enc.D))
         dxn.zero_()
         ops.scatter_rows(drows, idx, dxn)

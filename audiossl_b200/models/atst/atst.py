@@ -132,6 +132,8 @@ class _Runtime:
         dz = self.pred.backward(fs, self.ws, pred_ctx, d, need_dx=True, sums_sync=sums)
         ops.round_tf32(dz, dz)
         dcls = self.proj.backward(fs, self.ws, proj_ctx, dz, need_dx=True, sums_sync=sums)
+        if self.enc.debug is not None:
+            self.enc.debug.append(("d_heads_in", "s", -1, dcls.clone()))
         row = 0
         for ctx in enc_ctxs:
             S = ctx["S"]

@@ -58,6 +58,19 @@ def _count(n):
     STATS["launches"] += n
 
 
+def _split3(x, pattern, along_rows):
+    """3xTF32 validation build: hi/lo split of a GEMM operand, the three parts laid side by side (or stacked) so
+    that ONE pass of the unchanged GEMM kernel over the tripled contraction dimension accumulates
+    hi*hi + lo*hi + hi*lo in fp32 (include/atst_b200.h atst_split_tf32)."""
+    rows, cols = x.shape
+    assert x.stride(1) == 1
+    out = torch.empty((3 * rows, cols) if along_rows else (rows, 3 * cols), device=x.device, dtype=torch.float32)
+    check(_lib.lib().atst_split_tf32(ptr(x), x.stride(0), rows, cols, ptr(out), pattern, 1 if along_rows else 0,
+                                     _lib.stream()), "atst_split_tf32")
+    _count(1)
+    return out
+
+
 def _f32c(t, name):
     if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
         raise ValueError("%s must be a contiguous fp32 CUDA tensor" % name)
@@ -88,6 +101,8 @@ def gemm_nt(A, B, bias=None, epi=EPI_STORE, resid=None, aux=None, rowscale=None,
     assert B.shape[1] == K
     if out is None:
         out = torch.empty((M, N), device=A.device, dtype=torch.float32)
+    if _lib.is_precise():
+        A, B, K = _split3(A, 0, False), _split3(B, 1, False), 3 * K
     _t = _GemmTimer(2.0 * M * N * K, "nt %dx%dx%d e%d" % (M, N, K, epi),
                    4.0 * (M * K + N * K + M * N * (1 + (resid is not None) + (aux is not None))))
     check(_lib.lib().atst_gemm_nt(ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(out), out.stride(0), M, N, K,
@@ -106,6 +121,8 @@ def gemm_nn(A, W, epi=EPI_STORE, aux=None, rowscale=None, rows_per_seq=1, round_
     assert W.shape[0] == K
     if out is None:
         out = torch.empty((M, N), device=A.device, dtype=torch.float32)
+    if _lib.is_precise():
+        A, W, K = _split3(A, 0, False), _split3(W, 1, True), 3 * K
     _t = _GemmTimer(2.0 * M * N * K, "nn %dx%dx%d e%d" % (M, N, K, epi), 4.0 * (M * K + N * K + M * N * (1 + (aux is not None))))
     check(_lib.lib().atst_gemm_nn(ptr(A), A.stride(0), ptr(W), W.stride(0), ptr(out), out.stride(0), M, N, K, epi,
                                   ptr(aux), aux.stride(0) if aux is not None else 0, ptr(rowscale), rows_per_seq,
@@ -119,6 +136,8 @@ def gemm_tn_acc(A, B, out):
     T, M = A.shape
     N = B.shape[1]
     assert B.shape[0] == T and tuple(out.shape) == (M, N)
+    if _lib.is_precise():
+        A, B, T = _split3(A, 0, True), _split3(B, 1, True), 3 * T
     _t = _GemmTimer(2.0 * M * N * T, "tn %dx%dx%d" % (M, N, T), 4.0 * (T * M + T * N + M * N))
     check(_lib.lib().atst_gemm_tn(ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(out), out.stride(0), M, N, T,
                                   _lib.stream()), "atst_gemm_tn")

