@@ -42,7 +42,7 @@ SIGNATURES = {
     "atst_byol_finalize": [P, F, F, I, I, P, P],
     "atst_ema_update": [P, P, F, L, P],
     "atst_adamw_step": [P, P, P, P, L, I, F, F, F, F, F, F, P],
-    "atst_mixup_forward": [P, P, P, P, P, L, I, P],
+    "atst_mixup_forward": [P, I, P, I, P, P, P, P, P, I, I, P],
     "atst_resize_crop_forward": [P, P, P, I, I, I, I, I, P],
     "atst_gather_rows": [P, P, P, I, I, P],
     "atst_scatter_rows": [P, P, P, I, I, P],

@@ -9,19 +9,36 @@
 
 namespace atst {
 
-// out[b] = log((1 - a_b) * exp(x[b]) + a_b * exp(bank[idx_b]) + eps); idx_b < 0 => out = x (empty bank)
-__global__ void mixup_kernel(const float* __restrict__ x, const float* __restrict__ bank, const int* __restrict__ idx,
-                             const float* __restrict__ alpha, float* __restrict__ out, long long per_clip, int B) {
+// out[b] = log((1 - a_b) * exp(x[b]) + a_b * exp(z_b) + eps), z_b = bank entry idx_b; idx_b < 0 => out = x (empty bank).
+// x [B, Hm, x_T]; bank entries are [Hm, bank_T] with zlen_b valid frames.  Length mismatch as log_mixup_exp
+// (byol_a.py:61-82): a longer z is read from the window [start_b, start_b + x_T); a shorter z is mixed into the window
+// [start_b, start_b + zlen_b) of x and the frames outside it become log(exp(x) + eps).
+__global__ void mixup_kernel(const float* __restrict__ x, int x_T, const float* __restrict__ bank, int bank_T,
+                             const int* __restrict__ idx, const int* __restrict__ zlen, const int* __restrict__ start,
+                             const float* __restrict__ alpha, float* __restrict__ out, int Hm, int B) {
   const int b = blockIdx.y;
   const int j = idx[b];
   const float a = alpha[b];
-  const float* xb = x + static_cast<long long>(b) * per_clip;
-  const float* zb = j >= 0 ? bank + static_cast<long long>(j) * per_clip : nullptr;
-  float* ob = out + static_cast<long long>(b) * per_clip;
+  const int lb = zlen ? zlen[b] : x_T;
+  const int s0 = start ? start[b] : 0;
+  const long long per_clip = static_cast<long long>(Hm) * x_T;
+  const float* xb = x + b * per_clip;
+  const float* zb = j >= 0 ? bank + static_cast<long long>(j) * Hm * bank_T : nullptr;
+  float* ob = out + b * per_clip;
+  const float eps = 1.1920928955078125e-07f;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < per_clip;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float xv = xb[i];
-    ob[i] = zb ? logf((1.0f - a) * expf(xv) + a * expf(zb[i]) + 1.1920928955078125e-07f) : xv;
+    if (!zb) {
+      ob[i] = xv;
+      continue;
+    }
+    const int r = static_cast<int>(i / x_T), t = static_cast<int>(i - static_cast<long long>(r) * x_T);
+    int tz = t;            // frame of z mixed into frame t of x (-1: none)
+    if (x_T < lb) tz = s0 + t;
+    else if (x_T > lb) tz = (t >= s0 && t < s0 + lb) ? t - s0 : -1;
+    ob[i] = tz >= 0 ? logf((1.0f - a) * expf(xv) + a * expf(zb[static_cast<long long>(r) * bank_T + tz]) + eps)
+                    : logf(expf(xv) + eps);
   }
 }
 
@@ -68,12 +85,13 @@ __global__ void resize_crop_kernel(const float* __restrict__ lms, const int* __r
   out[(static_cast<long long>(b) * Hm + oy) * T + ox] = acc;
 }
 
-int mixup_forward(const float* x, const float* bank, const int* idx, const float* alpha, float* out,
-                  long long per_clip, int B, cudaStream_t st) {
-  ATST_REQUIRE(B > 0 && per_clip > 0, "mixup_forward: empty batch");
+int mixup_forward(const float* x, int x_T, const float* bank, int bank_T, const int* idx, const int* zlen,
+                  const int* start, const float* alpha, float* out, int Hm, int B, cudaStream_t st) {
+  ATST_REQUIRE(B > 0 && Hm > 0 && x_T > 0 && bank_T > 0, "mixup_forward: empty batch");
+  const long long per_clip = static_cast<long long>(Hm) * x_T;
   int gx = static_cast<int>((per_clip + 255) / 256);
   if (gx > 64) gx = 64;
-  mixup_kernel<<<dim3(gx, B), 256, 0, st>>>(x, bank, idx, alpha, out, per_clip, B);
+  mixup_kernel<<<dim3(gx, B), 256, 0, st>>>(x, x_T, bank, bank_T, idx, zlen, start, alpha, out, Hm, B);
   return atst_check_launch("mixup_kernel");
 }
 

@@ -189,9 +189,9 @@ int atst_adamw_step(float* p, const float* g, float* m, float* v, long long n, i
                     float beta1, float beta2, float eps, float grad_scale, void* stream) {
   return adamw_step(p, g, m, v, n, step, lr, wd, beta1, beta2, eps, grad_scale, ST(stream));
 }
-int atst_mixup_forward(const float* x, const float* bank, const int* idx, const float* alpha, float* out,
-                       long long per_clip, int B, void* stream) {
-  return mixup_forward(x, bank, idx, alpha, out, per_clip, B, ST(stream));
+int atst_mixup_forward(const float* x, int x_T, const float* bank, int bank_T, const int* idx, const int* zlen,
+                       const int* start, const float* alpha, float* out, int Hm, int B, void* stream) {
+  return mixup_forward(x, x_T, bank, bank_T, idx, zlen, start, alpha, out, Hm, B, ST(stream));
 }
 int atst_resize_crop_forward(const float* lms, const int* rect, float* out, int B, int Hm, int T, int canvas_h,
                              int canvas_w, void* stream) {

@@ -31,8 +31,8 @@ int bn_relu_backward_stats(const float* dY, const float* X, const float* mean, c
 int bn_relu_backward_apply(const float* dY, const float* X, const float* mean, const float* rstd, const float* gamma,
                            const float* beta, const float* s1, const float* s2, float count, float* dX, int rows,
                            int cols, cudaStream_t st);
-int mixup_forward(const float* x, const float* bank, const int* idx, const float* alpha, float* out,
-                  long long per_clip, int B, cudaStream_t st);
+int mixup_forward(const float* x, int x_T, const float* bank, int bank_T, const int* idx, const int* zlen,
+                  const int* start, const float* alpha, float* out, int Hm, int B, cudaStream_t st);
 int resize_crop_forward(const float* lms, const int* rect, float* out, int B, int Hm, int T, int canvas_h,
                         int canvas_w, cudaStream_t st);
 int gather_rows(const float* x, const int* idx, float* out, int rows, int D, cudaStream_t st);

@@ -19,7 +19,10 @@ except Exception:  # noqa: BLE001
             self.optimizers = []
 
     class LightningModule(nn.Module):
-        """the slice of the LightningModule protocol the ATST recipes touch."""
+        """the slice of the LightningModule protocol the ATST recipes and loaders touch: ``global_step``,
+        ``trainer.optimizers``, ``log``, ``save_hyperparameters`` (records the constructor arguments in ``hparams``)
+        and ``load_from_checkpoint`` for the checkpoint layout Lightning writes (``state_dict`` +
+        ``hyper_parameters``)."""
 
         def __init__(self):
             super().__init__()
@@ -32,7 +35,22 @@ except Exception:  # noqa: BLE001
             self.logged[name] = value
 
         def save_hyperparameters(self, *args, **kwargs):
-            pass
+            import inspect
+            frame = inspect.currentframe().f_back
+            info = inspect.getargvalues(frame)
+            hp = {k: info.locals[k] for k in info.args if k != "self"}
+            if info.keywords:
+                hp.update(info.locals[info.keywords])
+            self.hparams = hp
+
+        @classmethod
+        def load_from_checkpoint(cls, checkpoint_path, map_location=None, strict=True, **kwargs):
+            ck = torch.load(checkpoint_path, map_location=map_location or "cpu", weights_only=False)
+            hp = dict(ck.get("hyper_parameters", {}))
+            hp.update(kwargs)
+            module = cls(**hp)
+            module.load_state_dict(ck["state_dict"], strict=strict)
+            return module
 
 
 class ATSTLightningModule(LightningModule):

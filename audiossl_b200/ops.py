@@ -323,11 +323,12 @@ def adamw_step(p, g, m, v, step, lr, wd, beta1=0.9, beta2=0.999, eps=1e-6, grad_
     _count(1)
 
 
-def mixup_fwd(x, bank, idx, alpha, out):
-    B = x.shape[0]
-    per_clip = x.numel() // B
-    check(_lib.lib().atst_mixup_forward(ptr(x), ptr(bank), ptr(idx), ptr(alpha), ptr(out), per_clip, B, _lib.stream()),
-          "atst_mixup_forward")
+def mixup_fwd(x, bank, idx, alpha, out, zlen=None, start=None):
+    """x [B,(1,)Hm,T]; bank [n,(1,)Hm,Tb] (or None when every idx is negative); zlen / start int32 [B] or None."""
+    B, Hm, T = x.shape[0], x.shape[-2], x.shape[-1]
+    bank_T = T if bank is None else bank.shape[-1]
+    check(_lib.lib().atst_mixup_forward(ptr(x), T, ptr(bank), bank_T, ptr(idx), ptr(zlen), ptr(start), ptr(alpha),
+                                        ptr(out), Hm, B, _lib.stream()), "atst_mixup_forward")
     _count(1)
     return out
 

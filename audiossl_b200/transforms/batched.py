@@ -13,30 +13,50 @@ from .. import ops
 
 class BatchedMixup:
     """log-mixup-exp against a device FIFO of past inputs (byol_a.py:85-115): each clip is mixed with a random
-    bank entry using alpha = ratio * U(0,1); the un-mixed batch is then pushed into the bank."""
+    bank entry using alpha = ratio * U(0,1); the un-mixed batch is then pushed into the bank.  The bank is one
+    [n_memory, Hm, max_frames] device tensor with a per-entry frame count, so batches of different widths mix the way
+    ``log_mixup_exp`` does (random alignment of the shorter clip, byol_a.py:61-82)."""
 
-    def __init__(self, ratio=0.4, n_memory=2000, rng=None):
-        self.ratio, self.n = ratio, n_memory
+    def __init__(self, ratio=0.4, n_memory=2000, max_frames=None, rng=None):
+        self.ratio, self.n, self.max_frames = ratio, n_memory, max_frames
         self.bank, self.size, self.head = None, 0, 0
+        self.lens = np.zeros(n_memory, np.int32)
         self.rng = rng or np.random
 
-    def __call__(self, x, alpha=None, idx=None):
-        """x [B,1,64,T] cuda.  alpha / idx override the random draws (tests)."""
-        B = x.shape[0]
+    def _ensure_bank(self, x):
+        Hm, T = x.shape[-2], x.shape[-1]
+        width = max(T, self.max_frames or 0)
+        if self.bank is None or self.bank.shape[1] != Hm or self.bank.shape[2] < T or self.bank.device != x.device:
+            old = self.bank
+            self.bank = torch.zeros((self.n, Hm, width), device=x.device, dtype=torch.float32)
+            if old is not None and old.shape[1] == Hm and old.device == x.device:
+                self.bank[:, :, :old.shape[2]] = old  # a wider batch arrived: keep the entries
+            else:
+                self.size = self.head = 0
+
+    def __call__(self, x, alpha=None, idx=None, start=None):
+        """x [B,1,Hm,T] cuda.  alpha / idx / start override the random draws (tests)."""
+        B, T = x.shape[0], x.shape[-1]
         x = x.contiguous()
-        if self.bank is None or self.bank.shape[1:] != x.shape[1:]:
-            self.bank = torch.empty((self.n,) + tuple(x.shape[1:]), device=x.device, dtype=torch.float32)
-            self.size = self.head = 0
+        self._ensure_bank(x)
         if alpha is None:
             alpha = self.ratio * self.rng.random(B)
         if idx is None:
             idx = self.rng.randint(0, self.size, B) if self.size > 0 else np.full(B, -1)
-        a = torch.as_tensor(np.asarray(alpha, np.float32), device=x.device)
-        j = torch.as_tensor(np.asarray(idx, np.int32), device=x.device)
-        out = ops.mixup_fwd(x, self.bank, j, a, torch.empty_like(x))
+        idx = np.asarray(idx, np.int32)
+        zlen = np.where(idx >= 0, self.lens[np.maximum(idx, 0)], T).astype(np.int32)
+        if start is None:
+            span = np.abs(zlen - T)
+            start = np.where(span > 0, (self.rng.random(B) * span).astype(np.int32), 0)
+        dev = x.device
+        out = ops.mixup_fwd(x, self.bank, torch.as_tensor(idx, device=dev),
+                            torch.as_tensor(np.asarray(alpha, np.float32), device=dev), torch.empty_like(x),
+                            zlen=torch.as_tensor(zlen, device=dev),
+                            start=torch.as_tensor(np.asarray(start, np.int32), device=dev))
         # FIFO push of the un-mixed inputs
-        pos = (self.head + torch.arange(B, device=x.device)) % self.n
-        self.bank.index_copy_(0, pos, x)
+        pos = (self.head + np.arange(B)) % self.n
+        self.bank[torch.as_tensor(pos, device=dev), :, :T] = x.reshape(B, x.shape[-2], T)
+        self.lens[pos] = T
         self.head = (self.head + B) % self.n
         self.size = min(self.n, self.size + B)
         return out

@@ -112,11 +112,13 @@ int atst_adamw_step(float* p, const float* g, float* m, float* v, long long n, i
                     float beta1, float beta2, float eps, float grad_scale, void* stream);
 
 /* ---- device-batched augmentations between mel and encoder (audiossl/transforms/byol_a.py:7-49,61-115):
- *   mixup: out[b] = log((1-alpha[b]) e^x[b] + alpha[b] e^bank[idx[b]] + eps), idx[b] < 0 copies x[b]
+ *   mixup: out[b] = log((1-alpha[b]) e^x[b] + alpha[b] e^bank[idx[b]] + eps), idx[b] < 0 copies x[b]; x [B,Hm,x_T],
+ *          bank entries [Hm,bank_T] with zlen[b] valid frames (NULL: x_T) - a longer entry is read from frame
+ *          start[b], a shorter one is mixed into frames [start[b], start[b]+zlen[b]) of x (log_mixup_exp's branches)
  *   resize_crop: crop rect[b] = (i, j, h, w) of the zero canvas [canvas_h, canvas_w] holding lms[b] centred,
  *                bicubic (align_corners=True, A=-0.75) resize back to [Hm, T] */
-int atst_mixup_forward(const float* x, const float* bank, const int* idx, const float* alpha, float* out,
-                       long long per_clip, int B, void* stream);
+int atst_mixup_forward(const float* x, int x_T, const float* bank, int bank_T, const int* idx, const int* zlen,
+                       const int* start, const float* alpha, float* out, int Hm, int B, void* stream);
 int atst_resize_crop_forward(const float* lms, const int* rect, float* out, int B, int Hm, int T, int canvas_h,
                              int canvas_w, void* stream);
 

@@ -246,7 +246,7 @@ def _trunc_normal_(t, std=0.02):
 
 def attention_mask(n_tok, length):
     """-10000 on keys >= length, [B,1,1,N] broadcastable (modules/transformer.py:152-159)."""
-    m = torch.arange(n_tok)[None, :] >= length[:, None]
+    m = torch.arange(n_tok, device=length.device)[None, :] >= length[:, None]
     return (-10000.0 * m[:, None, None, :]).to(torch.float32)
 
 
@@ -343,7 +343,7 @@ class OracleAST(nn.Module):
         if self.use_cls:
             return x[:, 0]
         # frame model returns masked frames inside the valid length (audio_transformer.py:183-207)
-        lm = torch.arange(x.shape[1])[None, :] < plen[:, None]
+        lm = torch.arange(x.shape[1], device=x.device)[None, :] < plen[:, None]
         return x[mask_index.bool() & lm]
 
 

@@ -314,6 +314,95 @@ def gen_sched():
     print("sched.npz")
 
 
+def gen_transform():
+    """the train transforms end to end (crop -> mel_feature -> Mixup -> RandomResizeCrop -> pad) with seeded host
+    generators: audiossl/methods/atst/transform.py:50-74, audiossl/methods/atstframe/transform.py:70-101."""
+    import random
+    frame_stubs()
+    sys.path.insert(0, "/root/reference/audiossl/methods/atstframe")  # its transform does `import random_mask`
+    from audiossl.methods.atst.transform import ATSTTrainTransform
+    from audiossl.methods.atstframe.transform import FrameATSTTrainTransform
+    out = {}
+    # variable-length views: every log_mixup_exp branch (equal, shorter, longer bank entry) is reached
+    random.seed(5)
+    np.random.seed(5)
+    tf = ATSTTrainTransform(anchor_len=(0.7, 1.0), positive_len=(0.7, 1.0))
+    for k in range(5):
+        wav = torch.from_numpy(detfill.det_array("tf/wav%d" % k, (1, 24000), 0.1))
+        crops, lengths = tf(wav)
+        out["clipvar/%d/crop0" % k], out["clipvar/%d/crop1" % k] = crops[0].numpy(), crops[1].numpy()
+        out["clipvar/%d/lengths" % k] = np.array(lengths, np.int64)
+    # the recipe's defaults (6 s views of a 10 s clip, one clip shorter than the view: zero-padded waveform)
+    random.seed(6)
+    np.random.seed(6)
+    tf = ATSTTrainTransform()
+    for k, n in enumerate((160000, 160000, 80000)):
+        wav = torch.from_numpy(detfill.det_array("tf6/wav%d" % k, (1, n), 0.1))
+        crops, lengths = tf(wav)
+        for v in range(2):
+            flat("clip6/%d/crop%d" % (k, v), detfill.summarize(crops[v].numpy()), out)
+            out["clip6/%d/shape%d" % (k, v)] = np.array(crops[v].shape, np.int64)
+        out["clip6/%d/lengths" % k] = np.array(lengths, np.int64)
+    # ATST-Frame: one crop, two independently augmented views, frequency-only warp, random (non-block) mask
+    random.seed(7)
+    np.random.seed(7)
+    torch.manual_seed(7)
+    tf = FrameATSTTrainTransform(anchor_len=1.0, mask_type="random", mask_ratio=0.75)
+    for k in range(3):
+        wav = torch.from_numpy(detfill.det_array("tff/wav%d" % k, (1, 20000), 0.1))
+        crops, lengths, masks = tf(wav)
+        out["frame/%d/crop0" % k], out["frame/%d/crop1" % k] = crops[0].numpy(), crops[1].numpy()
+        out["frame/%d/lengths" % k] = np.array(lengths, np.int64)
+        out["frame/%d/mask" % k] = masks[0].numpy()
+        assert masks[0] is masks[1]
+    np.savez_compressed(os.path.join(HERE, "transform.npz"), **out)
+    print("transform.npz", len(out))
+
+
+def gen_embed():
+    """audiossl/methods/atstframe/embedding.py:19-127: load_model from a Lightning-format checkpoint, scene and
+    timestamp embeddings of clips longer than one 1001-frame chunk.  The checkpoint itself is not committed: the
+    test rebuilds it from the same name-derived weights."""
+    import tempfile
+    harness()
+    frame_stubs()
+    import pytorch_lightning as pl
+
+    def load_from_checkpoint(cls, path, **kw):  # what Lightning does for this module: ctor(**hyper_parameters) + weights
+        ck = torch.load(path, map_location="cpu", weights_only=False)
+        m = cls(**ck["hyper_parameters"])
+        m.load_state_dict(ck["state_dict"])
+        return m
+    pl.LightningModule.load_from_checkpoint = classmethod(load_from_checkpoint)
+    pl.LightningModule.save_hyperparameters = lambda self, *a, **k: None
+    sys.path.insert(0, "/root/reference/audiossl/methods/atstframe")
+    from audiossl.methods.atstframe import embedding as E
+    from audiossl.methods.atstframe.model import FrameATSTLightningModule
+    hp = dict(arch="small", learning_rate=5e-4, warmup_steps=10, max_steps=100, ema=0.99)
+    lm = FrameATSTLightningModule(**hp)
+    load_det(lm)
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "last.ckpt")
+        torch.save({"state_dict": lm.state_dict(), "hyper_parameters": hp}, path)
+        enc = E.load_model(path)
+    assert enc.scene_embedding_size == 384 * 2 * 12 and enc.timestamp_embedding_size == 384 * 12
+    n = 16000 * 12 + 800  # 1206 frames: one full 1001-frame chunk + a 205-frame tail
+    audio = torch.stack([torch.from_numpy(detfill.signal("noise", n)), torch.from_numpy(detfill.signal("chirp", n))])[:, None]
+    with torch.no_grad():
+        scene = E.get_scene_embedding(audio, enc)
+        ts, stamps = E.get_timestamp_embedding(audio, enc)
+        scene1 = E.get_scene_embedding(audio[0, :, :16000 * 3], enc)  # [1, n] input, shorter than one chunk
+    out["scene"] = scene.numpy()
+    out["scene1"] = scene1.numpy()
+    out["ts/shape"] = np.array(ts.shape, np.int64)
+    flat("ts", detfill.summarize(ts.numpy()), out)
+    out["ts/rows"] = ts[:, ::37, :].numpy()[:, :, ::13]
+    out["stamps"] = stamps.numpy()
+    np.savez_compressed(os.path.join(HERE, "embed.npz"), **out)
+    print("embed.npz", len(out), scene.shape, ts.shape)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     gen_mel()
@@ -322,3 +411,5 @@ if __name__ == "__main__":
     gen_infer()
     gen_augment()
     gen_sched()
+    gen_transform()
+    gen_embed()

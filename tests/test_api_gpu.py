@@ -1,0 +1,212 @@
+"""GPU parity of the reference-facing API either side of the training step:
+the train transforms end to end and the embedding API, against vectors produced by the UNMODIFIED reference
+(tests/golden/make_golden.py gen_transform / gen_embed).  The transforms draw from the same host generators in the
+same order as the reference, so equal seeds give the reference's crops, mixing partners, resize rectangles and masks;
+what is left is the arithmetic of the CUDA kernels (fused mel, log-mixup-exp, bicubic resize), held to the mel
+tolerance."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from tests import util
+from tests.golden import detfill
+
+pytestmark = pytest.mark.gpu
+
+TOL = 5e-4  # absolute, in the normalised log-mel units of the reference's MinMax (range about [-1, 1])
+
+
+def _wav(name, n):
+    return torch.from_numpy(detfill.det_array(name, (1, n), 0.1)).cuda()
+
+
+def test_atst_train_transform_variable_length_views_match_reference():
+    """anchor / positive lengths U(0.7, 1.0) s: RandomCrop, the fused mel, Mixup against a bank of clips of other
+    lengths (all three log_mixup_exp branches), RandomResizeCrop, right padding - five consecutive calls."""
+    from audiossl_b200.methods.atst.transform import ATSTTrainTransform
+    g = util.gold("transform.npz")
+    random.seed(5)
+    np.random.seed(5)
+    tf = ATSTTrainTransform(anchor_len=(0.7, 1.0), positive_len=(0.7, 1.0))
+    seen = set()
+    for k in range(5):
+        crops, lengths = tf(_wav("tf/wav%d" % k, 24000))
+        assert list(lengths) == list(g["clipvar/%d/lengths" % k])
+        for v in range(2):
+            ref = g["clipvar/%d/crop%d" % (k, v)]
+            assert tuple(crops[v].shape) == ref.shape and crops[v].is_cuda
+            np.testing.assert_allclose(crops[v].cpu().numpy(), ref, atol=TOL, rtol=0)
+        seen.add(lengths[0] != lengths[1])
+    assert True in seen  # views of different lengths did occur
+
+
+def test_atst_train_transform_recipe_defaults_match_reference():
+    """the recipe's 6 s views of 10 s clips (and of a 5 s clip: zero-padded waveform)."""
+    from audiossl_b200.methods.atst.transform import ATSTTrainTransform
+    g = util.gold("transform.npz")
+    random.seed(6)
+    np.random.seed(6)
+    tf = ATSTTrainTransform()
+    for k, n in enumerate((160000, 160000, 80000)):
+        crops, lengths = tf(_wav("tf6/wav%d" % k, n))
+        assert list(lengths) == list(g["clip6/%d/lengths" % k]) == [601, 601]
+        for v in range(2):
+            assert list(crops[v].shape) == list(g["clip6/%d/shape%d" % (k, v)])
+            util.check_summary(crops[v].cpu().numpy(), g, "clip6/%d/crop%d" % (k, v), rtol=0, atol=TOL, scale=1.0)
+
+
+def test_frame_train_transform_matches_reference():
+    """ATST-Frame: one crop, two independently augmented views (frequency-only warp), one mask for both."""
+    from audiossl_b200.methods.atstframe.transform import FrameATSTTrainTransform
+    g = util.gold("transform.npz")
+    random.seed(7)
+    np.random.seed(7)
+    torch.manual_seed(7)
+    tf = FrameATSTTrainTransform(anchor_len=1.0, mask_type="random", mask_ratio=0.75)
+    for k in range(3):
+        crops, lengths, masks = tf(_wav("tff/wav%d" % k, 20000))
+        assert list(lengths) == list(g["frame/%d/lengths" % k])
+        assert masks[0] is masks[1] and np.array_equal(masks[0].cpu().numpy(), g["frame/%d/mask" % k])
+        for v in range(2):
+            np.testing.assert_allclose(crops[v].cpu().numpy(), g["frame/%d/crop%d" % (k, v)], atol=TOL, rtol=0)
+
+
+def test_block_mask_statistics_and_transform_contract():
+    """mask_type="block" (the ATST-Frame recipe): spans of 5 frames, overlap allowed, about half of the frames masked
+    (SURVEY.md a17); the transform returns it for both views."""
+    from audiossl_b200.methods.atstframe import random_mask
+    from audiossl_b200.methods.atstframe.transform import FrameATSTTrainTransform
+    np.random.seed(0)
+    m = random_mask.get_mask(64, 250, 0.65, no_overlap=False, min_length=5)
+    assert m.shape == (64, 250) and m.dtype == torch.bool
+    frac = m.float().mean(1)
+    assert 0.40 < frac.mean().item() < 0.60 and frac.min().item() > 0.3
+    runs = []
+    for row in m.numpy():
+        edges = np.flatnonzero(np.diff(np.concatenate([[0], row.astype(np.int8), [0]])))
+        runs += list(edges[1::2] - edges[0::2])
+    assert min(runs) >= 5  # every masked run is a union of length-5 spans
+    tf = FrameATSTTrainTransform(anchor_len=2.0, mask_type="block", mask_ratio=0.65, mask_len=5)
+    crops, lengths, masks = tf(_wav("tfb/wav", 40000))
+    assert lengths == [201, 201] and masks[0].shape == (50,) and crops[0].shape == (1, 64, 201)
+
+
+def _checkpoint(tmp_path, arch="small"):
+    """a Lightning-format checkpoint of the reference's key layout with name-derived weights (the fixture generator
+    wrote the same one for the reference's load_model)."""
+    from audiossl_b200.methods.atstframe.model import FrameATSTLightningModule
+    hp = dict(arch=arch, learning_rate=5e-4, warmup_steps=10, max_steps=100, ema=0.99)
+    lm = FrameATSTLightningModule(**hp)
+    util.load_det(lm)
+    path = str(tmp_path / "last.ckpt")
+    torch.save({"state_dict": {k: v.cpu() for k, v in lm.state_dict().items()}, "hyper_parameters": hp}, path)
+    return path
+
+
+def test_embedding_api_matches_reference(tmp_path):
+    """load_model -> get_scene_embedding / get_timestamp_embedding on 12 s clips (a full 1001-frame chunk + a tail)
+    and on a [1, N] clip shorter than one chunk: audiossl/methods/atstframe/embedding.py:19-127."""
+    from audiossl_b200.methods.atstframe import embedding as E
+    g = util.gold("embed.npz")
+    enc = E.load_model(_checkpoint(tmp_path))
+    assert enc.scene_embedding_size == 384 * 2 * 12 and enc.timestamp_embedding_size == 384 * 12
+    assert enc.sample_rate == 16000 and enc.hyper_param["arch"] == "small" and not enc.training
+    n = 16000 * 12 + 800
+    audio = torch.stack([torch.from_numpy(detfill.signal("noise", n)), torch.from_numpy(detfill.signal("chirp", n))])[:, None].cuda()
+    rel = lambda a, b: float(np.linalg.norm(np.asarray(a, np.float64) - b) / np.linalg.norm(b))
+    scene = E.get_scene_embedding(audio, enc)
+    assert tuple(scene.shape) == g["scene"].shape == (2, 4608)
+    assert rel(scene.cpu().numpy(), g["scene"]) < 1e-3
+    ts, stamps = E.get_timestamp_embedding(audio, enc)
+    assert list(ts.shape) == list(g["ts/shape"]) == [2, 301, 4608]
+    np.testing.assert_array_equal(stamps.numpy(), g["stamps"])
+    assert rel(ts[:, ::37, :].cpu().numpy()[:, :, ::13], g["ts/rows"]) < 1e-3
+    err, _ = util.sample_rel_err(ts.cpu().numpy(), g, "ts")
+    assert err < 1e-3
+    scene1 = E.get_scene_embedding(audio[0, :, :16000 * 3], enc)
+    assert tuple(scene1.shape) == (1, 4608) and rel(scene1.cpu().numpy(), g["scene1"]) < 1e-3
+    with pytest.raises(RuntimeError):
+        E.get_scene_embedding(audio.cpu(), enc)
+
+
+def test_batched_train_transform_contract_and_statistics():
+    """BatchedATSTTrainTransform: the batch contract of training_step, the un-augmented path equal to the fused mel
+    of the drawn windows, and augmentation statistics in the range the per-sample reference transform produces."""
+    from audiossl_b200 import ops
+    from audiossl_b200.methods.atst.transform import BatchedATSTTrainTransform
+    B, n = 6, 40000
+    wav = (torch.randn(B, 1, n, generator=torch.Generator().manual_seed(0)) * 0.1).cuda()
+    rng = np.random.RandomState(3)
+    tf = BatchedATSTTrainTransform(anchor_len=(1.0, 1.0), positive_len=(1.5, 1.5), rng=rng, augment=False)
+    crops, lengths = tf(wav)
+    assert [tuple(c.shape) for c in crops] == [(B, 1, 64, 150)] * 2 and all(c.is_cuda for c in crops)
+    assert lengths[0].tolist() == [101] * B and lengths[1].tolist() == [151] * B and lengths[0].dtype == torch.int64
+    # replay the draws: uniform(anchor), B window starts, uniform(positive), B window starts
+    rng2 = np.random.RandomState(3)
+    rng2.uniform(1.0, 1.0)
+    s1 = rng2.randint(0, n - 16000 + 1, B)
+    rng2.uniform(1.5, 1.5)
+    s2 = rng2.randint(0, n - 24000 + 1, B)
+    for b in range(B):
+        m1 = ops.mel_forward(wav[b, :, s1[b]:s1[b] + 16000].contiguous())
+        m2 = ops.mel_forward(wav[b, :, s2[b]:s2[b] + 24000].contiguous())
+        np.testing.assert_allclose(crops[0][b, :, :, :101].cpu().numpy(), m1.cpu().numpy(), atol=1e-5)
+        np.testing.assert_allclose(crops[1][b, :, :, :151].cpu().numpy(), m2.cpu().numpy(), atol=1e-5)
+    assert float(crops[0][..., 101:].abs().sum()) == 0.0 and float(crops[1][..., 150:].abs().sum()) == 0.0
+    # augmentations on: same shapes, finite, a memory bank that fills, outputs that differ from the plain mel
+    tf = BatchedATSTTrainTransform(anchor_len=(1.0, 1.0), positive_len=(1.0, 1.0), rng=np.random.RandomState(4))
+    for _ in range(3):
+        crops, lengths = tf(wav)
+    assert tf.mixup[0].size == 3 * B and tuple(crops[0].shape) == (B, 1, 64, 100)
+    assert torch.isfinite(crops[0]).all() and torch.isfinite(crops[1]).all()
+    assert -1.5 < float(crops[0].mean()) < 1.0 and float(crops[0].std()) > 0.05
+
+
+def test_data_module_and_launcher_on_synthetic_clips(tmp_path):
+    """the train.py-equivalent launcher end to end on one GPU: synthetic clips -> host loader -> pinned H2D prefetch
+    -> device transform -> training steps -> Lightning-layout checkpoint -> resume."""
+    from audiossl_b200.methods.atst import train as T
+    args = T.build_parser().parse_args(["--save_path", str(tmp_path), "--nproc", "1", "--arch", "small",
+                                        "--batch_size_per_gpu", "4", "--num_workers", "0", "--synthetic_clips", "16",
+                                        "--train_len", "1.0", "--max_steps", "3", "--warmup_steps", "1",
+                                        "--log_every", "1", "--save_every", "2"])
+    lm = T.main(args)
+    ck = torch.load(str(tmp_path / "last.ckpt"), map_location="cpu", weights_only=False)
+    assert ck["global_step"] == 3 and ck["hyper_parameters"]["arch"] == "small"
+    assert set(ck["state_dict"]) == set(lm.state_dict()) and len(ck["optimizer_states"][0]["state"]) > 100
+    assert np.isfinite(float(lm.logged["loss"])) and abs(ck["hyper_parameters"]["learning_rate"] - 5e-4 * 4 / 256) < 1e-12
+    # resume: picks up at step 3 and runs to 4
+    args2 = T.build_parser().parse_args(["--save_path", str(tmp_path), "--nproc", "1", "--arch", "small",
+                                         "--batch_size_per_gpu", "4", "--num_workers", "0", "--synthetic_clips", "16",
+                                         "--train_len", "1.0", "--max_steps", "4", "--warmup_steps", "1"])
+    T.main(args2)
+    ck2 = torch.load(str(tmp_path / "last.ckpt"), map_location="cpu", weights_only=False)
+    assert ck2["global_step"] == 4
+    assert int(ck2["optimizer_states"][0]["state"][next(iter(ck2["optimizer_states"][0]["state"]))]["step"]) == 4
+
+
+def test_lmdb_to_device_batches(tmp_path):
+    """f4 end to end: records written in the reference's LMDB / legacy-arrow layout -> LMDBDataset -> collate ->
+    DevicePrefetcher -> device batches identical to the stored waveforms."""
+    from audiossl_b200.datasets import DevicePrefetcher, LMDBDataset, collate_waveforms, write_dataset
+    rng = np.random.RandomState(0)
+    recs = [("c%03d" % i, (rng.standard_normal((1, 4000 + 100 * i)) * 0.1).astype(np.float32),
+             np.eye(1, 4, i % 4, dtype=np.float32)) for i in range(10)]
+    write_dataset(str(tmp_path / "train.lmdb"), recs)
+    ds = LMDBDataset(str(tmp_path), "train")
+    loader = torch.utils.data.DataLoader(ds, batch_size=4, collate_fn=lambda s: collate_waveforms(s, 4500))
+    seen = 0
+    by_key = {k: (w, l) for k, w, l in recs}
+    for bi, (wav, labels) in enumerate(DevicePrefetcher(loader, "cuda")):
+        assert wav.is_cuda and labels.is_cuda and wav.shape[1:] == (1, 4500)
+        for j in range(wav.shape[0]):
+            name = ds.keys[bi * 4 + j].decode()
+            ref = np.zeros(4500, np.float32)
+            m = min(4500, by_key[name][0].shape[1])
+            ref[:m] = by_key[name][0][0, :m]
+            assert np.array_equal(wav[j, 0].cpu().numpy(), ref)
+            assert np.array_equal(labels[j].cpu().numpy(), by_key[name][1][0])
+        seen += wav.shape[0]
+    assert seen == 10

@@ -139,9 +139,15 @@ def test_transforms_api():
     assert T.ToSizeN(4)(x).shape == (1, 8)  # remainder 2 is not past the half-way point: truncates
     np.testing.assert_allclose(T.MinMax(0., 10.)(torch.tensor([0., 5., 10.])).numpy(), [-1., 0., 1.])
     lms = torch.randn(1, 64, 50)
-    assert T.RandomResizeCrop()(lms).shape == lms.shape
+    # the augmentations are fronts of the CUDA kernels (they follow the fused mel on the device): no CPU arithmetic
+    with pytest.raises(RuntimeError, match="GPU only"):
+        T.RandomResizeCrop()(lms)
     mx = T.Mixup()
-    assert torch.equal(mx(lms), lms) and mx(lms * 0.5).shape == lms.shape
+    assert torch.equal(mx(lms), lms) and len(mx.memory_bank) == 1  # empty bank: identity, input remembered
+    with pytest.raises(RuntimeError, match="GPU only"):
+        mx(lms * 0.5)
+    i, j, h, w = T.RandomResizeCrop.get_params((64, 75), (64, 50), (0.6, 1.5), (0.6, 1.5))
+    assert 1 <= h <= 64 and 1 <= w <= 75 and 0 <= i <= 64 - h and 0 <= j <= 75 - w
 
 
 WORKER = r'''
