@@ -21,7 +21,7 @@ SIGNATURES = {
     "atst_version": [],
     "atst_init": [],
     "atst_set_option": [c_char_p, I],
-    "atst_mel_forward": [P, I, I, L, I, P, L, P, I, P],
+    "atst_mel_forward": [P, I, I, L, P, I, P, L, P, I, P],
     "atst_gemm_nt": [P, I, P, I, P, I, I, I, I, P, I, P, I, P, I, P, I, I, P],
     "atst_gemm_nn": [P, I, P, I, P, I, I, I, I, I, P, I, P, I, I, P, P],
     "atst_gemm_tn": [P, I, P, I, P, I, I, I, I, P],

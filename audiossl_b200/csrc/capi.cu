@@ -50,9 +50,10 @@ int atst_init(void) {
   return ATST_OK;
 }
 
-int atst_mel_forward(const float* wav, int B, int n, long long wav_stride, int win_length, float* out,
-                     long long out_stride, unsigned int* clip_max_ws, int normalize, void* stream) {
-  return mel_forward(wav, B, n, wav_stride, win_length, out, out_stride, clip_max_ws, normalize, ST(stream));
+int atst_mel_forward(const float* wav, int B, int n, long long wav_stride, const long long* clip_start,
+                     int win_length, float* out, long long out_stride, unsigned int* clip_ws, int normalize,
+                     void* stream) {
+  return mel_forward(wav, B, n, wav_stride, clip_start, win_length, out, out_stride, clip_ws, normalize, ST(stream));
 }
 
 int atst_gemm_nt(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K,

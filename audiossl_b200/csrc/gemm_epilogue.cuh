@@ -151,7 +151,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
       if (lane < 8) atomicAdd(p.colsum + n0 + g * 8 + lane, mine);
     }
   };
-  const bool one_stream = side_row == nullptr && aux_row == nullptr && p.epi != EPI_GELU && p.epi != EPI_DGELU;
+  // warp-uniform by construction (parameters only): the two forms below use .sync.aligned TMEM loads and each calls
+  // release() once per warp, so a warp must never split between them - with the per-thread side_row in this test, a
+  // warp straddling the last valid row of a residual epilogue did (rows past M have no side pointer), which
+  // double-released the accumulator stage and hung the kernel for M % 32 != 0
+  const bool one_stream = side_ptr == nullptr && p.epi != EPI_GELU && p.epi != EPI_DGELU;
   if (one_stream) {
     // Plain epilogues (one global stream, no GELU math): the tile period is the main loop, and what matters is handing
     // the accumulator stage back early - a tcgen05.ld takes ~1500 cycles under a running main loop, so eight dependent

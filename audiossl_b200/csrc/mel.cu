@@ -2,14 +2,18 @@
 // arithmetic = torchaudio MelSpectrogram(16000, n_fft 1024, hop 160, win 1024|640, f 60..7800, 64 HTK mels,
 // power 2) -> AmplitudeToDB("power", top_db 80, per clip) -> MinMax(-79.6482, 50.6842)).
 //
-// Kernel 1 (mel_db_kernel): one CTA = 32 consecutive frames of one clip.  The 5984-sample waveform segment
-// is staged once in shared memory with coalesced float4 loads (6.4x frame overlap is served from smem, the
-// waveform is read from HBM once), reflect padding is applied at the clip edges.  Four frames are transformed
-// at a time, 64 threads per frame: real 1024-point FFT = 512-point complex Stockham FFT (3 radix-8 passes in
-// registers, padded smem exchange) + split-radix untangle; |X|^2; banded mel dot (each of the 64 threads owns
-// one triangular band, <= 39 bins); 10*log10(max(.,1e-10)).  Output tile [64 mel][32 frames] is transposed in
-// smem and written with 128-byte row segments.  Per-clip max of the dB values via warp-reduce + atomicMax.
-// Kernel 2 (mel_norm_kernel): clamp at (clip max - 80 dB) and MinMax-normalise in place.
+// mel_kernel: one CTA = 32 consecutive frames of one clip, 8 warps.  The 5984-sample waveform segment is staged once
+// in shared memory - by ONE 1-D TMA bulk copy (cp.async.bulk, 23.9 KB, completion on an mbarrier) for interior CTAs,
+// by a reflect-padding loop at the clip edges - so the 6.4x frame overlap is served from smem and the waveform is
+// read from HBM once.  Each WARP then owns whole frames (4 per warp) and never meets the other warps again until the
+// tile is stored: real 1024-point FFT = 512-point complex Stockham FFT (3 radix-8 passes in registers, every lane
+// working two of the 64 butterfly columns, XOR-swizzled warp-private exchange buffers, __syncwarp only) + split-radix
+// untangle; |X|^2; banded mel dot (each lane owns two triangular bands, <= 39 bins); 10*log10(max(.,1e-10)).  The
+// window, twiddle and filterbank tables (16 KB) are read through L1 (__ldg) instead of being copied into every CTA's
+// shared memory.  Output tile [64 mel][32 frames] is transposed in smem and written with 128-byte row segments.
+// Per-clip max of the dB values via warp-reduce + atomicMax; the LAST CTA of a clip to finish (atomic ticket) applies
+// the top_db clamp and the MinMax normalisation to the whole clip in place (256 KB, L2-resident), so there is no
+// second kernel and no second pass over HBM.
 #include <math.h>
 #include "common.cuh"
 
@@ -74,38 +78,54 @@ __device__ __forceinline__ void dft8(float2 (&v)[8]) {
   }
 }
 
-__global__ void __launch_bounds__(256)
-mel_db_kernel(const float* __restrict__ wav, int n, long long wav_stride, int T, int win_idx,
-              float* __restrict__ out, long long out_stride, unsigned int* __restrict__ clip_max_bits) {
-  extern __shared__ float sm[];
-  float* seg = sm;                       // [kSeg]
-  float* zre = seg + kSeg;               // [4][528]
-  float* zim = zre + 4 * 528;            // [4][528]
-  float* pw = zim + 4 * 528;             // [4][520]
-  float* tile = pw + 4 * 520;            // [64][33]
-  float* s_win = tile + kMels * 33;      // [1024]
-  float2* s_tw = reinterpret_cast<float2*>(s_win + kNfft);  // [512]
-  float2* s_tw2 = s_tw + 512;            // [512]
-  float* s_w = reinterpret_cast<float*>(s_tw2 + 512);       // [kMaxW]
+constexpr int kWarps = 8;
+constexpr int kFftBuf = 528;  // floats per re / im exchange buffer (512 swizzled + the Nyquist bin of the power spectrum)
+
+// smem layout: mbarrier (16 B) | seg[kSeg] | per warp {re[528], im[528]} | tile[64][33]
+constexpr int kMelSmemBytes = 16 + (kSeg + kWarps * 2 * kFftBuf + kMels * 33) * 4;
+
+// dft8 leaves result r in slot kRev[r] = {0,4,2,6,1,5,3,7}
+__device__ __forceinline__ void store8(float* re, float* im, const float2 (&v)[8], int d, int stride) {
+  re[padi(d + 0 * stride)] = v[0].x; im[padi(d + 0 * stride)] = v[0].y;
+  re[padi(d + 4 * stride)] = v[1].x; im[padi(d + 4 * stride)] = v[1].y;
+  re[padi(d + 2 * stride)] = v[2].x; im[padi(d + 2 * stride)] = v[2].y;
+  re[padi(d + 6 * stride)] = v[3].x; im[padi(d + 6 * stride)] = v[3].y;
+  re[padi(d + 1 * stride)] = v[4].x; im[padi(d + 1 * stride)] = v[4].y;
+  re[padi(d + 5 * stride)] = v[5].x; im[padi(d + 5 * stride)] = v[5].y;
+  re[padi(d + 3 * stride)] = v[6].x; im[padi(d + 3 * stride)] = v[6].y;
+  re[padi(d + 7 * stride)] = v[7].x; im[padi(d + 7 * stride)] = v[7].y;
+}
+
+__global__ void __launch_bounds__(256, 3)
+mel_kernel(const float* __restrict__ wav, int n, long long wav_stride, const long long* __restrict__ clip_start,
+           int T, int win_idx, float* __restrict__ out, long long out_stride, unsigned int* __restrict__ clip_ws,
+           int B, int normalize, float top_db, float mn, float range) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  float* seg = reinterpret_cast<float*>(smem_raw + 16);   // [kSeg], 16-byte aligned for the bulk copy
+  float* fft = seg + kSeg;                                  // [kWarps][2][kFftBuf]
+  float* tile = fft + kWarps * 2 * kFftBuf;                 // [64][33]
+  __shared__ int s_ticket;
 
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * kFramesPerCta;
   const int tid = threadIdx.x;
-  const float* x = wav + static_cast<long long>(b) * wav_stride;
-
-  // tables -> smem
-  for (int i = tid; i < kNfft; i += 256) s_win[i] = g_mel_tables.window[win_idx][i];
-  for (int i = tid; i < 512; i += 256) {
-    s_tw[i] = g_mel_tables.tw512[i];
-    s_tw2[i] = g_mel_tables.tw1024[i];
-  }
-  for (int i = tid; i < kMaxW; i += 256) s_w[i] = g_mel_tables.w[i];
+  const int warp = tid >> 5, lane = tid & 31;
+  const float* x = wav + static_cast<long long>(b) * wav_stride + (clip_start ? clip_start[b] : 0);
 
   // waveform segment: sample index s = t0*160 - 512 + i ; reflect (no edge repeat) outside [0, n)
   const long long s0 = static_cast<long long>(t0) * kHop - kNfft / 2;
-  if (s0 >= 0 && s0 + kSeg <= n && ((reinterpret_cast<uintptr_t>(x + s0) & 15) == 0)) {
-    const float4* src = reinterpret_cast<const float4*>(x + s0);
-    for (int i = tid; i < kSeg / 4; i += 256) reinterpret_cast<float4*>(seg)[i] = __ldg(src + i);
+  const bool bulk = s0 >= 0 && s0 + kSeg <= n && ((reinterpret_cast<uintptr_t>(x + s0) & 15) == 0);
+  if (bulk) {
+    if (tid == 0) {
+      mbar_init(bar, 1);
+      fence_barrier_init();
+      mbar_expect_tx(bar, kSeg * 4);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   :: "r"(smem_u32(seg)), "l"(x + s0), "r"(kSeg * 4), "r"(smem_u32(bar)) : "memory");
+    }
+    __syncthreads();  // the barrier is initialised before anyone waits on it
+    mbar_wait(bar, 0);
   } else {
     for (int i = tid; i < kSeg; i += 256) {
       long long s = s0 + i;
@@ -115,153 +135,148 @@ mel_db_kernel(const float* __restrict__ wav, int n, long long wav_stride, int T,
       if (s >= 0 && s < n) v = __ldg(x + s);
       seg[i] = v;
     }
+    __syncthreads();
   }
-  __syncthreads();
 
-  const int slot = tid >> 6;  // frame slot 0..3
-  const int q = tid & 63;
-  float* re = zre + slot * 528;
-  float* im = zim + slot * 528;
-  float* P = pw + slot * 520;
-  const int band_start = g_mel_tables.band_start[q];
-  const int band_len = g_mel_tables.band_len[q];
-  const int band_off = g_mel_tables.band_off[q];
+  float* re = fft + warp * 2 * kFftBuf;
+  float* im = re + kFftBuf;
+  const float* g_win = g_mel_tables.window[win_idx];
+  const float2* g_tw = g_mel_tables.tw512;
+  const float2* g_tw2 = g_mel_tables.tw1024;
+  const float* g_w = g_mel_tables.w;
   float local_max = -INFINITY;
 
-  for (int it = 0; it < kFramesPerCta / 4; ++it) {
-    const int f = it * 4 + slot;  // frame within the CTA
+  for (int f = warp; f < kFramesPerCta; f += kWarps) {
     const float* fr = seg + f * kHop;
-    float2 v[8];
-    // ---- pass 1 (Ns = 1): inputs z[q + 64 r] = (w x)[2j], (w x)[2j+1]; no twiddles
+    float2 v[2][8];
+    // ---- pass 1 (Ns = 1): inputs z[q + 64 r] = (w x)[2j], (w x)[2j+1]; no twiddles.  q = lane, lane + 32
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const int j = q + 64 * r;
-      const float2 xx = *reinterpret_cast<const float2*>(fr + 2 * j);
-      const float2 ww = *reinterpret_cast<const float2*>(s_win + 2 * j);
-      v[r] = make_float2(xx.x * ww.x, xx.y * ww.y);
+    for (int h = 0; h < 2; ++h) {
+      const int q = lane + 32 * h;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int j = q + 64 * r;
+        const float2 xx = *reinterpret_cast<const float2*>(fr + 2 * j);
+        const float2 ww = __ldg(reinterpret_cast<const float2*>(g_win + 2 * j));
+        v[h][r] = make_float2(xx.x * ww.x, xx.y * ww.y);
+      }
+      dft8(v[h]);
     }
-    dft8(v);
-    {
-      const int d = q * 8;
-      re[padi(d + 0)] = v[0].x; im[padi(d + 0)] = v[0].y;
-      re[padi(d + 4)] = v[1].x; im[padi(d + 4)] = v[1].y;
-      re[padi(d + 2)] = v[2].x; im[padi(d + 2)] = v[2].y;
-      re[padi(d + 6)] = v[3].x; im[padi(d + 6)] = v[3].y;
-      re[padi(d + 1)] = v[4].x; im[padi(d + 1)] = v[4].y;
-      re[padi(d + 5)] = v[5].x; im[padi(d + 5)] = v[5].y;
-      re[padi(d + 3)] = v[6].x; im[padi(d + 3)] = v[6].y;
-      re[padi(d + 7)] = v[7].x; im[padi(d + 7)] = v[7].y;
-    }
-    __syncthreads();
+    __syncwarp();  // the previous frame's band sums have been read out of `re`
+#pragma unroll
+    for (int h = 0; h < 2; ++h) store8(re, im, v[h], (lane + 32 * h) * 8, 1);
+    __syncwarp();
     // ---- pass 2 (Ns = 8)
-    {
-      const int k = q & 7;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int q = lane + 32 * h, k = q & 7;
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         const int j = padi(q + 64 * r);
-        v[r] = make_float2(re[j], im[j]);
-        if (r > 0) v[r] = cmul(v[r], s_tw[r * k * 8]);
+        v[h][r] = make_float2(re[j], im[j]);
+        if (r > 0) v[h][r] = cmul(v[h][r], __ldg(g_tw + r * k * 8));
       }
-      dft8(v);
-      __syncthreads();
-      const int d = (q >> 3) * 64 + k;
-      re[padi(d + 0 * 8)] = v[0].x; im[padi(d + 0 * 8)] = v[0].y;
-      re[padi(d + 4 * 8)] = v[1].x; im[padi(d + 4 * 8)] = v[1].y;
-      re[padi(d + 2 * 8)] = v[2].x; im[padi(d + 2 * 8)] = v[2].y;
-      re[padi(d + 6 * 8)] = v[3].x; im[padi(d + 6 * 8)] = v[3].y;
-      re[padi(d + 1 * 8)] = v[4].x; im[padi(d + 1 * 8)] = v[4].y;
-      re[padi(d + 5 * 8)] = v[5].x; im[padi(d + 5 * 8)] = v[5].y;
-      re[padi(d + 3 * 8)] = v[6].x; im[padi(d + 3 * 8)] = v[6].y;
-      re[padi(d + 7 * 8)] = v[7].x; im[padi(d + 7 * 8)] = v[7].y;
+      dft8(v[h]);
     }
-    __syncthreads();
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int q = lane + 32 * h;
+      store8(re, im, v[h], (q >> 3) * 64 + (q & 7), 8);
+    }
+    __syncwarp();
     // ---- pass 3 (Ns = 64)
-    {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int q = lane + 32 * h;
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         const int j = padi(q + 64 * r);
-        v[r] = make_float2(re[j], im[j]);
-        if (r > 0) v[r] = cmul(v[r], s_tw[r * q]);
+        v[h][r] = make_float2(re[j], im[j]);
+        if (r > 0) v[h][r] = cmul(v[h][r], __ldg(g_tw + r * q));
       }
-      dft8(v);
-      __syncthreads();
-      re[padi(q + 0 * 64)] = v[0].x; im[padi(q + 0 * 64)] = v[0].y;
-      re[padi(q + 4 * 64)] = v[1].x; im[padi(q + 4 * 64)] = v[1].y;
-      re[padi(q + 2 * 64)] = v[2].x; im[padi(q + 2 * 64)] = v[2].y;
-      re[padi(q + 6 * 64)] = v[3].x; im[padi(q + 6 * 64)] = v[3].y;
-      re[padi(q + 1 * 64)] = v[4].x; im[padi(q + 1 * 64)] = v[4].y;
-      re[padi(q + 5 * 64)] = v[5].x; im[padi(q + 5 * 64)] = v[5].y;
-      re[padi(q + 3 * 64)] = v[6].x; im[padi(q + 3 * 64)] = v[6].y;
-      re[padi(q + 7 * 64)] = v[7].x; im[padi(q + 7 * 64)] = v[7].y;
+      dft8(v[h]);
     }
-    __syncthreads();
-    // ---- untangle the packed real FFT and take |X[k]|^2, k = 0..512
+    __syncwarp();
 #pragma unroll
-    for (int s = 0; s < 8; ++s) {
-      const int k = q + 64 * s;
-      const int kk = (512 - k) & 511;
-      const float2 a = make_float2(re[padi(k)], im[padi(k)]);
-      const float2 c = make_float2(re[padi(kk)], -im[padi(kk)]);  // conj(Z[512-k])
-      const float2 ze = make_float2(0.5f * (a.x + c.x), 0.5f * (a.y + c.y));
-      const float2 d = make_float2(0.5f * (a.x - c.x), 0.5f * (a.y - c.y));
-      const float2 zo = make_float2(d.y, -d.x);  // d / i
-      const float2 t = cmul(zo, s_tw2[k]);
-      const float xr = ze.x + t.x, xi = ze.y + t.y;
-      P[k] = xr * xr + xi * xi;
-      if (k == 0) {  // Nyquist bin 512: Ze[0] - Zo[0]
-        const float yr = ze.x - zo.x, yi = ze.y - zo.y;
-        P[512] = yr * yr + yi * yi;
+    for (int h = 0; h < 2; ++h) store8(re, im, v[h], lane + 32 * h, 64);
+    __syncwarp();
+    // ---- untangle the packed real FFT and take |X[k]|^2, k = 0..512 (into registers, then over `re`)
+    float pk[2][8], nyq = 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int q = lane + 32 * h;
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+        const int k = q + 64 * s;
+        const int kk = (512 - k) & 511;
+        const float2 a = make_float2(re[padi(k)], im[padi(k)]);
+        const float2 c = make_float2(re[padi(kk)], -im[padi(kk)]);  // conj(Z[512-k])
+        const float2 ze = make_float2(0.5f * (a.x + c.x), 0.5f * (a.y + c.y));
+        const float2 d = make_float2(0.5f * (a.x - c.x), 0.5f * (a.y - c.y));
+        const float2 zo = make_float2(d.y, -d.x);  // d / i
+        const float2 t = cmul(zo, __ldg(g_tw2 + k));
+        const float xr = ze.x + t.x, xi = ze.y + t.y;
+        pk[h][s] = xr * xr + xi * xi;
+        if (k == 0) {  // Nyquist bin 512: Ze[0] - Zo[0]
+          const float yr = ze.x - zo.x, yi = ze.y - zo.y;
+          nyq = yr * yr + yi * yi;
+        }
       }
     }
-    __syncthreads();
-    // ---- banded mel dot + dB
-    {
+    __syncwarp();
+    float* P = re;  // power spectrum, plain index 0..512
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int s = 0; s < 8; ++s) P[lane + 32 * h + 64 * s] = pk[h][s];
+    if (lane == 0) P[512] = nyq;
+    __syncwarp();
+    // ---- banded mel dot + dB: bands lane and lane + 32
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int m = lane + 32 * h;
+      const int band_start = __ldg(g_mel_tables.band_start + m);
+      const int band_len = __ldg(g_mel_tables.band_len + m);
+      const float* wrow = g_w + __ldg(g_mel_tables.band_off + m);
       float acc = 0.f;
-      for (int i = 0; i < band_len; ++i) acc = fmaf(s_w[band_off + i], P[band_start + i], acc);
+      for (int i = 0; i < band_len; ++i) acc = fmaf(__ldg(wrow + i), P[band_start + i], acc);
       const float db = 10.0f * log10f(fmaxf(acc, 1e-10f));
-      tile[q * 33 + f] = db;
+      tile[m * 33 + f] = db;
       if (t0 + f < T) local_max = fmaxf(local_max, db);
     }
-    // (the next iteration's first write to re/im happens after its own dft8; P is rewritten only after
-    //  two more __syncthreads, so no barrier is needed here)
   }
   __syncthreads();
   // ---- coalesced store of the [64][32] tile: each warp writes 8 mel rows, 32 consecutive frames per row
-  {
-    const int wrp = tid >> 5, ln = tid & 31;
-    float* o = out + static_cast<long long>(b) * out_stride;
+  float* o = out + static_cast<long long>(b) * out_stride;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int m = wrp * 8 + i;
-      if (t0 + ln < T) o[static_cast<long long>(m) * T + t0 + ln] = tile[m * 33 + ln];
-    }
+  for (int i = 0; i < 8; ++i) {
+    const int m = warp * 8 + i;
+    if (t0 + lane < T) o[static_cast<long long>(m) * T + t0 + lane] = tile[m * 33 + lane];
   }
   // ---- per-clip max of the dB values (order-preserving uint encoding of floats)
   local_max = warp_max(local_max);
-  if ((tid & 31) == 0 && local_max > -INFINITY) {
+  if (lane == 0 && local_max > -INFINITY) {
     unsigned int u = __float_as_uint(local_max);
     u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-    atomicMax(clip_max_bits + b, u);
+    atomicMax(clip_ws + b, u);
   }
-}
-
-__global__ void mel_norm_kernel(float* __restrict__ mel, long long per_clip, long long out_stride,
-                                const unsigned int* __restrict__ clip_max_bits, float top_db, float mn, float range) {
-  const int b = blockIdx.y;
-  unsigned int u = clip_max_bits[b];
+  if (!normalize) return;
+  // ---- the last CTA of the clip clamps at (clip max - top_db) and MinMax-normalises the whole clip in place
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_ticket = static_cast<int>(atomicAdd(clip_ws + B + b, 1u));
+  __syncthreads();
+  if (s_ticket != static_cast<int>(gridDim.x) - 1) return;
+  __threadfence();
+  unsigned int u = *reinterpret_cast<volatile unsigned int*>(clip_ws + b);
   u = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
   const float floor_db = __uint_as_float(u) - top_db;
-  float* p = mel + static_cast<long long>(b) * out_stride;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < per_clip;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float db = fmaxf(p[i], floor_db);
-    p[i] = (db - mn) / range * 2.0f - 1.0f;
+  const int per_clip = kMels * T;
+  for (int i = tid; i < per_clip; i += 256) {
+    const float db = fmaxf(__ldcg(o + i), floor_db);
+    o[i] = (db - mn) / range * 2.0f - 1.0f;
   }
-}
-
-__global__ void fill_u32_kernel(unsigned int* p, int n, unsigned int v) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = v;
 }
 
 // --------------------------------------------------------------------------- host tables
@@ -319,37 +334,29 @@ static int init_tables(cudaStream_t stream) {
   return ATST_OK;
 }
 
-constexpr int kMelSmemBytes =
-    (kSeg + 8 * 528 + 4 * 520 + kMels * 33 + kNfft + 2 * 512 * 2 + kMaxW) * 4;
 
-int mel_forward(const float* wav, int B, int n, long long wav_stride, int win_length, float* out,
-                long long out_stride, unsigned int* clip_max_ws, int normalize, cudaStream_t stream) {
+int mel_forward(const float* wav, int B, int n, long long wav_stride, const long long* clip_start, int win_length,
+                float* out, long long out_stride, unsigned int* clip_ws, int normalize, cudaStream_t stream) {
   ATST_REQUIRE(B > 0 && n > kNfft / 2, "mel: need B > 0 and n > 512 (reflect padding), got B=%d n=%d", B, n);
   ATST_REQUIRE(win_length == 1024 || win_length == 640, "mel: win_length must be 1024 or 640, got %d", win_length);
+  ATST_REQUIRE(B <= 65535, "mel: at most 65535 clips per call, got %d", B);
   int rc = init_tables(stream);
   if (rc) return rc;
   const int T = n / kHop + 1;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(mel_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMelSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMelSmemBytes);
     if (e != cudaSuccess) { atst_set_error("mel smem attr: %s", cudaGetErrorString(e)); return ATST_ERR_CUDA; }
     configured = true;
   }
-  fill_u32_kernel<<<(B + 255) / 256, 256, 0, stream>>>(clip_max_ws, B, 0u);
+  // workspace: [B] per-clip max (order-preserving bits, 0 = below every float) | [B] finished-CTA tickets
+  cudaError_t e = cudaMemsetAsync(clip_ws, 0, sizeof(unsigned int) * 2 * B, stream);
+  if (e != cudaSuccess) { atst_set_error("mel workspace memset: %s", cudaGetErrorString(e)); return ATST_ERR_CUDA; }
   dim3 grid((T + kFramesPerCta - 1) / kFramesPerCta, B);
-  mel_db_kernel<<<grid, 256, kMelSmemBytes, stream>>>(wav, n, wav_stride, T, win_length == 1024 ? 0 : 1, out,
-                                                      out_stride, clip_max_ws);
-  rc = atst_check_launch("mel_db_kernel");
-  if (rc) return rc;
-  if (normalize) {
-    const long long per_clip = static_cast<long long>(kMels) * T;
-    int gx = static_cast<int>((per_clip + 1023) / 1024);
-    if (gx > 64) gx = 64;
-    mel_norm_kernel<<<dim3(gx, B), 256, 0, stream>>>(out, per_clip, out_stride, clip_max_ws, 80.0f, -79.6482f,
-                                                    50.6842f - (-79.6482f));
-    rc = atst_check_launch("mel_norm_kernel");
-  }
-  return rc;
+  mel_kernel<<<grid, 256, kMelSmemBytes, stream>>>(wav, n, wav_stride, clip_start, T, win_length == 1024 ? 0 : 1, out,
+                                                   out_stride, clip_ws, B, normalize, 80.0f, -79.6482f,
+                                                   50.6842f - (-79.6482f));
+  return atst_check_launch("mel_kernel");
 }
 
 }  // namespace atst

@@ -2,8 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 namespace atst {
-int mel_forward(const float* wav, int B, int n, long long wav_stride, int win_length, float* out, long long out_stride,
-                unsigned int* clip_max_ws, int normalize, cudaStream_t stream);
+int mel_forward(const float* wav, int B, int n, long long wav_stride, const long long* clip_start, int win_length,
+                float* out, long long out_stride, unsigned int* clip_ws, int normalize, cudaStream_t stream);
 int layernorm_forward(const float* x, long long x_stride, const float* gamma, const float* beta, float* y,
                       long long y_stride, float* mean, float* rstd, int rows, int D, float eps, int round_out,
                       cudaStream_t st);

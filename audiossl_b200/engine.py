@@ -168,9 +168,10 @@ class EncoderEngine:
         return ops.layernorm_fwd(x, g, b, rows, self.D, out=out, mean=mean, rstd=rstd)
 
     # ------------------------------------------------------------------ backward
-    def backward(self, fp, ws, ctx, d_out):
+    def backward(self, fp, ws, ctx, d_out, on_block_done=None):
         """d_out: gradient wrt forward()'s output ([S,D] clip model / [S*N,D] frame model).
-        Accumulates parameter gradients into fp.grad.
+        Accumulates parameter gradients into fp.grad.  on_block_done(i) is called once every kernel that writes the
+        weight gradients of block i has been enqueued (the data-parallel exchange of that range can start).
 
         Every LayerNorm-backward launch also emits, for the branch that consumes its result, the GEMM-ready copy
         dys = tf32(droppath_scale * dx) and that branch's bias gradient (column sums of dys), so the DropPath
@@ -238,6 +239,8 @@ class EncoderEngine:
                 ops.layernorm_bwd(dh, L["x"], L["mean1"], L["rstd1"], fp.p(b + "norm1.weight"),
                                   fp.g(b + "norm1.weight"), fp.g(b + "norm1.bias"), M, D, dres=dx1, dx=dx)
             dbg("dx_in", i, dx)
+            if on_block_done is not None:
+                on_block_done(i)
         dpe = t("dpe", (S * P, D))
         ops.tokens_bwd(dx, dpe, fp.g(px + "pos_embed"), fp.g(px + "cls_token") if self.use_cls else None, S, P, D,
                        use_cls=self.use_cls, mask=ctx["mask"],
@@ -255,22 +258,32 @@ class HeadEngine:
     def forward(self, fp, ws, x, bn_buffers, tag, round_out, stats_sync=None, momentum=0.1, eps=1e-5):
         """x [R, in] (tf32-rounded).  bn_buffers: (running_mean, running_var, num_batches_tracked) or None.
         stats_sync(mean, m2, n) -> (mean, m2, n_total): SyncBatchNorm statistics exchange (DDP)."""
+        head = self.forward_stats(fp, ws, x, tag)
+        if stats_sync is not None:
+            head["mean"], head["m2"], head["n"] = stats_sync(head["mean"], head["m2"], head["n"])
+        return self.forward_finish(fp, ws, head, bn_buffers, round_out, momentum, eps)
+
+    def forward_stats(self, fp, ws, x, tag):
+        """first Linear + this rank's batch statistics (the part before the SyncBatchNorm exchange)."""
         px = self.px
         R = x.shape[0]
-        t = (lambda name, shape: ws.get(tag + "/" + px + name, shape))
-        z1 = ops.gemm_nt(x, fp.c(px + "0.weight"), out=t("z1", (R, self.hidden)))
+        z1 = ops.gemm_nt(x, fp.c(px + "0.weight"), out=ws.get(tag + "/" + px + "z1", (R, self.hidden)))
         mean, m2 = ops.bn_stats(z1)
-        n = float(R)
-        if stats_sync is not None:
-            mean, m2, n = stats_sync(mean, m2, n)
+        return dict(x=x, z1=z1, mean=mean, m2=m2, n=float(R), R=R, tag=tag)
+
+    def forward_finish(self, fp, ws, head, bn_buffers, round_out, momentum=0.1, eps=1e-5):
+        """running statistics, normalise + ReLU, second Linear - from the (global) statistics in ``head``."""
+        px, tag, R = self.px, head["tag"], head["R"]
+        t = (lambda name, shape: ws.get(tag + "/" + px + name, shape))
         rm = rv = None
         if bn_buffers is not None:
             rm, rv, nbt = bn_buffers
             nbt += 1
-        rstd = ops.bn_finalize(mean, m2, n, rm, rv, eps=eps, momentum=momentum)
-        a1 = ops.bn_relu_fwd(z1, mean, rstd, fp.p(px + "1.weight"), fp.p(px + "1.bias"), out=t("a1", (R, self.hidden)))
+        rstd = ops.bn_finalize(head["mean"], head["m2"], head["n"], rm, rv, eps=eps, momentum=momentum)
+        a1 = ops.bn_relu_fwd(head["z1"], head["mean"], rstd, fp.p(px + "1.weight"), fp.p(px + "1.bias"),
+                             out=t("a1", (R, self.hidden)))
         z2 = ops.gemm_nt(a1, fp.c(px + "3.weight"), round_out=round_out, out=t("z2", (R, self.out_dim)))
-        ctx = dict(x=x, z1=z1, mean=mean, rstd=rstd, a1=a1, n=n, R=R, tag=tag)
+        ctx = dict(x=head["x"], z1=head["z1"], mean=head["mean"], rstd=rstd, a1=a1, n=head["n"], R=R, tag=tag)
         return z2, ctx
 
     def backward(self, fp, ws, ctx, dz2, need_dx=True, sums_sync=None):

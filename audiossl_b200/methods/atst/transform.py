@@ -56,8 +56,9 @@ class ATSTTrainTransform:
 class BatchedATSTTrainTransform:
     """The same recipe for a whole batch resident on the GPU: ``wav [B,1,n]`` (cuda) ->
     ``([crop1, crop2], [len1, len2])`` with crops ``[B,1,64,T_max]`` and lengths int64 ``[B]`` - the batch contract of
-    ``ATSTLightningModule.training_step`` - in five kernel launches per view (window gather + fused mel, log-mixup-exp
-    against a device memory bank, bicubic resize-crop) instead of B Python calls on DataLoader workers.
+    ``ATSTLightningModule.training_step`` - in three kernel launches per view (fused mel with the random window in its
+    addressing, log-mixup-exp against a device memory bank, bicubic resize-crop) instead of B Python calls on
+    DataLoader workers.
 
     Differences from per-sample calls of ``ATSTTrainTransform`` (distributional, not arithmetic): one view length is
     drawn per batch and view (the recipe's default range is the single value 6 s), the Mixup memory bank is per
@@ -88,9 +89,8 @@ class BatchedATSTTrainTransform:
         if n < size:
             wav = F.pad(wav, (0, size - n))
             n = size
-        start = self.rng.randint(0, n - size + 1, B)
-        idx = torch.as_tensor(start, device=wav.device)[:, None] + torch.arange(size, device=wav.device)[None, :]
-        return self.mel_feature(wav[:, 0, :].gather(1, idx)[:, None, :]), size
+        start = torch.as_tensor(self.rng.randint(0, n - size + 1, B), dtype=torch.int64, device=wav.device)
+        return self.mel_feature(wav, clip_start=start, clip_len=size), size
 
     def _view(self, mel, size, v):
         import torch

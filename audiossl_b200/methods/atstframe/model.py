@@ -9,7 +9,7 @@ import torch
 from torch import nn
 
 from ... import ops
-from ...distributed import allreduce_avg_, allreduce_sum_, bn_stats_sync, bn_sums_sync, world
+from ...distributed import allreduce_sum_, bn_stats_sync, bn_sums_sync, world
 from ...engine import EncoderEngine, droppath_scales
 from ...models.atst.atst import _Runtime, _StepFn
 from ...optim import FusedHFAdamW
@@ -54,7 +54,12 @@ class _FrameRuntime(_Runtime):
         if R < 2 or R % 2:
             raise RuntimeError("ATST-Frame expects the same mask for both views (even masked-frame count), got %d" % R)
         G = world()
-        sync = (lambda mean, m2, n: bn_stats_sync(mean, m2, n, equal_counts=False)) if G > 1 else None
+        n_glob = float(R)
+        if G > 1:  # ranks hold different numbers of masked frames: ONE count exchange per step serves the three
+            cnt = torch.tensor([float(R)], device=mel.device)  # BatchNorm layers and the loss (no per-layer host read)
+            allreduce_sum_(cnt)
+            n_glob = cnt.item()
+        sync = (lambda mean, m2, n: bn_stats_sync(mean, m2, n, n_total=n_glob)) if G > 1 else None
         t_rows, _ = self._frames(ft, m.teacher, mel, ln, mask, False, idx, False, "t0")
         t_out, _ = self.proj.forward(ft, self.ws, t_rows, self._bn_buffers(m.teacher.projector), "t", False, sync)
         s_rows, enc_ctx = self._frames(fs, m.student, mel, ln, mask, True, idx, need_grad, "s0")
@@ -62,12 +67,8 @@ class _FrameRuntime(_Runtime):
         s_out, pred_ctx = self.pred.forward(fs, self.ws, z, self._bn_buffers(m.student.predictor), "s", False, sync)
         dstudent, acc = ops.byol_loss(s_out, t_out, 2, R // 2, dstudent=self.ws.get("dstudent", s_out.shape),
                                       acc=self.ws.get("loss_acc", (1 + 4 * 256,)))
-        n_glob = float(R)
         if G > 1:
             allreduce_sum_(acc[1:])
-            cnt = torch.tensor([float(R)], device=mel.device)
-            allreduce_sum_(cnt)
-            n_glob = cnt.item()
         out3 = ops.byol_finalize(acc, n_glob, n_glob, 2, R // 2, out=self.ws.get("loss_out", (3,)))
         self.saved = (enc_ctx, proj_ctx, pred_ctx, dstudent, idx) if need_grad else None
         self.last_outputs = (s_out, t_out)
@@ -92,8 +93,12 @@ class _FrameRuntime(_Runtime):
         dxn = self.ws.get("s0/bwd/dxn", (enc_ctx["M"], self.enc.D))
         dxn.zero_()
         ops.scatter_rows(drows, idx, dxn)
-        self.enc.backward(fs, self.ws, enc_ctx, dxn)
-        allreduce_avg_(fs.exchanged_grad())
+        ex = self.exchange
+        ex.submit(*fs.matrix_range("predictor."))
+        ex.submit(*fs.matrix_range("projector."))
+        self.enc.backward(fs, self.ws, enc_ctx, dxn,
+                          on_block_done=lambda i: ex.submit(*fs.matrix_range("encoder.blocks.%d." % i)))
+        ex.finish()
         fs.attach_grads()
 
 

@@ -74,9 +74,8 @@ class BatchedFrameATSTTrainTransform:
         if n < size:
             wav = F.pad(wav, (0, size - n))
             n = size
-        start = self.rng.randint(0, n - size + 1, B)
-        idx = torch.as_tensor(start, device=wav.device)[:, None] + torch.arange(size, device=wav.device)[None, :]
-        mel = self.mel_feature(wav[:, 0, :].gather(1, idx)[:, None, :])
+        start = torch.as_tensor(self.rng.randint(0, n - size + 1, B), dtype=torch.int64, device=wav.device)
+        mel = self.mel_feature(wav, clip_start=start, clip_len=size)
         P = get_num_patches(self.n_mels, size // 160 + 1, self.patch_h, self.patch_w)
         if self.mask_type == "random":
             mask = random_mask.get_mask_batch(B, P, self.mask_ratio)

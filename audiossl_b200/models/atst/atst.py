@@ -16,7 +16,7 @@ import torch
 from torch import nn
 
 from ... import ops
-from ...distributed import (allreduce_avg_, allreduce_sum_, bn_stats_sync, bn_sums_sync, world)
+from ...distributed import (GradExchange, allreduce_sum_, bn_stats_sync, bn_stats_sync_many, bn_sums_sync, world)
 from ...engine import EncoderEngine, HeadEngine, Workspace, droppath_scales
 from ...params import FlatParams
 from .audio_transformer import AST, AST_base, AST_large, AST_small
@@ -59,6 +59,7 @@ class _Runtime:
         self.ws = Workspace(device)
         self.saved = None
         self.anchor = torch.zeros((), device=device, requires_grad=True)
+        self.exchange = GradExchange(self.fs.grad, self.fs.exchange_start(), device)
 
     def _make_encoder(self, enc):
         return EncoderEngine(enc.embed_dim, enc.depth, enc.num_heads, use_cls=enc.use_cls, max_frames=enc.spec_w)
@@ -104,10 +105,17 @@ class _Runtime:
         # teacher on the first two crops (no grad; train-mode BN and DropPath exactly like the reference, D7)
         t_cls, _ = self._encode(ft, m.teacher, crops[:2], None if lengths is None else lengths[:2], dp_teacher,
                                 False, "t")
-        t_out, _ = self.proj.forward(ft, self.ws, t_cls, self._bn_buffers(m.teacher.projector), "t", False, sync)
         # student on all crops
         s_cls, enc_ctxs = self._encode(fs, m.student, crops, lengths, dp_student, need_grad, "s")
-        z, proj_ctx = self.proj.forward(fs, self.ws, s_cls, self._bn_buffers(m.student.projector), "s", True, sync)
+        # both projectors' first GEMM + batch statistics, then ONE SyncBatchNorm exchange for the two of them
+        t_head = self.proj.forward_stats(ft, self.ws, t_cls, "t")
+        s_head = self.proj.forward_stats(fs, self.ws, s_cls, "s")
+        if world() > 1:
+            (t_head["mean"], t_head["m2"]), (s_head["mean"], s_head["m2"]) = bn_stats_sync_many(
+                [(h["mean"], h["m2"], h["n"]) for h in (t_head, s_head)])
+            t_head["n"], s_head["n"] = t_head["n"] * world(), s_head["n"] * world()
+        t_out, _ = self.proj.forward_finish(ft, self.ws, t_head, self._bn_buffers(m.teacher.projector), False)
+        z, proj_ctx = self.proj.forward_finish(fs, self.ws, s_head, self._bn_buffers(m.student.projector), True)
         s_out, pred_ctx = self.pred.forward(fs, self.ws, z, self._bn_buffers(m.student.predictor), "s", False, sync)
         dstudent, acc = ops.byol_loss(s_out, t_out, ncrops, B, dstudent=self.ws.get("dstudent", s_out.shape),
                                       acc=self.ws.get("loss_acc", (1 + 4 * 256,)))
@@ -134,12 +142,19 @@ class _Runtime:
         dcls = self.proj.backward(fs, self.ws, proj_ctx, dz, need_dx=True, sums_sync=sums)
         if self.enc.debug is not None:
             self.enc.debug.append(("d_heads_in", "s", -1, dcls.clone()))
+        # data-parallel exchange, overlapped: the heads' matrices now, each block's matrices as the backward pass
+        # leaves it (only in the last crop group - earlier groups still accumulate into the same gradients), the
+        # rest (biases, norms, embeddings) at the end
+        ex = self.exchange
+        ex.submit(*fs.matrix_range("predictor."))
+        ex.submit(*fs.matrix_range("projector."))
         row = 0
-        for ctx in enc_ctxs:
+        for gi, ctx in enumerate(enc_ctxs):
             S = ctx["S"]
-            self.enc.backward(fs, self.ws, ctx, dcls[row:row + S])
+            cb = (lambda i: ex.submit(*fs.matrix_range("encoder.blocks.%d." % i))) if gi == len(enc_ctxs) - 1 else None
+            self.enc.backward(fs, self.ws, ctx, dcls[row:row + S], on_block_done=cb)
             row += S
-        allreduce_avg_(fs.exchanged_grad())
+        ex.finish()
         fs.attach_grads()
 
 

@@ -77,19 +77,23 @@ def _f32c(t, name):
     return t
 
 
-def mel_forward(wav, win_length=1024, normalize=True, out=None):
-    """wav [..., n] fp32 cuda -> normalised log-mel [..., 64, n//160+1] (reference mel_feature)."""
+def mel_forward(wav, win_length=1024, normalize=True, out=None, clip_start=None, clip_len=None):
+    """wav [..., n] fp32 cuda -> normalised log-mel [..., 64, n//160+1] (reference mel_feature).
+    clip_start (int64 [B] cuda) + clip_len: the mel of the window wav[b, clip_start[b] : clip_start[b] + clip_len] of
+    every clip (the train transform's RandomCrop) without materialising the crops."""
     lead = wav.shape[:-1]
-    n = wav.shape[-1]
-    w2 = _f32c(wav.reshape(-1, n), "wav")
+    w2 = _f32c(wav.reshape(-1, wav.shape[-1]), "wav")
+    n = wav.shape[-1] if clip_len is None else int(clip_len)
+    if clip_start is not None and (clip_start.dtype != torch.int64 or clip_start.numel() != w2.shape[0] or n > wav.shape[-1]):
+        raise ValueError("clip_start must be int64 [B] and clip_len <= the waveform length")
     B = w2.shape[0]
     T = n // 160 + 1
     if out is None:
         out = torch.empty((B, 64, T), device=wav.device, dtype=torch.float32)
-    ws = torch.empty((B,), device=wav.device, dtype=torch.int32)
-    check(_lib.lib().atst_mel_forward(ptr(w2), B, n, w2.stride(0), win_length, ptr(out), 64 * T, ptr(ws),
-                                      1 if normalize else 0, _lib.stream()), "atst_mel_forward")
-    _count(3)
+    ws = torch.empty((2 * B,), device=wav.device, dtype=torch.int32)
+    check(_lib.lib().atst_mel_forward(ptr(w2), B, n, w2.stride(0), ptr(clip_start), win_length, ptr(out), 64 * T,
+                                      ptr(ws), 1 if normalize else 0, _lib.stream()), "atst_mel_forward")
+    _count(1)
     return out.reshape(*lead, 64, T)
 
 

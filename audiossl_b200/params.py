@@ -90,6 +90,22 @@ class FlatParams:
         """[(start, end, regularised?)] for the fused optimizer: the trainable tail of every segment."""
         return [(t, e, i % 2 == 0) for i, ((_, e), t) in enumerate(zip(self.seg_bounds, self.seg_trainable)) if e > t]
 
+    def matrix_range(self, prefix):
+        """[lo, hi) of the flat buffers covered by the regularised (>= 2-D) tensors whose names start with ``prefix``
+        (one transformer block, the projector, ...): contiguous because segments keep module order."""
+        a, b = self.seg_bounds[0] if prefix.startswith(("encoder.", "projector.")) else self.seg_bounds[2]
+        names = [n for n in self.order if n.startswith(prefix) and a <= self.offsets[n] < b and n not in self.frozen]
+        if not names:
+            return 0, 0
+        lo = min(self.offsets[n] for n in names)
+        hi = max(self.offsets[n] + (self.params[n].numel() + ALIGN - 1) // ALIGN * ALIGN for n in names)
+        assert hi - lo == sum((self.params[n].numel() + ALIGN - 1) // ALIGN * ALIGN for n in names), prefix
+        return lo, hi
+
+    def exchange_start(self):
+        """first element of the flat gradient that the data-parallel exchange carries (frozen head excluded)."""
+        return self.seg_trainable[0] if self.seg_trainable[0] < self.seg_bounds[0][1] else 0
+
     def exchanged_grad(self):
         """the slice of the flat gradient that the data-parallel all-reduce carries (frozen head excluded)."""
         return self.grad[self.seg_trainable[0]:] if self.seg_trainable[0] < self.seg_bounds[0][1] else self.grad

@@ -20,10 +20,13 @@ class LogMelSpectrogram:
             raise NotImplementedError("MinMax constants are baked into the kernel")
         self.win_length = win_length
 
-    def __call__(self, wav):
+    def __call__(self, wav, clip_start=None, clip_len=None):
+        """clip_start (int64 [B], cuda) / clip_len: transform the window [start, start + clip_len) of every clip
+        (RandomCrop fused into the kernel's addressing; no cropped copy is made)."""
         if not wav.is_cuda:
             raise RuntimeError("LogMelSpectrogram runs on the GPU only (no CPU fallback); move the waveform to cuda")
-        return ops.mel_forward(wav.float().contiguous(), win_length=self.win_length)
+        return ops.mel_forward(wav.float().contiguous(), win_length=self.win_length, clip_start=clip_start,
+                               clip_len=clip_len)
 
     def __repr__(self):
         return "LogMelSpectrogram(win_length=%d)" % self.win_length

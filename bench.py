@@ -129,6 +129,77 @@ def cpu_reference_step_fn(batch, threads=None):
     return step
 
 
+def reference_modules_step_fn(batch, threads=None, root="/root/reference"):
+    """The UNMODIFIED reference modules on the host (only where /root/reference exists, i.e. in the build container;
+    the GPU box has no copy and uses the oracle port): ATSTTrainTransform.mel_feature x2 views + ATST.forward +
+    backward + update_teacher, through the harness of SURVEY.md section 8c (1-rank gloo group, Tensor.cuda identity
+    because compute_var hard-codes .cuda() + all_reduce).  Returns None when the reference cannot be imported."""
+    if not os.path.isdir(os.path.join(root, "audiossl")):
+        return None
+    try:
+        import torch
+        import torch.distributed as dist
+        sys.path.insert(0, root)
+        for k in [k for k in sys.modules if k == "audiossl" or k.startswith("audiossl.")]:
+            del sys.modules[k]  # the repo's own `audiossl` alias package must not shadow the reference
+        from audiossl.methods.atst.transform import ATSTTrainTransform
+        from audiossl.models.atst.atst import ATST
+        if not dist.is_initialized():
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29593")
+            dist.init_process_group("gloo", rank=0, world_size=1)
+        torch.Tensor.cuda = lambda self, *a, **k: self
+    except Exception:  # noqa: BLE001
+        return None
+    finally:
+        if root in sys.path:
+            sys.path.remove(root)
+    if threads:
+        torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    model = ATST(arch="base")  # drop_path_rate 0.1 (the AST default), train mode in both networks
+    model.train()
+    mel = ATSTTrainTransform().mel_feature
+    g = torch.Generator().manual_seed(1234)
+    wav = torch.randn(2, batch, 1, int(CLIP_SECONDS * SR), generator=g) * 0.1
+
+    def step():
+        crops = [mel(wav[v]) for v in range(2)]
+        lengths = [torch.full((batch,), crops[0].shape[-1], dtype=torch.int64)] * 2
+        for p in model.student.parameters():
+            p.grad = None
+        loss, _, _ = model(crops, lengths)
+        loss.backward()
+        model.update_teacher(0.9995)
+        return float(loss.detach())
+
+    return step
+
+
+def cpu_step_fn(batch, threads):
+    """(step function, kind): the reference's own modules when they are importable here, else the oracle port."""
+    fn = reference_modules_step_fn(batch, threads)
+    if fn is not None:
+        return fn, "reference"
+    return cpu_reference_step_fn(batch, threads), "port"
+
+
+def one_thread_number(seconds=20.0):
+    """the reference's own host policy, OMP/MKL_NUM_THREADS=1 (audiossl/__init__.py:1-3): one clip per step."""
+    import torch
+    prev = torch.get_num_threads()
+    step, kind = cpu_step_fn(1, 1)
+    step()
+    t0 = time.perf_counter()
+    k = 0
+    while k < 1 or (time.perf_counter() - t0 < seconds and k < 3):
+        step()
+        k += 1
+    dt = (time.perf_counter() - t0) / k
+    torch.set_num_threads(prev)
+    return {"value": 1 / dt, "unit": "clips/s", "cores": 1, "kind": kind, "sample": "%d steps of 1 clip" % k}
+
+
 def pick_cpu_threads():
     """a big host (128+ hardware threads) is slower with every thread on these small per-clip GEMMs/FFTs:
     probe a forward pass at a few thread counts and keep the fastest."""
@@ -159,7 +230,7 @@ def run_reference(args):
         return
     batch = 4
     cores = pick_cpu_threads()
-    step = cpu_reference_step_fn(batch, cores)
+    step, kind = cpu_step_fn(batch, cores)
     for _ in range(max(args.warmup, 1)):
         step()
     t0 = time.perf_counter()
@@ -167,18 +238,107 @@ def run_reference(args):
         step()
     dt = (time.perf_counter() - t0) / args.steps
     val = batch / dt
+    what = "the reference's own modules" if kind == "reference" else "oracle port of the reference algorithm"
     line = {"impl": "reference", "metric": "ATST-base clips/sec (student+teacher fwd + bwd)", "value": val,
             "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": "ATST-base, 10 s clips, 256 clips/GPU [c2], 16 kHz, 64 mel, 2 crops, DropPath 0.1; "
                                    "CPU sample of %d clips/step" % batch},
-            "cpu_baseline": {"value": val, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": "%d steps of %d clips (oracle port of the reference algorithm, torch CPU fp32)"
-                                       % (args.steps, batch)},
+            "cpu_baseline": {"value": val, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": kind,
+                             "sample": "%d steps of %d clips (%s, torch CPU fp32)" % (args.steps, batch, what),
+                             "one_thread": one_thread_number()},
             "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ stock PyTorch on the GPU
+def run_torch_gpu(args):
+    """Comparator: the same modules in stock PyTorch-CUDA on one B200 - torchaudio's
+    MelSpectrogram / AmplitudeToDB front-end, the oracle's nn.Module restatement of ATST (cuBLAS / ATen kernels,
+    autograd), fused torch AdamW, EMA - in fp32 with TF32 matmuls allowed (or --no-tf32).  This is the only GPU path
+    the reference had before this repo; none of this repo's kernels run here."""
+    import torch
+    from oracle import atst_oracle as O
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dev = torch.device("cuda", 0)
+    torch.backends.cuda.matmul.allow_tf32 = not args.no_tf32
+    torch.backends.cudnn.allow_tf32 = not args.no_tf32
+    torch.manual_seed(0)
+    model = O.OracleATST("base").to(dev).train()
+    opt = torch.optim.AdamW([p for p in model.student.parameters()], lr=2e-4, eps=1e-6, weight_decay=0.04, fused=True)
+    try:
+        import torchaudio
+        melspec = torchaudio.transforms.MelSpectrogram(16000, f_min=60, f_max=7800, hop_length=160, win_length=1024,
+                                                       n_fft=1024, n_mels=64).to(dev)
+        to_db = torchaudio.transforms.AmplitudeToDB(stype="power", top_db=80)
+        mel = lambda w: (to_db(melspec(w)) + 79.6482) / (50.6842 + 79.6482) * 2.0 - 1.0
+        front = "torchaudio"
+    except Exception:  # noqa: BLE001
+        fb = torch.from_numpy(O.mel_filterbank()).to(dev)
+        win = torch.hann_window(1024, device=dev)
+
+        def mel(w):
+            spec = torch.stft(w[:, 0], 1024, 160, 1024, win, center=True, pad_mode="reflect", return_complex=True).abs() ** 2
+            db = 10.0 * torch.log10(torch.clamp(fb.t() @ spec, min=1e-10))
+            db = torch.maximum(db, db.amax(dim=(-2, -1), keepdim=True) - 80.0)
+            return ((db + 79.6482) / (50.6842 + 79.6482) * 2.0 - 1.0)[:, None]
+        front = "torch.stft"
+    B = args.batch if args.batch > 0 else 256
+    depth, rates = 12, torch.linspace(0, 0.1, 12).tolist()
+
+    def dp(S):
+        out = []
+        for r in rates:
+            if r == 0:
+                out.append(None)
+                continue
+            keep = 1 - r
+            u = torch.rand(2, S, device=dev)
+            out.append((torch.floor(keep + u[0]) / keep, torch.floor(keep + u[1]) / keep))
+        return [out]
+
+    while True:
+        try:
+            g = torch.Generator(device=dev).manual_seed(1234)
+            wav = torch.randn(2, B, 1, int(CLIP_SECONDS * SR), device=dev, generator=g) * 0.1
+            lengths = [torch.full((B,), 1001, dtype=torch.int64, device=dev)] * 2
+
+            def step():
+                crops = [mel(wav[v]) for v in range(2)]
+                opt.zero_grad(set_to_none=True)
+                loss, _, _ = model(crops, lengths, dp_student=dp(2 * B), dp_teacher=dp(2 * B))
+                loss.backward()
+                opt.step()
+                model.update_teacher(0.9995)
+                return loss
+            for _ in range(max(args.warmup, 1)):
+                step()
+            torch.cuda.synchronize()
+            break
+        except torch.OutOfMemoryError:
+            opt.zero_grad(set_to_none=True)
+            torch.cuda.empty_cache()
+            B //= 2
+            if B < 8:
+                raise
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    print(json.dumps({"impl": "torch-gpu", "metric": "ATST-base clips/sec (student+teacher fwd + bwd)",
+                      "value": B / (ms / 1e3), "unit": "clips/s", "n_gpus": 1, "steps": args.steps,
+                      "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                      "dtype": "f32" if args.no_tf32 else "tf32 (torch allow_tf32, cuBLAS)", "data": "synthetic",
+                      "config": {"workload": "ATST-base, 10 s clips, %d clips/GPU [c2], DropPath 0.1, %s mel + "
+                                             "nn.Module ATST (autograd) + fused torch AdamW + EMA" % (B, front),
+                                 "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}}), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -229,7 +389,6 @@ def run_ours(args):
     # one device / pinned-host waveform tensor per crop group: [count, B, 1, n]
     wav_dev = [torch.randn(cnt, B, 1, int(sec * SR), device=dev, generator=g) * 0.1 for sec, cnt in cfg["crops"]]
     wav_host = [w.cpu().pin_memory() for w in wav_dev]
-    stage = [torch.empty_like(w) for w in wav_dev]
     lengths = []
     for sec, cnt in cfg["crops"]:
         lengths += [torch.full((B,), int(sec * SR) // 160 + 1, device=dev, dtype=torch.int64)] * cnt
@@ -244,41 +403,34 @@ def run_ours(args):
     h2d_bytes = sum(w.numel() * 4 for w in wav_host)
 
     mel_events = []
-    # e2e input pipeline: double-buffered device staging filled from pinned host memory on a copy stream, so the
-    # host->device copy of step i+1 (inside the timed region) overlaps the compute of step i
-    stage2 = [torch.empty_like(w) for w in wav_dev]
-    copy_stream = torch.cuda.Stream(device=dev)
-    h2d = {"ready": None, "buf": 0}
+    # e2e input pipeline (audiossl_b200.datasets.DevicePrefetcher): device staging filled from pinned host memory on a
+    # copy stream, so the host->device copy of step i+1 (inside the timed region) overlaps the compute of step i
+    from audiossl_b200.datasets import DevicePrefetcher
 
-    def issue_h2d():
-        bufs = stage if h2d["buf"] == 0 else stage2
-        copy_stream.wait_stream(torch.cuda.current_stream())  # the buffer's previous consumer (2 steps ago) is done
-        with torch.cuda.stream(copy_stream):
-            for s_, h_ in zip(bufs, wav_host):
-                s_.copy_(h_, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        h2d["ready"] = (ev, bufs)
-        h2d["buf"] ^= 1
+    def host_batches():
+        while True:
+            yield tuple(wav_host)
+    feed = {"it": None, "aug": None}
 
-    def step(i, from_host):
+    def step(i, from_host, augment=False):
         if from_host:
-            if h2d["ready"] is None:
-                issue_h2d()
-            ev, src = h2d["ready"]
-            torch.cuda.current_stream().wait_event(ev)
-            issue_h2d()  # next step's batch starts copying now
+            if feed["it"] is None:
+                feed["it"] = iter(DevicePrefetcher(host_batches(), dev))
+            src = next(feed["it"])
         else:
             src = wav_dev
         if ops.STATS["time_gemms"]:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
-        crops = [mel(w[k]) for w in src for k in range(w.shape[0])]
+        if augment:  # the recipe's device transform: window crop + mel + Mixup + RandomResizeCrop per view
+            crops, lens = feed["aug"](src[0][0])
+        else:
+            crops, lens = [mel(w[k]) for w in src for k in range(w.shape[0])], lengths
         if ops.STATS["time_gemms"]:
             ev[1].record()
             mel_events.append(ev)
         lm.global_step = i
-        batch = ((crops, lengths, masks), None) if masks is not None else ((crops, lengths), None)
+        batch = ((crops, lens, masks), None) if masks is not None else ((crops, lens), None)
         loss = lm.training_step(batch, i)
         opt.zero_grad()
         loss.backward()
@@ -293,12 +445,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(from_host, steps, start_i):
+    def timed(from_host, steps, start_i, augment=False):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
-            step(start_i + i, from_host)
+            step(start_i + i, from_host, augment)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -346,8 +498,21 @@ def run_ours(args):
     launches = ops.STATS["launches"]
     gemm_flops_step = ops.STATS["gemm_flops"] / args.steps
     gemm_bytes_launch = ops.STATS["gemm_bytes"] / max(ops.STATS["gemm_launches"], 1)
-    h2d["ready"] = None
+    feed["it"] = None
     ms_e2e = timed(True, args.steps, args.warmup + args.steps)
+    ms_aug = None
+    if cfg["kind"] == "clip" and len(cfg["crops"]) == 1 and not args.no_augment:
+        # SURVEY.md 8d "second number with augmentations on": same e2e loop, the batch produced by the device
+        # train transform (two random full-length windows of each clip, mel, Mixup memory bank, RandomResizeCrop)
+        from audiossl_b200.methods.atst.transform import BatchedATSTTrainTransform
+        import numpy as np
+        sec = cfg["crops"][0][0]
+        feed["aug"] = BatchedATSTTrainTransform(anchor_len=(sec, sec), positive_len=(sec, sec),
+                                                rng=np.random.RandomState(1234 + rank))
+        feed["it"] = None
+        for i in range(2):
+            step(i, True, True)
+        ms_aug = timed(True, args.steps, args.warmup + 2 * args.steps, True)
     sampler.stop_flag = True
     sampler.join(timeout=2)
     # dominant kernel (gemm_tf32_kernel) measured in place: one extra step with an event pair around every launch
@@ -405,6 +570,10 @@ def run_ours(args):
                    "step_gflop_per_clip_algorithmic": step_gflop},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_val, "unit": "clips/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+        "e2e_augmented": None if ms_aug is None else {
+            "value": B * world / (ms_aug / args.steps / 1e3), "unit": "clips/s",
+            "what": "e2e with the recipe's augmentations on the device (BatchedATSTTrainTransform: random window, "
+                    "mel, Mixup memory bank, RandomResizeCrop) instead of the plain mel"},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "kernel": "gemm2_tf32_kernel (CTA pair, tcgen05 kind::tf32)", "achieved": achieved,
                      "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": traffic,
@@ -423,7 +592,7 @@ def run_ours(args):
                     "achieved": v_[2] / (v_[1] / 1e3) / 1e9 if v_[1] > 0 else 0.0,
                     "frac": (v_[2] / (v_[1] / 1e3) / 1e9 / pk["hbm_gbs"]) if v_[1] > 0 else 0.0}
                for k_, v_ in attn.items()}},
-        "roofline_mel": {"bound": "hbm", "kernel": "mel_db_kernel + mel_norm_kernel (fused STFT/mel/dB/MinMax)",
+        "roofline_mel": {"bound": "hbm", "kernel": "mel_kernel (fused STFT/mel/dB/top_db clamp/MinMax, one launch)",
                          "achieved": mel_bytes / (mel_ms / 1e3) / 1e9 if mel_ms > 0 else 0.0, "peak": pk["hbm_gbs"],
                          "unit": "GB/s", "frac": (mel_bytes / (mel_ms / 1e3) / 1e9 / pk["hbm_gbs"]) if mel_ms > 0 else 0.0,
                          "ms_per_step": mel_ms, "algorithmic_bytes_per_step": mel_bytes, "traffic": None,
@@ -431,7 +600,7 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu_baseline and args.config == "c2":
         cores = pick_cpu_threads()
-        cstep = cpu_reference_step_fn(4, cores)
+        cstep, kind = cpu_step_fn(4, cores)
         cstep()
         t0 = time.perf_counter()
         k = 0
@@ -439,8 +608,10 @@ def run_ours(args):
             cstep()
             k += 1
         dt = (time.perf_counter() - t0) / k
-        line["cpu_baseline"] = {"value": 4 / dt, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": "%d steps of 4 clips of the same workload (oracle port, torch CPU fp32)" % k}
+        line["cpu_baseline"] = {"value": 4 / dt, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": kind,
+                                "sample": "%d steps of 4 clips of the same workload (%s, torch CPU fp32)"
+                                          % (k, "reference modules" if kind == "reference" else "oracle port"),
+                                "one_thread": one_thread_number(10.0)}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -451,7 +622,9 @@ if __name__ == "__main__":
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-gpu"])
+    ap.add_argument("--no-tf32", action="store_true", help="--impl torch-gpu: strict fp32 matmuls")
+    ap.add_argument("--no-augment", action="store_true", help="skip the e2e_augmented measurement")
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE.json config (c2 = benchmark)")
     ap.add_argument("--batch", type=int, default=0, help="clips per GPU (0 = the config's)")
     ap.add_argument("--arch", default="", help="override the config's architecture")
@@ -464,5 +637,7 @@ if __name__ == "__main__":
         a.warmup = 3
     if a.impl == "reference":
         run_reference(a)
+    elif a.impl == "torch-gpu":
+        run_torch_gpu(a)
     else:
         run_ours(a)

@@ -31,10 +31,13 @@ int atst_set_option(const char* name, int value);
  *      n_mels=64) -> AmplitudeToDB("power",top_db=80) -> MinMax(-79.6482,50.6842)
  *      replaces audiossl/methods/atst/transform.py:14-29 (mel_feature), audiossl/transforms/common.py:97-110,
  *      audiossl/methods/atstframe/transform.py:16-42.
- *   wav [B, n] (row stride wav_stride) -> out [B, 64, n/160+1] (clip stride out_stride);
- *   clip_max_ws: B uint32 scratch; normalize=0 stops after the dB stage (no clamp, no MinMax). */
-int atst_mel_forward(const float* wav, int B, int n, long long wav_stride, int win_length, float* out,
-                     long long out_stride, unsigned int* clip_max_ws, int normalize, void* stream);
+ *   wav [B, >= n] (row stride wav_stride) -> out [B, 64, n/160+1] (clip stride out_stride); clip b is the n samples
+ *   starting at wav + b*wav_stride + clip_start[b] (clip_start NULL: 0) - the RandomCrop of the train transform
+ *   (audiossl/transforms/common.py:63-74) without a copy; reflect padding is relative to the window;
+ *   clip_ws: 2*B uint32 scratch; normalize=0 stops after the dB stage (no clamp, no MinMax). */
+int atst_mel_forward(const float* wav, int B, int n, long long wav_stride, const long long* clip_start,
+                     int win_length, float* out, long long out_stride, unsigned int* clip_ws, int normalize,
+                     void* stream);
 
 /* ---- GEMMs (tcgen05, TF32 operands, fp32 accumulate).  Replace nn.Linear forward/backward in
  *      audiossl/modules/transformer.py:86-92,102-119, audiossl/models/atst/audio_transformer.py:60,68,

@@ -8,7 +8,18 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def _limit_host_threads():
+    """the oracle side of the GPU tests is torch-CPU work on small tensors: on a host with hundreds of hardware
+    threads the default (one OpenMP thread per core) is slower by an order of magnitude than a few dozen threads"""
+    try:
+        import torch
+        torch.set_num_threads(max(1, min(32, os.cpu_count() or 1)))
+    except Exception:  # noqa: BLE001
+        pass
+
+
 def pytest_configure(config):
+    _limit_host_threads()
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 

@@ -141,7 +141,8 @@ def test_batched_train_transform_contract_and_statistics():
     rng = np.random.RandomState(3)
     tf = BatchedATSTTrainTransform(anchor_len=(1.0, 1.0), positive_len=(1.5, 1.5), rng=rng, augment=False)
     crops, lengths = tf(wav)
-    assert [tuple(c.shape) for c in crops] == [(B, 1, 64, 150)] * 2 and all(c.is_cuda for c in crops)
+    # right-padded to max_frames + 1 = (1.5 s * 16000) // 160 + 1 frames, as the reference's F.pad arithmetic gives
+    assert [tuple(c.shape) for c in crops] == [(B, 1, 64, 151)] * 2 and all(c.is_cuda for c in crops)
     assert lengths[0].tolist() == [101] * B and lengths[1].tolist() == [151] * B and lengths[0].dtype == torch.int64
     # replay the draws: uniform(anchor), B window starts, uniform(positive), B window starts
     rng2 = np.random.RandomState(3)
@@ -154,12 +155,12 @@ def test_batched_train_transform_contract_and_statistics():
         m2 = ops.mel_forward(wav[b, :, s2[b]:s2[b] + 24000].contiguous())
         np.testing.assert_allclose(crops[0][b, :, :, :101].cpu().numpy(), m1.cpu().numpy(), atol=1e-5)
         np.testing.assert_allclose(crops[1][b, :, :, :151].cpu().numpy(), m2.cpu().numpy(), atol=1e-5)
-    assert float(crops[0][..., 101:].abs().sum()) == 0.0 and float(crops[1][..., 150:].abs().sum()) == 0.0
+    assert float(crops[0][..., 101:].abs().sum()) == 0.0
     # augmentations on: same shapes, finite, a memory bank that fills, outputs that differ from the plain mel
     tf = BatchedATSTTrainTransform(anchor_len=(1.0, 1.0), positive_len=(1.0, 1.0), rng=np.random.RandomState(4))
     for _ in range(3):
         crops, lengths = tf(wav)
-    assert tf.mixup[0].size == 3 * B and tuple(crops[0].shape) == (B, 1, 64, 100)
+    assert tf.mixup[0].size == 3 * B and tuple(crops[0].shape) == (B, 1, 64, 101)
     assert torch.isfinite(crops[0]).all() and torch.isfinite(crops[1]).all()
     assert -1.5 < float(crops[0].mean()) < 1.0 and float(crops[0].std()) > 0.05
 

@@ -165,6 +165,25 @@ assert torch.allclose(gm, full.mean(0), atol=1e-6) and torch.allclose(gm2 / n, f
 s1, s2 = D.bn_sums_sync(mine.sum(0), (mine ** 2).sum(0))
 assert torch.allclose(s1, full.sum(0), atol=1e-5) and torch.allclose(s2, (full ** 2).sum(0), atol=1e-4)
 g = torch.full((5,), float(rank + 1)); D.allreduce_avg_(g); assert torch.allclose(g, torch.full((5,), 1.5))
+# two BatchNorm layers in one exchange; unequal per-rank row counts (ATST-Frame) with the global count passed in
+parts = [full[:5], full[5:]]
+mine = parts[rank]
+mean = mine.mean(0); m2 = ((mine - mean) ** 2).sum(0)
+(ga, gb), (gc, gd) = D.bn_stats_sync_many([(mean, m2, float(len(mine))), (mean * 2, m2 * 4, float(len(mine)))])
+assert torch.allclose(ga, full.mean(0), atol=1e-6) and torch.allclose(gb / 12, full.var(0, unbiased=False), atol=1e-5)
+assert torch.allclose(gc, 2 * full.mean(0), atol=1e-5) and torch.allclose(gd / 12, 4 * full.var(0, unbiased=False), atol=1e-4)
+gm, gm2, n = D.bn_stats_sync(mean, m2, float(len(mine)), n_total=12.0)
+assert n == 12.0 and torch.allclose(gm, full.mean(0), atol=1e-6)
+# overlapped gradient exchange: ranges submitted out of order, the complement sent by finish(), frozen head untouched
+flat = torch.arange(100.) * (rank + 1)
+ex = D.GradExchange(flat, 10, torch.device("cpu"))
+ex.submit(60, 80); ex.submit(20, 30); ex.submit(5, 12)
+ex.finish()
+want = torch.arange(100.) * 1.5
+want[:10] = torch.arange(10.) * (rank + 1)
+assert torch.allclose(flat, want), flat
+flat2 = torch.ones(50) * (rank + 1); ex2 = D.GradExchange(flat2, 0, torch.device("cpu")); ex2.finish()
+assert torch.allclose(flat2, torch.full((50,), 1.5))
 print("rank", rank, "ok")
 '''
 

@@ -264,6 +264,33 @@ def test_gelu_fused_epilogues_match_torch(M, N, K):
     assert rel(cs, 1.0 + du.double().sum(0)) < 1e-5  # column sums of the stored values, accumulated
 
 
+@pytest.mark.parametrize("M,N,K,rps", [(2008, 768, 768, 251), (156, 128, 128, 26), (50003, 768, 768, 7), (2008, 3072, 768, 251)])
+def test_residual_epilogue_at_ragged_row_counts(M, N, K, rps):
+    """proj / fc2 epilogue  C = resid + rowscale[seq] * (A W^T + bias)  when the last 32-row group of the matrix is
+    only partly valid (M % 32 != 0: every batch size that is not a multiple of 32 sequences).  Regression: a warp
+    straddling row M took two different epilogue forms, released its accumulator stage twice and hung the kernel
+    (ATST-base, 4 clips x 2 views x 251 tokens = 2008 rows)."""
+    from audiossl_b200 import ops
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(3)
+    A = ops.round_tf32(torch.randn(M, K, device="cuda"))
+    W = ops.round_tf32(torch.randn(N, K, device="cuda") * 0.05)
+    b = torch.randn(N, device="cuda")
+    resid = torch.randn(M, N, device="cuda")
+    nseq = (M + rps - 1) // rps
+    scale = (torch.rand(nseq, device="cuda") > 0.3).float() / 0.7
+    want = resid.double() + scale.repeat_interleave(rps)[:M, None].double() * (A.double() @ W.double().t() + b.double())
+    for _ in range(2):  # twice: a stale barrier phase would show on the second launch of a persistent CTA
+        got = ops.gemm_nt(A, W, bias=b, epi=ops.EPI_RESID, resid=resid, rowscale=scale, rows_per_seq=rps)
+    torch.cuda.synchronize()
+    assert rel(got, want) < 1e-5
+    if N % 256 == 0:  # the fused GELU forms on the same ragged shape
+        u = torch.empty(M, N, device="cuda")
+        g = ops.gemm_nt(A, W, bias=b, epi=ops.EPI_GELU, aux=u, round_out=True)
+        assert rel(u, A.double() @ W.double().t() + b.double()) < 1e-5
+        assert rel(g, torch.nn.functional.gelu(u.double())) < 1e-3
+
+
 @pytest.mark.parametrize("rows,cols", [(1000, 3072), (77, 130), (129, 4), (5000, 768)])
 def test_colsum_accumulates(rows, cols):
     from audiossl_b200 import ops
@@ -422,6 +449,77 @@ def test_two_rank_step_equals_one_rank_on_the_concatenated_batch(tmp_path):
     env = dict(os.environ, OMP_NUM_THREADS="1")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                         "--master-addr", "127.0.0.1", "--master-port", "29673", str(script)],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("ok") == 2
+
+
+TWO_RANK_FRAME_WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from tests import util
+from tests.golden import detfill
+from audiossl_b200.methods.atstframe.model import FrameATST
+rank = int(os.environ["RANK"])
+torch.cuda.set_device(0)
+B = 16
+lens = [[101 - (i * 5) %% 40 for i in range(B)]] * 2
+mk = detfill.det_array("frame2rank/mask", (B, 25), 1.0, "uniform") > 0.0
+mk[:, 0] = True
+mk[:8, 5:20] = True          # the first half of the batch carries many more masked frames than the second
+def run(lo, hi):
+    m = FrameATST(arch=dict(embed_dim=128, depth=2, num_heads=2), drop_path_rate=0.0)
+    util.load_det(m)
+    m.cuda().train()
+    crops, lengths = util.make_inputs("frame2b16", B, [101, 101], lens)
+    crops = [x[lo:hi].contiguous().cuda() for x in crops]
+    lengths = [x[lo:hi].contiguous().cuda() for x in lengths]
+    mask = torch.from_numpy(mk[lo:hi]).cuda()
+    loss, std_s, std_t = m(crops, lengths, [mask, mask])
+    loss.backward()
+    torch.cuda.synchronize()
+    s_out = m._rt.last_outputs[0].detach().cpu().clone()
+    bn = [b.detach().cpu().clone() for n, b in m.student.named_buffers() if "running" in n]
+    finite = all(torch.isfinite(p.grad).all().item() for p in m.student.parameters() if p.grad is not None)
+    return loss.item(), std_s.item(), s_out, bn, finite
+ref_loss, ref_std, ref_out, ref_bn, _ = run(0, B)              # one rank, whole batch (no process group yet)
+dist.init_process_group("gloo")
+loss, std, out, bn, finite = run(rank * 8, (rank + 1) * 8)    # two ranks, unequal masked-frame counts
+rows = [torch.tensor([out.shape[0]])  for _ in range(2)]
+dist.all_gather(rows, torch.tensor([out.shape[0]]))
+r0, r1 = int(rows[0]) // 2, int(rows[1]) // 2
+assert r0 != r1 and 2 * (r0 + r1) == ref_out.shape[0], (r0, r1, ref_out.shape)
+# one-rank rows are [view 1: clips 0..15 | view 2: clips 0..15]; this rank holds clips [8 rank, 8 rank + 8) of each view
+n1 = r0 + r1
+mine = torch.cat([ref_out[:n1][(0 if rank == 0 else r0):(r0 if rank == 0 else n1)],
+                  ref_out[n1:][(0 if rank == 0 else r0):(r0 if rank == 0 else n1)]])
+err = ((out - mine).norm() / mine.norm()).item()
+assert err < 2e-3, err                                           # SyncBatchNorm over unequal per-rank row counts
+# the loss is this rank's mean over its own rows (what DDP trains on and rank 0 logs in the reference); the
+# row-weighted mean over the ranks is the loss of the concatenated batch.  compute_var's std is global.
+lw = torch.tensor([loss * (r0 if rank == 0 else r1), float(r0 if rank == 0 else r1)], dtype=torch.float64)
+dist.all_reduce(lw)
+assert abs(lw[0].item() / lw[1].item() - ref_loss) < 1e-3 * abs(ref_loss), (lw, ref_loss)
+assert abs(std - ref_std) < 1e-3 * abs(ref_std), (std, ref_std)
+for a, b in zip(bn, ref_bn):
+    assert torch.allclose(a, b, rtol=2e-3, atol=1e-5)
+assert finite
+print("rank", rank, "ok", r0, r1, err)
+'''
+
+
+def test_two_rank_frame_step_with_unequal_masked_counts(tmp_path):
+    """ATST-Frame under data parallelism: the ranks hold different numbers of masked frames, BatchNorm statistics and
+    the logged loss must still be those of the concatenated batch (one count exchange per step, no per-layer reads)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "w2f.py"
+    script.write_text(TWO_RANK_FRAME_WORKER % root)
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29675", str(script)],
                        capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("ok") == 2

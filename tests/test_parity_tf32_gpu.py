@@ -240,7 +240,7 @@ def _three_steps(lm, ref, batches, frame, loss_rtol=5e-3, emulate=True):
     return opt
 
 
-def _compare_updates(model, ref, init, label, tol):
+def _compare_updates(model, ref, init, label, tol, lr_sum=None):
     """every student and teacher tensor: the accumulated update (value - initial value) against the oracle's.
     Adam normalises gradients element-wise (the first steps are ~ lr * sign(g)), so the decorrelated TF32 rounding
     of the two sides (module docstring) shows up as sign flips of the small-gradient elements: the bound on the
@@ -255,7 +255,13 @@ def _compare_updates(model, ref, init, label, tol):
         if want.norm().item() == 0.0:
             assert mine.norm().item() == 0.0, "%s%s moved, the reference leaves it untouched" % (label, name)
             continue
-        e = ((mine - want).norm() / want.norm()).item()
+        # Adam moves every element by about lr per step whatever the gradient's size, so a tensor whose true gradient
+        # is numerically zero (the final-norm bias: BatchNorm in the projector removes any constant added to its
+        # input) takes steps that are pure rounding noise in BOTH implementations - with transformers' eps = 1e-6 they
+        # come out a few hundred times smaller than a regular step.  Measure against the larger of the reference
+        # update and a fifth of a full-rate update, so that such tensors are checked for being small, not for agreeing
+        floor = 0.0 if lr_sum is None else 0.2 * lr_sum * want.numel() ** 0.5
+        e = ((mine - want).norm() / max(want.norm().item(), floor)).item()
         n += 1
         if e > worst[0]:
             worst = (e, name)
@@ -279,7 +285,7 @@ def test_three_training_steps_follow_the_oracle_every_tensor():
                                                                               [101 - (i * 9) % 40 for i in range(B)]])
         batches.append((crops, lengths))
     opt = _three_steps(lm, ref, batches, frame=False)
-    worst, n = _compare_updates(lm.model, ref, init, "clip: ", tol=0.5)
+    worst, n = _compare_updates(lm.model, ref, init, "clip: ", tol=0.5, lr_sum=float(sum(lm.mylr_scheduler[:3])))
     # the clip forward never reads mask_embed: no gradient, no Adam step, no weight decay (reference: grad is None)
     assert torch.equal(lm.model.student.encoder.mask_embed.detach().cpu(), init["student.encoder.mask_embed"])
     assert lm.model.student.encoder.mask_embed.grad is None
@@ -309,6 +315,6 @@ def test_three_frame_training_steps_follow_the_oracle_every_tensor():
         mask = torch.from_numpy(mk)
         batches.append((crops, lengths, [mask, mask]))
     _three_steps(lm, ref, batches, frame=True)
-    worst, n = _compare_updates(lm.model, ref, init, "frame: ", tol=0.5)
+    worst, n = _compare_updates(lm.model, ref, init, "frame: ", tol=0.5, lr_sum=float(sum(lm.mylr_scheduler[:3])))
     assert not torch.equal(lm.model.student.encoder.mask_embed.detach().cpu(), init["student.encoder.mask_embed"])
     print("frame 3 steps: worst update error %.2e (%s) over %d tensors" % (worst[0], worst[1], n))
