@@ -71,7 +71,7 @@ def main(args):
             if rank == 0 and step % args.log_every == 0:
                 dt = time.time() - t0
                 print("step %d  loss %.4f  std_s %.3f  std_t %.3f  lr %.2e  %.0f clips/s" % (
-                    step, float(loss), float(model.logged["std_cls_s"]), float(model.logged["std_cls_t"]),
+                    step, float(loss.detach()), float(model.logged["std_cls_s"]), float(model.logged["std_cls_t"]),
                     model.logged["lr"], seen / dt), flush=True)
                 t0, seen = time.time(), 0
             if rank == 0 and (step % args.save_every == 0 or step == args.max_steps):

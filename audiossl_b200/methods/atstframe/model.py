@@ -80,7 +80,7 @@ class _FrameRuntime(_Runtime):
         enc_ctx, proj_ctx, pred_ctx, dstudent, idx = self.saved
         self.saved = None
         fs = self.fs
-        fs.grad.zero_()
+        self._claim_gradient_buffer()
         d = self.ws.get("dstudent_scaled", dstudent.shape)
         torch.mul(dstudent, grad_out.to(dstudent.dtype), out=d)
         ops.round_tf32(d, d)

@@ -126,13 +126,24 @@ class _Runtime:
         self.last_outputs = (s_out, t_out)
         return out3
 
+    def _claim_gradient_buffer(self):
+        """one backward pass per optimizer step: the flat gradient is rebuilt (and, under DDP, averaged) by every
+        backward, so gradient accumulation over micro-batches would silently keep only the last one."""
+        fs = self.fs
+        if fs.has_optimizer and fs.grads_pending:
+            raise RuntimeError("a second backward pass before optimizer.step() / zero_grad(): gradient accumulation "
+                               "(accumulate_grad_batches > 1) is not supported by the fused step - raise the per-GPU "
+                               "batch size instead")
+        fs.grads_pending = True
+        fs.grad.zero_()
+
     def backward(self, grad_out):
         if self.saved is None:
             raise RuntimeError("backward called without a recorded forward (was the step run under no_grad?)")
         enc_ctxs, proj_ctx, pred_ctx, dstudent = self.saved
         self.saved = None
         fs = self.fs
-        fs.grad.zero_()
+        self._claim_gradient_buffer()
         d = self.ws.get("dstudent_scaled", dstudent.shape)
         torch.mul(dstudent, grad_out.to(dstudent.dtype), out=d)
         ops.round_tf32(d, d)

@@ -52,13 +52,31 @@ class _EncoderInference:
             raise RuntimeError("audiossl_b200 has no CPU path: move the encoder and its input to a B200 (cuda) device")
         rt = self._inf
         if rt is None or rt["device"] != device or not rt["fp"].is_current():
-            self.to(device)
-            fp = FlatParams(list(self.named_parameters()), device, ema_prefixes=("",))
+            fp, prefix = self._owner_storage(device)
+            if fp is None:  # a free-standing encoder (e.g. returned by load_model): its own flat buffer
+                self.to(device)
+                fp, prefix = FlatParams(list(self.named_parameters()), device, ema_prefixes=("",)), ""
             eng = EncoderEngine(self.embed_dim, self.depth, self.num_heads, use_cls=self.use_cls,
-                                norm_name="norm" if self.use_cls else "norm_frame", prefix="", max_frames=self.spec_w)
+                                norm_name="norm" if self.use_cls else "norm_frame", prefix=prefix,
+                                max_frames=self.spec_w)
             rt = dict(device=device, fp=fp, eng=eng, ws=Workspace(device))
             self._inf = rt
         return rt
+
+    def _owner_storage(self, device):
+        """(FlatParams, name prefix) when this encoder's parameters already live in the flat buffer of a training
+        runtime (``model.teacher.encoder`` during validation): inference then reads that storage in place instead of
+        re-pointing the parameters at a private copy - which would invalidate the training runtime and make every
+        eval / train alternation rebuild tens of GB of buffers."""
+        owners = [getattr(p, "_atst_flat", None) for p in self.parameters()]
+        if not owners or any(o is None for o in owners) or any(o[0] is not owners[0][0] for o in owners):
+            return None, ""
+        fp = owners[0][0]
+        if fp.data.device != device or not fp.is_current():
+            return None, ""
+        mine = next(iter(dict(self.named_parameters())))
+        full = next(o[1] for o, (n, _) in zip(owners, self.named_parameters()) if n == mine)
+        return fp, full[:len(full) - len(mine)]
 
     @torch.no_grad()
     def _run(self, x, length, collect=0, mask_index=None, mask_input=False):

@@ -39,6 +39,7 @@ class FusedHFAdamW(torch.optim.Optimizer):
     def step(self, closure=None):
         loss = closure() if closure is not None else None
         fp = self.flat_provider()
+        fp.has_optimizer, fp.grads_pending = True, False
         m, v = self._moments(fp)
         self._step += 1
         g_reg, g_noreg = self.param_groups[0], self.param_groups[1]
@@ -49,7 +50,12 @@ class FusedHFAdamW(torch.optim.Optimizer):
         return loss
 
     def zero_grad(self, set_to_none=True):
-        # gradients live in one flat buffer that the backward pass overwrites; nothing to do per tensor
+        # gradients live in one flat buffer that the backward pass rebuilds; nothing to clear per tensor
+        try:
+            fp = self.flat_provider()
+            fp.has_optimizer, fp.grads_pending = True, False
+        except RuntimeError:  # no CUDA runtime yet (module still on the host)
+            pass
         for group in self.param_groups:
             for p in group["params"]:
                 if set_to_none:
@@ -80,7 +86,7 @@ class FusedHFAdamW(torch.optim.Optimizer):
         return sd
 
     def load_state_dict(self, sd):
-        sd = dict(sd)
+        sd = dict(sd)  # shallow copy: the caller's dict keeps its keys
         flat = sd.pop("flat_state", None)  # round-1 checkpoints of this class
         state = sd.get("state", {})
         sd["state"] = {}

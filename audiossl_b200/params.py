@@ -59,6 +59,12 @@ class FlatParams:
                 v.copy_(p.data.to(device))
                 p.data = v
         self._ptrs = {name: p.data_ptr() for name, p in named_params}
+        for name, p in named_params:
+            p._atst_flat = (self, name)  # lets a sub-module (an encoder used stand-alone) find its storage again
+        # set by the backward pass, cleared by the optimizer: a second backward before the gradients were consumed
+        # would overwrite them (Lightning's accumulate_grad_batches > 1), which must not happen silently
+        self.grads_pending = False
+        self.has_optimizer = False
 
     def view(self, buf, name):
         off = self.offsets[name]

@@ -474,22 +474,58 @@ def run_ours(args):
             torch.cuda.synchronize()
         ks = sorted(((e.time_range.start, e.time_range.end, e.name) for e in prof.events()
                      if e.device_type == torch.autograd.DeviceType.CUDA), key=lambda t: t[0])
-        busy = sum(b - a for a, b, _ in ks)
         span = ks[-1][1] - ks[0][0]
+        # union of the busy intervals (kernels of the compute stream and NCCL kernels of the exchange stream overlap)
+        busy, cur_a, cur_b = 0.0, None, None
+        for a, b, _ in ks:
+            if cur_b is None or a > cur_b:
+                if cur_b is not None:
+                    busy += cur_b - cur_a
+                cur_a, cur_b = a, b
+            else:
+                cur_b = max(cur_b, b)
+        busy += cur_b - cur_a
         agg = {}
         for a, b, nm in ks:
             d = agg.setdefault(nm[:60], [0, 0.0])
             d[0] += 1
             d[1] += (b - a) / 1e3
-        gaps = sorted(((ks[i + 1][0] - ks[i][1], ks[i][2][:40], ks[i + 1][2][:40]) for i in range(len(ks) - 1)),
+        nccl = [(a, b, nm) for a, b, nm in ks if "nccl" in nm.lower()]
+        mine = [(a, b, nm) for a, b, nm in ks if "nccl" not in nm.lower()]
+        # NCCL time that no kernel of ours overlaps = the exposed part of the exchange
+        exposed = 0.0
+        j = 0
+        for a, b, _ in nccl:
+            covered, pos = 0.0, a
+            while j < len(mine) and mine[j][1] <= a:
+                j += 1
+            k = j
+            while k < len(mine) and mine[k][0] < b:
+                lo, hi = max(mine[k][0], pos), min(mine[k][1], b)
+                if hi > lo:
+                    covered += hi - lo
+                    pos = hi
+                k += 1
+            exposed += (b - a) - covered
+        gaps = sorted(((mine[i + 1][0] - mine[i][1], mine[i][2][:40], mine[i + 1][2][:40]) for i in range(len(mine) - 1)),
                       reverse=True)
-        print("steps %d  kernels %d  span %.2f ms  busy %.2f ms  idle %.2f ms" %
-              (max(args.steps, 1), len(ks), span / 1e3, busy / 1e3, (span - busy) / 1e3))
+        nsteps = max(args.steps, 1)
+        out = open(args.gaps_out % rank, "w") if args.gaps_out else sys.stdout
+        print("rank %d of %d  steps %d  kernels %d  span %.2f ms/step  busy %.2f ms/step  idle %.2f ms/step" %
+              (rank, world, nsteps, len(ks), span / 1e3 / nsteps, busy / 1e3 / nsteps, (span - busy) / 1e3 / nsteps),
+              file=out)
+        print("NCCL kernels: %d per step, %.3f ms per step, of which %.3f ms not overlapped by a kernel of this repo" %
+              (len(nccl) // nsteps, sum(b - a for a, b, _ in nccl) / 1e3 / nsteps, exposed / 1e3 / nsteps), file=out)
         for nm, (n_, ms_) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:25]:
-            print("  %-60s n=%4d %8.3f ms" % (nm, n_, ms_))
-        print("largest gaps (us):")
+            print("  %-60s n=%4d %8.3f ms/step" % (nm, n_ // nsteps, ms_ / nsteps), file=out)
+        print("largest gaps between this repo's kernels (us):", file=out)
         for g_, a_, b_ in gaps[:15]:
-            print("  %8.1f  %s -> %s" % (g_, a_, b_))
+            print("  %8.1f  %s -> %s" % (g_, a_, b_), file=out)
+        if out is not sys.stdout:
+            out.close()
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
         return
     sampler = ClockSampler(local)
     sampler.start()
@@ -631,6 +667,7 @@ if __name__ == "__main__":
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="warm-up + one step only (for ncu captures)")
     ap.add_argument("--gaps", action="store_true", help="in-situ kernel timeline of one step: busy / idle GPU time")
+    ap.add_argument("--gaps-out", default="", help="per-rank output file pattern for --gaps, e.g. out/timeline_rank%%d.txt")
     ap.add_argument("--breakdown", default="", help="write a per-GEMM-shape timing table to this file")
     a = ap.parse_args()
     if a.warmup < 3 and a.impl == "ours" and not a.profile and not a.gaps:

@@ -211,3 +211,52 @@ def test_lmdb_to_device_batches(tmp_path):
             assert np.array_equal(labels[j].cpu().numpy(), by_key[name][1][0])
         seen += wav.shape[0]
     assert seen == 10
+
+
+def test_validation_between_training_steps_keeps_the_runtime_and_accumulation_is_refused():
+    """model.teacher.encoder used stand-alone between two training steps (Lightning validation, downstream probes)
+    reads the training runtime's flat storage in place - no rebuild of the runtime, same numbers as a free-standing
+    copy of the encoder - and a second backward before the optimizer consumed the first one is an error, not a silent
+    overwrite (accumulate_grad_batches > 1)."""
+    import copy
+    from audiossl_b200.methods.atst.model import ATSTLightningModule
+    torch.manual_seed(0)
+    lm = ATSTLightningModule(arch=dict(embed_dim=128, depth=2, num_heads=2), learning_rate=1e-3, warmup_steps=1,
+                             max_steps=10, drop_path_rate=0.0).cuda().train()
+    opt = lm.configure_optimizers()[0]
+    lm.trainer.optimizers = [opt]
+    crops, lengths = util.make_inputs("tiny2b32", 8, [101, 101], [[101] * 8, [101 - i for i in range(8)]])
+    batch = (([c.cuda() for c in crops], [l.cuda() for l in lengths]), None)
+
+    def train_step(i):
+        lm.global_step = i
+        loss = lm.training_step(batch, i)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        lm.on_train_batch_end(None, None, i)
+        return loss
+    train_step(0)
+    rt = lm.model._rt
+    enc = lm.model.teacher.encoder
+    emb = enc(crops[0].cuda(), length=lengths[0].cuda())
+    assert lm.model._rt is rt and rt.current()                       # the parameters were not re-pointed
+    assert enc._inf["fp"] is rt.ft
+    free = copy.deepcopy(enc)                                         # a free-standing encoder: private flat buffer
+    free._inf = None
+    for p in free.parameters():
+        p._atst_flat = None
+    emb2 = free(crops[0].cuda(), length=lengths[0].cuda())
+    assert torch.equal(emb, emb2)
+    train_step(1)
+    assert lm.model._rt is rt                                         # and the training runtime survived validation
+    emb3 = enc(crops[0].cuda(), length=lengths[0].cuda())
+    assert not torch.equal(emb, emb3)                                 # the EMA update is visible to the next validation
+    # gradient accumulation is refused
+    lm.global_step = 2
+    l1 = lm.training_step(batch, 2)
+    opt.zero_grad()
+    l1.backward()
+    l2 = lm.training_step(batch, 2)
+    with pytest.raises(RuntimeError, match="accumulation"):
+        l2.backward()
