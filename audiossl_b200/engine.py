@@ -45,20 +45,27 @@ class Workspace:
         return sum(t.numel() * t.element_size() for t in self.bufs.values())
 
 
+_KEEP_CACHE = {}
+
+
 def droppath_scales(depth, drop_path_rate, S, device, generator=None):
     """per-block (attn, mlp) DropPath scales floor(keep + U[0,1)) / keep for S sequences
     (modules/transformer.py:48-57; rates linspace(0, rate, depth), audio_transformer.py:107).
     Blocks with rate 0 get None (nn.Identity in the reference: no random draw)."""
-    out = []
     rates = torch.linspace(0, drop_path_rate, depth).tolist()
-    for r in rates:
-        if r == 0.0:
-            out.append(None)
-            continue
-        keep = 1.0 - r
-        u = torch.rand((2, S), device=device, generator=generator)
-        s = torch.floor(keep + u) / keep
-        out.append((s[0].contiguous(), s[1].contiguous()))
+    live = [i for i, r in enumerate(rates) if r != 0.0]
+    out = [None] * depth
+    if not live:
+        return out
+    # one draw and one floor / divide for all blocks (four launches per encoder call instead of four per block)
+    key = (depth, float(drop_path_rate), str(device))
+    keep = _KEEP_CACHE.get(key)
+    if keep is None:
+        keep = _KEEP_CACHE[key] = torch.tensor([1.0 - rates[i] for i in live], device=device).view(-1, 1, 1)
+    u = torch.rand((len(live), 2, S), device=device, generator=generator)
+    s = torch.floor(keep + u) / keep
+    for j, i in enumerate(live):
+        out[i] = (s[j, 0], s[j, 1])
     return out
 
 

@@ -36,7 +36,8 @@ class _AttnTimer:
 
 
 class _GemmTimer:
-    def __init__(self, flops, tag="", nbytes=0.0):
+    def __init__(self, flops, tag=None, nbytes=0.0):
+        """tag: (format, args) - formatted only when a per-shape breakdown is being recorded"""
         self.flops = flops
         self.tag = tag
         STATS["gemm_bytes"] += nbytes  # algorithmic operand + result bytes of this launch
@@ -51,7 +52,8 @@ class _GemmTimer:
     def done(self):
         if self.ev is not None:
             self.ev[1].record()
-            STATS["gemm_events"].append((self.ev[0], self.ev[1], self.flops, self.tag))
+            tag = self.tag[0] % self.tag[1] if self.tag else ""
+            STATS["gemm_events"].append((self.ev[0], self.ev[1], self.flops, tag))
 
 
 def _count(n):
@@ -107,7 +109,7 @@ def gemm_nt(A, B, bias=None, epi=EPI_STORE, resid=None, aux=None, rowscale=None,
         out = torch.empty((M, N), device=A.device, dtype=torch.float32)
     if _lib.is_precise():
         A, B, K = _split3(A, 0, False), _split3(B, 1, False), 3 * K
-    _t = _GemmTimer(2.0 * M * N * K, "nt %dx%dx%d e%d" % (M, N, K, epi),
+    _t = _GemmTimer(2.0 * M * N * K, ("nt %dx%dx%d e%d", (M, N, K, epi)),
                    4.0 * (M * K + N * K + M * N * (1 + (resid is not None) + (aux is not None))))
     check(_lib.lib().atst_gemm_nt(ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(out), out.stride(0), M, N, K,
                                   ptr(bias), epi, ptr(resid), resid.stride(0) if resid is not None else 0,
@@ -127,7 +129,7 @@ def gemm_nn(A, W, epi=EPI_STORE, aux=None, rowscale=None, rows_per_seq=1, round_
         out = torch.empty((M, N), device=A.device, dtype=torch.float32)
     if _lib.is_precise():
         A, W, K = _split3(A, 0, False), _split3(W, 1, True), 3 * K
-    _t = _GemmTimer(2.0 * M * N * K, "nn %dx%dx%d e%d" % (M, N, K, epi), 4.0 * (M * K + N * K + M * N * (1 + (aux is not None))))
+    _t = _GemmTimer(2.0 * M * N * K, ("nn %dx%dx%d e%d", (M, N, K, epi)), 4.0 * (M * K + N * K + M * N * (1 + (aux is not None))))
     check(_lib.lib().atst_gemm_nn(ptr(A), A.stride(0), ptr(W), W.stride(0), ptr(out), out.stride(0), M, N, K, epi,
                                   ptr(aux), aux.stride(0) if aux is not None else 0, ptr(rowscale), rows_per_seq,
                                   1 if round_out else 0, ptr(colsum_out), _lib.stream()), "atst_gemm_nn")
@@ -142,7 +144,7 @@ def gemm_tn_acc(A, B, out):
     assert B.shape[0] == T and tuple(out.shape) == (M, N)
     if _lib.is_precise():
         A, B, T = _split3(A, 0, True), _split3(B, 1, True), 3 * T
-    _t = _GemmTimer(2.0 * M * N * T, "tn %dx%dx%d" % (M, N, T), 4.0 * (T * M + T * N + M * N))
+    _t = _GemmTimer(2.0 * M * N * T, ("tn %dx%dx%d", (M, N, T)), 4.0 * (T * M + T * N + M * N))
     check(_lib.lib().atst_gemm_tn(ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(out), out.stride(0), M, N, T,
                                   _lib.stream()), "atst_gemm_tn")
     _t.done()

@@ -63,6 +63,7 @@ class FlatParams:
             p._atst_flat = (self, name)  # lets a sub-module (an encoder used stand-alone) find its storage again
         # set by the backward pass, cleared by the optimizer: a second backward before the gradients were consumed
         # would overwrite them (Lightning's accumulate_grad_batches > 1), which must not happen silently
+        self._ranges = {}
         self.grads_pending = False
         self.has_optimizer = False
 
@@ -99,6 +100,13 @@ class FlatParams:
     def matrix_range(self, prefix):
         """[lo, hi) of the flat buffers covered by the regularised (>= 2-D) tensors whose names start with ``prefix``
         (one transformer block, the projector, ...): contiguous because segments keep module order."""
+        cached = self._ranges.get(prefix)
+        if cached is not None:
+            return cached
+        self._ranges[prefix] = rng = self._matrix_range(prefix)
+        return rng
+
+    def _matrix_range(self, prefix):
         a, b = self.seg_bounds[0] if prefix.startswith(("encoder.", "projector.")) else self.seg_bounds[2]
         names = [n for n in self.order if n.startswith(prefix) and a <= self.offsets[n] < b and n not in self.frozen]
         if not names:
