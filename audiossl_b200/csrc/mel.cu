@@ -201,36 +201,40 @@ mel_kernel(const float* __restrict__ wav, int n, long long wav_stride, const lon
 #pragma unroll
     for (int h = 0; h < 2; ++h) store8(re, im, v[h], lane + 32 * h, 64);
     __syncwarp();
-    // ---- untangle the packed real FFT and take |X[k]|^2, k = 0..512 (into registers, then over `re`)
-    float pk[2][8], nyq = 0.f;
+    // ---- untangle the packed real FFT and take |X[k]|^2, k = 0..512 (into registers, then over `re`).
+    // Bins k and 512 - k share everything but a sign: with Ze = (Z[k] + conj Z[512-k]) / 2, Zo = (Z[k] - conj Z[512-k]) / 2i
+    // and t = W^k Zo,  X[k] = Ze + t  and  X[512-k] = conj(Ze - t)  (W^(512-k) = -conj W^k), so one lane takes the
+    // pair; k = 0 pairs with the Nyquist bin 512 the same way, k = 256 is its own partner (lane 0).
+    float pk_lo[8], pk_hi[8], mid = 0.f;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int q = lane + 32 * h;
-#pragma unroll
-      for (int s = 0; s < 8; ++s) {
-        const int k = q + 64 * s;
-        const int kk = (512 - k) & 511;
-        const float2 a = make_float2(re[padi(k)], im[padi(k)]);
-        const float2 c = make_float2(re[padi(kk)], -im[padi(kk)]);  // conj(Z[512-k])
-        const float2 ze = make_float2(0.5f * (a.x + c.x), 0.5f * (a.y + c.y));
-        const float2 d = make_float2(0.5f * (a.x - c.x), 0.5f * (a.y - c.y));
-        const float2 zo = make_float2(d.y, -d.x);  // d / i
-        const float2 t = cmul(zo, __ldg(g_tw2 + k));
-        const float xr = ze.x + t.x, xi = ze.y + t.y;
-        pk[h][s] = xr * xr + xi * xi;
-        if (k == 0) {  // Nyquist bin 512: Ze[0] - Zo[0]
-          const float yr = ze.x - zo.x, yi = ze.y - zo.y;
-          nyq = yr * yr + yi * yi;
-        }
-      }
+    for (int s = 0; s < 8; ++s) {
+      const int k = lane + 32 * s;       // 0 .. 255
+      const int kk = (512 - k) & 511;
+      const float2 a = make_float2(re[padi(k)], im[padi(k)]);
+      const float2 c = make_float2(re[padi(kk)], -im[padi(kk)]);  // conj(Z[512-k])
+      const float2 ze = make_float2(0.5f * (a.x + c.x), 0.5f * (a.y + c.y));
+      const float2 d = make_float2(0.5f * (a.x - c.x), 0.5f * (a.y - c.y));
+      const float2 zo = make_float2(d.y, -d.x);  // d / i
+      const float2 t = cmul(zo, __ldg(g_tw2 + k));
+      const float xr = ze.x + t.x, xi = ze.y + t.y;
+      const float yr = ze.x - t.x, yi = ze.y - t.y;
+      pk_lo[s] = xr * xr + xi * xi;
+      pk_hi[s] = yr * yr + yi * yi;
+    }
+    if (lane == 0) {
+      const float2 a = make_float2(re[padi(256)], im[padi(256)]);
+      const float2 t = cmul(make_float2(a.y, 0.f), __ldg(g_tw2 + 256));  // Ze = (a.x, 0), Zo = (a.y, 0)
+      const float xr = a.x + t.x, xi = t.y;
+      mid = xr * xr + xi * xi;
     }
     __syncwarp();
     float* P = re;  // power spectrum, plain index 0..512
 #pragma unroll
-    for (int h = 0; h < 2; ++h)
-#pragma unroll
-      for (int s = 0; s < 8; ++s) P[lane + 32 * h + 64 * s] = pk[h][s];
-    if (lane == 0) P[512] = nyq;
+    for (int s = 0; s < 8; ++s) {
+      P[lane + 32 * s] = pk_lo[s];
+      P[512 - (lane + 32 * s)] = pk_hi[s];
+    }
+    if (lane == 0) P[256] = mid;
     __syncwarp();
     // ---- banded mel dot + dB: bands lane and lane + 32
 #pragma unroll
