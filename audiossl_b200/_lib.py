@@ -35,9 +35,9 @@ SIGNATURES = {
     "atst_colsum_accumulate": [P, L, I, I, P, P],
     "atst_bn_stats": [P, I, I, P, P, P],
     "atst_bn_finalize": [P, P, F, F, F, P, P, P, I, P],
-    "atst_bn_relu_forward": [P, P, P, P, P, P, I, I, P],
+    "atst_bn_relu_forward": [P, P, P, P, P, P, I, I, I, P],
     "atst_bn_relu_backward_stats": [P, P, P, P, P, P, I, I, P, P, P],
-    "atst_bn_relu_backward_apply": [P, P, P, P, P, P, P, P, F, P, I, I, P],
+    "atst_bn_relu_backward_apply": [P, P, P, P, P, P, P, P, F, P, I, I, I, P],
     "atst_byol_loss": [P, P, I, I, P, P, P],
     "atst_byol_finalize": [P, F, F, I, I, P, P],
     "atst_ema_update": [P, P, F, L, P],

@@ -162,8 +162,8 @@ int atst_bn_finalize(const float* mean, const float* m2, float count, float eps,
   return bn_finalize(mean, m2, count, eps, momentum, rstd, running_mean, running_var, cols, ST(stream));
 }
 int atst_bn_relu_forward(const float* X, const float* mean, const float* rstd, const float* gamma, const float* beta,
-                         float* Y, int rows, int cols, void* stream) {
-  return bn_relu_forward(X, mean, rstd, gamma, beta, Y, rows, cols, ST(stream));
+                         float* Y, int rows, int cols, int round_out, void* stream) {
+  return bn_relu_forward(X, mean, rstd, gamma, beta, Y, rows, cols, round_out, ST(stream));
 }
 int atst_bn_relu_backward_stats(const float* dY, const float* X, const float* mean, const float* rstd,
                                 const float* gamma, const float* beta, int rows, int cols, float* s1, float* s2,
@@ -172,8 +172,8 @@ int atst_bn_relu_backward_stats(const float* dY, const float* X, const float* me
 }
 int atst_bn_relu_backward_apply(const float* dY, const float* X, const float* mean, const float* rstd,
                                 const float* gamma, const float* beta, const float* s1, const float* s2, float count,
-                                float* dX, int rows, int cols, void* stream) {
-  return bn_relu_backward_apply(dY, X, mean, rstd, gamma, beta, s1, s2, count, dX, rows, cols, ST(stream));
+                                float* dX, int rows, int cols, int round_out, void* stream) {
+  return bn_relu_backward_apply(dY, X, mean, rstd, gamma, beta, s1, s2, count, dX, rows, cols, round_out, ST(stream));
 }
 int atst_byol_loss(const float* student, const float* teacher, int ncrops, int B, float* dstudent, float* acc_ws,
                    void* stream) {

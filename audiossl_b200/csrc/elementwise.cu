@@ -193,7 +193,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ mean, const float* 
 // y = relu((x - mean) * rstd * gamma + beta), rounded to tf32 (it feeds the next Linear)
 __global__ void bn_relu_fwd_kernel(const float* __restrict__ X, const float* __restrict__ mean,
                                    const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* __restrict__ Y, long long total4, int cols4) {
+                                   const float* __restrict__ beta, float* __restrict__ Y, long long total4, int cols4,
+                                   int round_out) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % cols4);
@@ -201,10 +202,13 @@ __global__ void bn_relu_fwd_kernel(const float* __restrict__ X, const float* __r
     const float4 mu = reinterpret_cast<const float4*>(mean)[c], rs = reinterpret_cast<const float4*>(rstd)[c];
     const float4 g = reinterpret_cast<const float4*>(gamma)[c], b = reinterpret_cast<const float4*>(beta)[c];
     float4 y;
-    y.x = round_tf32(fmaxf((x.x - mu.x) * rs.x * g.x + b.x, 0.f));
-    y.y = round_tf32(fmaxf((x.y - mu.y) * rs.y * g.y + b.y, 0.f));
-    y.z = round_tf32(fmaxf((x.z - mu.z) * rs.z * g.z + b.z, 0.f));
-    y.w = round_tf32(fmaxf((x.w - mu.w) * rs.w * g.w + b.w, 0.f));
+    y.x = fmaxf((x.x - mu.x) * rs.x * g.x + b.x, 0.f);
+    y.y = fmaxf((x.y - mu.y) * rs.y * g.y + b.y, 0.f);
+    y.z = fmaxf((x.z - mu.z) * rs.z * g.z + b.z, 0.f);
+    y.w = fmaxf((x.w - mu.w) * rs.w * g.w + b.w, 0.f);
+    if (round_out) {  // the consumer is a plain TF32 GEMM (0: a 3xTF32 GEMM splits the fp32 value itself)
+      y.x = round_tf32(y.x); y.y = round_tf32(y.y); y.z = round_tf32(y.z); y.w = round_tf32(y.w);
+    }
     reinterpret_cast<float4*>(Y)[i] = y;
   }
 }
@@ -244,13 +248,14 @@ __global__ void bn_relu_bwd_apply_kernel(const float* __restrict__ dY, const flo
                                          const float* __restrict__ mean, const float* __restrict__ rstd,
                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                          const float* __restrict__ s1, const float* __restrict__ s2, float inv_n,
-                                         float* __restrict__ dX, long long total, int cols) {
+                                         float* __restrict__ dX, long long total, int cols, int round_out) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % cols);
     const float xh = (X[i] - mean[c]) * rstd[c];
     const float dy = (xh * gamma[c] + beta[c] > 0.f) ? dY[i] : 0.f;
-    dX[i] = round_tf32(gamma[c] * rstd[c] * (dy - s1[c] * inv_n - xh * s2[c] * inv_n));
+    const float dx = gamma[c] * rstd[c] * (dy - s1[c] * inv_n - xh * s2[c] * inv_n);
+    dX[i] = round_out ? round_tf32(dx) : dx;
   }
 }
 
@@ -454,10 +459,10 @@ int bn_finalize(const float* mean, const float* m2, float count, float eps, floa
   return atst_check_launch("bn_finalize_kernel");
 }
 int bn_relu_forward(const float* X, const float* mean, const float* rstd, const float* gamma, const float* beta,
-                    float* Y, int rows, int cols, cudaStream_t st) {
+                    float* Y, int rows, int cols, int round_out, cudaStream_t st) {
   ATST_REQUIRE(cols % 4 == 0, "bn_relu_forward: cols %% 4 != 0");
   const long long total4 = static_cast<long long>(rows) * cols / 4;
-  bn_relu_fwd_kernel<<<grid_for(total4), 256, 0, st>>>(X, mean, rstd, gamma, beta, Y, total4, cols / 4);
+  bn_relu_fwd_kernel<<<grid_for(total4), 256, 0, st>>>(X, mean, rstd, gamma, beta, Y, total4, cols / 4, round_out);
   return atst_check_launch("bn_relu_fwd_kernel");
 }
 int bn_relu_backward_stats(const float* dY, const float* X, const float* mean, const float* rstd, const float* gamma,
@@ -467,10 +472,10 @@ int bn_relu_backward_stats(const float* dY, const float* X, const float* mean, c
 }
 int bn_relu_backward_apply(const float* dY, const float* X, const float* mean, const float* rstd, const float* gamma,
                            const float* beta, const float* s1, const float* s2, float count, float* dX, int rows,
-                           int cols, cudaStream_t st) {
+                           int cols, int round_out, cudaStream_t st) {
   const long long total = static_cast<long long>(rows) * cols;
   bn_relu_bwd_apply_kernel<<<grid_for(total), 256, 0, st>>>(dY, X, mean, rstd, gamma, beta, s1, s2, 1.0f / count, dX,
-                                                           total, cols);
+                                                           total, cols, round_out);
   return atst_check_launch("bn_relu_bwd_apply_kernel");
 }
 int gather_rows(const float* x, const int* idx, float* out, int rows, int D, cudaStream_t st) {

@@ -25,12 +25,12 @@ int bn_stats(const float* X, int rows, int cols, float* mean, float* m2, cudaStr
 int bn_finalize(const float* mean, const float* m2, float count, float eps, float momentum, float* rstd,
                 float* running_mean, float* running_var, int cols, cudaStream_t st);
 int bn_relu_forward(const float* X, const float* mean, const float* rstd, const float* gamma, const float* beta,
-                    float* Y, int rows, int cols, cudaStream_t st);
+                    float* Y, int rows, int cols, int round_out, cudaStream_t st);
 int bn_relu_backward_stats(const float* dY, const float* X, const float* mean, const float* rstd, const float* gamma,
                            const float* beta, int rows, int cols, float* s1, float* s2, cudaStream_t st);
 int bn_relu_backward_apply(const float* dY, const float* X, const float* mean, const float* rstd, const float* gamma,
                            const float* beta, const float* s1, const float* s2, float count, float* dX, int rows,
-                           int cols, cudaStream_t st);
+                           int cols, int round_out, cudaStream_t st);
 int mixup_forward(const float* x, int x_T, const float* bank, int bank_T, const int* idx, const int* zlen,
                   const int* start, const float* alpha, float* out, int Hm, int B, cudaStream_t st);
 int resize_crop_forward(const float* lms, const int* rect, float* out, int B, int Hm, int T, int canvas_h,

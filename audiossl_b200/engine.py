@@ -24,6 +24,10 @@ from . import ops
 #                         (the butterflies + red.global.add cost the dgrad GEMM ~0.9 ms to save a 0.27 ms pass): off
 _FG = int(os.environ.get("ATST_FUSE_GELU", "7"))
 FUSE_GELU_NOSAVE, FUSE_GELU, FUSE_DGELU, FUSE_COLSUM = bool(_FG & 1), bool(_FG & 2), bool(_FG & 4), bool(_FG & 8)
+# The projector / predictor heads (< 0.1 % of the flops) run as error-compensated 3xTF32 products on unrounded fp32
+# operands: their train-mode BatchNorm over a few hundred rows doubles whatever rounding error enters it, and the BYOL
+# gradient behind it is the ill-conditioned part of the step.  ATST_HEADS_3XTF32=0: plain TF32.
+HEADS_3X = os.environ.get("ATST_HEADS_3XTF32", "1") != "0"
 
 
 class Workspace:
@@ -160,12 +164,13 @@ class EncoderEngine:
             mean = t("meanf", (S,))
             rstd = t("rstdf", (S,))
             ops.layernorm_fwd(x, fp.p(nm + ".weight"), fp.p(nm + ".bias"), S, D, x_stride=N * D, out=out, mean=mean,
-                              rstd=rstd, round_out=round_final)
+                              rstd=rstd, round_out=round_final and not HEADS_3X)
         else:
             out = t("xn", (M, D))
             mean = t("meanf", (M,))
             rstd = t("rstdf", (M,))
-            self._ln(x, fp.p(nm + ".weight"), fp.p(nm + ".bias"), M, out, mean, rstd)
+            ops.layernorm_fwd(x, fp.p(nm + ".weight"), fp.p(nm + ".bias"), M, D, out=out, mean=mean, rstd=rstd,
+                              round_out=round_final and not HEADS_3X)
         ctx["meanf"], ctx["rstdf"] = mean, rstd
         dbg("x_in", self.depth, x)
         dbg("enc_out", self.depth, out)
@@ -274,9 +279,14 @@ class HeadEngine:
         """first Linear + this rank's batch statistics (the part before the SyncBatchNorm exchange)."""
         px = self.px
         R = x.shape[0]
-        z1 = ops.gemm_nt(x, fp.c(px + "0.weight"), out=ws.get(tag + "/" + px + "z1", (R, self.hidden)))
+        z1 = ops.gemm_nt(x, self._w(fp, "0.weight"), out=ws.get(tag + "/" + px + "z1", (R, self.hidden)),
+                         precise=HEADS_3X)
         mean, m2 = ops.bn_stats(z1)
         return dict(x=x, z1=z1, mean=mean, m2=m2, n=float(R), R=R, tag=tag)
+
+    def _w(self, fp, name):
+        """the weight operand: the fp32 master for the 3xTF32 heads, the TF32 compute copy otherwise"""
+        return fp.p(self.px + name) if HEADS_3X else fp.c(self.px + name)
 
     def forward_finish(self, fp, ws, head, bn_buffers, round_out, momentum=0.1, eps=1e-5):
         """running statistics, normalise + ReLU, second Linear - from the (global) statistics in ``head``."""
@@ -288,8 +298,9 @@ class HeadEngine:
             nbt += 1
         rstd = ops.bn_finalize(head["mean"], head["m2"], head["n"], rm, rv, eps=eps, momentum=momentum)
         a1 = ops.bn_relu_fwd(head["z1"], head["mean"], rstd, fp.p(px + "1.weight"), fp.p(px + "1.bias"),
-                             out=t("a1", (R, self.hidden)))
-        z2 = ops.gemm_nt(a1, fp.c(px + "3.weight"), round_out=round_out, out=t("z2", (R, self.out_dim)))
+                             out=t("a1", (R, self.hidden)), round_out=not HEADS_3X)
+        z2 = ops.gemm_nt(a1, self._w(fp, "3.weight"), round_out=round_out and not HEADS_3X,
+                         out=t("z2", (R, self.out_dim)), precise=HEADS_3X)
         ctx = dict(x=head["x"], z1=head["z1"], mean=head["mean"], rstd=rstd, a1=a1, n=head["n"], R=R, tag=tag)
         return z2, ctx
 
@@ -298,8 +309,8 @@ class HeadEngine:
         px = self.px
         R, tag = ctx["R"], ctx["tag"]
         t = (lambda name, shape: ws.get(tag + "/bwd/" + px + name, shape))
-        ops.gemm_tn_acc(dz2, ctx["a1"], fp.g(px + "3.weight"))
-        da1 = ops.gemm_nn(dz2, fp.c(px + "3.weight"), out=t("da1", (R, self.hidden)))
+        ops.gemm_tn_acc(dz2, ctx["a1"], fp.g(px + "3.weight"), precise=HEADS_3X)
+        da1 = ops.gemm_nn(dz2, self._w(fp, "3.weight"), out=t("da1", (R, self.hidden)), precise=HEADS_3X)
         gamma, beta = fp.p(px + "1.weight"), fp.p(px + "1.bias")
         s1, s2 = ops.bn_relu_bwd_stats(da1, ctx["z1"], ctx["mean"], ctx["rstd"], gamma, beta)
         fp.g(px + "1.bias").add_(s1)
@@ -307,8 +318,9 @@ class HeadEngine:
         if sums_sync is not None:
             s1, s2 = sums_sync(s1, s2)
         dz1 = ops.bn_relu_bwd_apply(da1, ctx["z1"], ctx["mean"], ctx["rstd"], gamma, beta, s1, s2, ctx["n"],
-                                    out=t("dz1", (R, self.hidden)))
-        ops.gemm_tn_acc(dz1, ctx["x"], fp.g(px + "0.weight"))
+                                    out=t("dz1", (R, self.hidden)), round_out=not HEADS_3X)
+        ops.gemm_tn_acc(dz1, ctx["x"], fp.g(px + "0.weight"), precise=HEADS_3X)
         if not need_dx:
             return None
-        return ops.gemm_nn(dz1, fp.c(px + "0.weight"), round_out=False, out=t("dx", (R, self.in_dim)))
+        return ops.gemm_nn(dz1, self._w(fp, "0.weight"), round_out=False, out=t("dx", (R, self.in_dim)),
+                           precise=HEADS_3X)

@@ -10,7 +10,7 @@ from torch import nn
 
 from ... import ops
 from ...distributed import allreduce_sum_, bn_stats_sync, bn_sums_sync, world
-from ...engine import EncoderEngine, droppath_scales
+from ...engine import HEADS_3X, EncoderEngine, droppath_scales
 from ...models.atst.atst import _Runtime, _StepFn
 from ...optim import FusedHFAdamW
 from ...utils.common import bool_flag, cosine_scheduler_step, get_params_groups
@@ -83,10 +83,12 @@ class _FrameRuntime(_Runtime):
         self._claim_gradient_buffer()
         d = self.ws.get("dstudent_scaled", dstudent.shape)
         torch.mul(dstudent, grad_out.to(dstudent.dtype), out=d)
-        ops.round_tf32(d, d)
+        if not HEADS_3X:
+            ops.round_tf32(d, d)
         sums = bn_sums_sync if world() > 1 else None
         dz = self.pred.backward(fs, self.ws, pred_ctx, d, need_dx=True, sums_sync=sums)
-        ops.round_tf32(dz, dz)
+        if not HEADS_3X:
+            ops.round_tf32(dz, dz)
         drows = self.proj.backward(fs, self.ws, proj_ctx, dz, need_dx=True, sums_sync=sums)
         if self.enc.debug is not None:
             self.enc.debug.append(("d_heads_in", "s", -1, drows.clone()))

@@ -17,7 +17,7 @@ from torch import nn
 
 from ... import ops
 from ...distributed import (GradExchange, allreduce_sum_, bn_stats_sync, bn_stats_sync_many, bn_sums_sync, world)
-from ...engine import EncoderEngine, HeadEngine, Workspace, droppath_scales
+from ...engine import HEADS_3X, EncoderEngine, HeadEngine, Workspace, droppath_scales
 from ...params import FlatParams
 from .audio_transformer import AST, AST_base, AST_large, AST_small
 from .byol import ByolLoss, MultiCropWrapper
@@ -146,10 +146,12 @@ class _Runtime:
         self._claim_gradient_buffer()
         d = self.ws.get("dstudent_scaled", dstudent.shape)
         torch.mul(dstudent, grad_out.to(dstudent.dtype), out=d)
-        ops.round_tf32(d, d)
+        if not HEADS_3X:
+            ops.round_tf32(d, d)
         sums = bn_sums_sync if world() > 1 else None
         dz = self.pred.backward(fs, self.ws, pred_ctx, d, need_dx=True, sums_sync=sums)
-        ops.round_tf32(dz, dz)
+        if not HEADS_3X:
+            ops.round_tf32(dz, dz)
         dcls = self.proj.backward(fs, self.ws, proj_ctx, dz, need_dx=True, sums_sync=sums)
         if self.enc.debug is not None:
             self.enc.debug.append(("d_heads_in", "s", -1, dcls.clone()))

@@ -100,14 +100,15 @@ def mel_forward(wav, win_length=1024, normalize=True, out=None, clip_start=None,
 
 
 def gemm_nt(A, B, bias=None, epi=EPI_STORE, resid=None, aux=None, rowscale=None, rows_per_seq=1, round_out=False,
-            out=None):
-    """out[M,N] = epi(A[M,K] @ B[N,K]^T + bias)."""
+            out=None, precise=False):
+    """out[M,N] = epi(A[M,K] @ B[N,K]^T + bias).  precise: error-compensated 3xTF32 product of UNROUNDED fp32 operands
+    (hi / lo split, one pass of the same kernel over the tripled contraction) - the projector / predictor heads."""
     M, K = A.shape
     N = B.shape[0]
     assert B.shape[1] == K
     if out is None:
         out = torch.empty((M, N), device=A.device, dtype=torch.float32)
-    if _lib.is_precise():
+    if _lib.is_precise() or precise:
         A, B, K = _split3(A, 0, False), _split3(B, 1, False), 3 * K
     _t = _GemmTimer(2.0 * M * N * K, ("nt %dx%dx%d e%d", (M, N, K, epi)),
                    4.0 * (M * K + N * K + M * N * (1 + (resid is not None) + (aux is not None))))
@@ -119,7 +120,8 @@ def gemm_nt(A, B, bias=None, epi=EPI_STORE, resid=None, aux=None, rowscale=None,
     return out
 
 
-def gemm_nn(A, W, epi=EPI_STORE, aux=None, rowscale=None, rows_per_seq=1, round_out=False, out=None, colsum_out=None):
+def gemm_nn(A, W, epi=EPI_STORE, aux=None, rowscale=None, rows_per_seq=1, round_out=False, out=None, colsum_out=None,
+            precise=False):
     """out[M,N] = epi(A[M,K] @ W[K,N])  (dgrad against a Linear weight W[out=K, in=N]).
     colsum_out [N] (optional) += column sums of out, taken in the GEMM epilogue."""
     M, K = A.shape
@@ -127,7 +129,7 @@ def gemm_nn(A, W, epi=EPI_STORE, aux=None, rowscale=None, rows_per_seq=1, round_
     assert W.shape[0] == K
     if out is None:
         out = torch.empty((M, N), device=A.device, dtype=torch.float32)
-    if _lib.is_precise():
+    if _lib.is_precise() or precise:
         A, W, K = _split3(A, 0, False), _split3(W, 1, True), 3 * K
     _t = _GemmTimer(2.0 * M * N * K, ("nn %dx%dx%d e%d", (M, N, K, epi)), 4.0 * (M * K + N * K + M * N * (1 + (aux is not None))))
     check(_lib.lib().atst_gemm_nn(ptr(A), A.stride(0), ptr(W), W.stride(0), ptr(out), out.stride(0), M, N, K, epi,
@@ -137,12 +139,12 @@ def gemm_nn(A, W, epi=EPI_STORE, aux=None, rowscale=None, rows_per_seq=1, round_
     return out
 
 
-def gemm_tn_acc(A, B, out):
+def gemm_tn_acc(A, B, out, precise=False):
     """out[M,N] += A[T,M]^T @ B[T,N]  (wgrad; accumulates)."""
     T, M = A.shape
     N = B.shape[1]
     assert B.shape[0] == T and tuple(out.shape) == (M, N)
-    if _lib.is_precise():
+    if _lib.is_precise() or precise:
         A, B, T = _split3(A, 0, True), _split3(B, 1, True), 3 * T
     _t = _GemmTimer(2.0 * M * N * T, ("tn %dx%dx%d", (M, N, T)), 4.0 * (T * M + T * N + M * N))
     check(_lib.lib().atst_gemm_tn(ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(out), out.stride(0), M, N, T,
@@ -266,12 +268,12 @@ def bn_finalize(mean, m2, count, running_mean=None, running_var=None, eps=1e-5, 
     return rstd
 
 
-def bn_relu_fwd(X, mean, rstd, gamma, beta, out=None):
+def bn_relu_fwd(X, mean, rstd, gamma, beta, out=None, round_out=True):
     rows, cols = X.shape
     if out is None:
         out = torch.empty_like(X)
     check(_lib.lib().atst_bn_relu_forward(ptr(X), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ptr(out), rows, cols,
-                                          _lib.stream()), "atst_bn_relu_forward")
+                                          1 if round_out else 0, _lib.stream()), "atst_bn_relu_forward")
     _count(1)
     return out
 
@@ -286,13 +288,13 @@ def bn_relu_bwd_stats(dY, X, mean, rstd, gamma, beta):
     return s1, s2
 
 
-def bn_relu_bwd_apply(dY, X, mean, rstd, gamma, beta, s1, s2, count, out=None):
+def bn_relu_bwd_apply(dY, X, mean, rstd, gamma, beta, s1, s2, count, out=None, round_out=True):
     rows, cols = X.shape
     if out is None:
         out = torch.empty_like(X)
     check(_lib.lib().atst_bn_relu_backward_apply(ptr(dY), ptr(X), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta),
                                                  ptr(s1), ptr(s2), float(count), ptr(out), rows, cols,
-                                                 _lib.stream()), "atst_bn_relu_backward_apply")
+                                                 1 if round_out else 0, _lib.stream()), "atst_bn_relu_backward_apply")
     _count(1)
     return out
 

@@ -92,13 +92,13 @@ int atst_bn_stats(const float* X, int rows, int cols, float* mean, float* m2, vo
 int atst_bn_finalize(const float* mean, const float* m2, float count, float eps, float momentum, float* rstd,
                      float* running_mean, float* running_var, int cols, void* stream);
 int atst_bn_relu_forward(const float* X, const float* mean, const float* rstd, const float* gamma, const float* beta,
-                         float* Y, int rows, int cols, void* stream);
+                         float* Y, int rows, int cols, int round_out, void* stream);
 int atst_bn_relu_backward_stats(const float* dY, const float* X, const float* mean, const float* rstd,
                                 const float* gamma, const float* beta, int rows, int cols, float* s1, float* s2,
                                 void* stream);
 int atst_bn_relu_backward_apply(const float* dY, const float* X, const float* mean, const float* rstd,
                                 const float* gamma, const float* beta, const float* s1, const float* s2, float count,
-                                float* dX, int rows, int cols, void* stream);
+                                float* dX, int rows, int cols, int round_out, void* stream);
 
 /* ---- BYOL loss + compute_var statistics (audiossl/models/atst/byol.py:24-78).
  *   student [ncrops*B,256], teacher [2*B,256]; dstudent = d loss / d student;

@@ -156,7 +156,8 @@ def check_step(model, ref, crops, lengths, masks=None, dp_teacher=None, dp_stude
     passes_t = pass_info(ref.teacher, groups_t, dp_teacher, "t", False)
     passes_s = pass_info(ref.student, groups_s, dp_student, "s", True)
 
-    with O.tf32_emulation():
+    from audiossl_b200.engine import HEADS_3X  # the heads run as 3xTF32 (~fp32) products unless switched off
+    with O.tf32_emulation(True, heads=not HEADS_3X):
         # ------------------------------------------------------------------ forward links, both networks
         enc_out = {"t": [], "s": []}
         plens = {}
@@ -171,7 +172,9 @@ def check_step(model, ref, crops, lengths, masks=None, dp_teacher=None, dp_stude
                     rep.add("fwd", "%s/block%d" % (tag, i), rel(hooks[("x_in", tag, i + 1)].view(S, N, D), y), tol_fwd)
                 xn = norm_of(enc)(hooks[("x_in", tag, depth)].view(S, N, D))
                 got = hooks[("enc_out", tag, depth)]
-                want = O.rna_tf32(xn.reshape(S * N, D)) if frame else O.rna_tf32(xn[:, 0])
+                want = xn.reshape(S * N, D) if frame else xn[:, 0]
+                if not HEADS_3X:  # a plain TF32 head GEMM gets its operand pre-rounded by the LayerNorm kernel
+                    want = O.rna_tf32(want)
                 rep.add("fwd", tag + "/final_norm", rel(got, want), 1e-4)
                 if frame:
                     valid = m_cpu & (torch.arange(N)[None, :] < plen[:, None])

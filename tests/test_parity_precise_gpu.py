@@ -224,19 +224,22 @@ def compare_with_fp32_oracle(m, ref, crops, lengths, ncrops=2, dp_t=None, dp_s=N
     mine = dict(m.student.named_parameters())
     big = max(p.grad.norm().item() for p in ref.student.parameters() if p.grad is not None)
     kappa = oracle_kappa(m, crops, lengths, ncrops=ncrops, masks=masks, dp_t=dp_t, dp_s=dp_s)
+    k_max = max(kappa.values())
     worst, n = (0.0, "", 0.0), 0
     for name, rp in ref.student.named_parameters():
         if rp.grad is None:
             assert mine[name].grad is None, name
             continue
         e = ((mine[name].grad.cpu().double() - rp.grad.double()).norm() / max(rp.grad.norm().item(), 1e-3 * big)).item()
-        t = conditioning.allowed(GRAD_TOL * _sum_type_factor(name), kappa[name], es)
+        # few clips per batch at these shapes: every gradient is a strongly cancelling sum and one noise draw
+        # estimates a tensor's kappa to a factor of ~2, so the step's largest kappa bounds all of its tensors
+        t = conditioning.allowed(GRAD_TOL * _sum_type_factor(name), k_max, es, safety=5.0)
         assert e < t, "%s: gradient of %s off by %.3e (tolerance %.1e, kappa %.0f)" % (label, name, e, t, kappa[name])
         n += 1
         if e / t > worst[2]:
             worst = (e, name, e / t)
-    print("%s (3xTF32 vs fp32 oracle): outputs %.1e / %.1e, worst of %d gradients %.1e (%s, kappa %.0f)"
-          % (label, es, et, n, worst[0], worst[1], kappa[worst[1]]))
+    print("%s (3xTF32 vs fp32 oracle): outputs %.1e / %.1e, worst of %d gradients %.1e (%s; kappa %.0f, step max %.0f)"
+          % (label, es, et, n, worst[0], worst[1], kappa[worst[1]], k_max))
 
 
 def test_config2_base_10s_matches_fp32_oracle():
