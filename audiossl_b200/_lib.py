@@ -106,6 +106,9 @@ def load(name=None):
 
 def lib():
     """library handle for compute calls: checks the device once per variant."""
+    l = _libs.get(_variant)
+    if l is not None and _variant in _inited:
+        return l
     l = load()
     if _variant not in _inited:
         rc = l.atst_init()
@@ -129,6 +132,16 @@ def ptr(t):
     return None if t is None else t.data_ptr()
 
 
+_raw_stream = None
+
+
 def stream():
-    import torch
-    return torch.cuda.current_stream().cuda_stream
+    """the caller's current CUDA stream as a raw cudaStream_t (what every entry point takes last).  Goes through
+    torch's C accessors: torch.cuda.current_stream() builds a Stream object per call (~5 us), which at ~500 launches
+    per step was half of the host time of a small-batch step."""
+    global _raw_stream
+    if _raw_stream is None:
+        import torch
+        get_raw, get_dev = torch._C._cuda_getCurrentRawStream, torch._C._cuda_getDevice
+        _raw_stream = lambda: get_raw(get_dev())  # noqa: E731
+    return _raw_stream()

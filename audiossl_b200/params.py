@@ -64,6 +64,7 @@ class FlatParams:
         # set by the backward pass, cleared by the optimizer: a second backward before the gradients were consumed
         # would overwrite them (Lightning's accumulate_grad_batches > 1), which must not happen silently
         self._ranges = {}
+        self._pv, self._gv, self._cv = {}, {}, {}  # views of the three flat buffers by name (built on first use)
         self.grads_pending = False
         self.has_optimizer = False
 
@@ -75,14 +76,20 @@ class FlatParams:
             n *= s
         return buf[off:off + n].view(shape)
 
+    def _cached(self, cache, buf, name):
+        v = cache.get(name)
+        if v is None:
+            v = cache[name] = self.view(buf, name)
+        return v
+
     def p(self, name):
-        return self.view(self.data, name)
+        return self._cached(self._pv, self.data, name)
 
     def g(self, name):
-        return self.view(self.grad, name)
+        return self._cached(self._gv, self.grad, name)
 
     def c(self, name):
-        return self.view(self.compute, name)
+        return self._cached(self._cv, self.compute, name)
 
     def is_current(self):
         """False if someone (e.g. module.cuda()/load_state_dict with assign) re-allocated a parameter."""

@@ -535,7 +535,9 @@ def run_ours(args):
     gemm_flops_step = ops.STATS["gemm_flops"] / args.steps
     gemm_bytes_launch = ops.STATS["gemm_bytes"] / max(ops.STATS["gemm_launches"], 1)
     feed["it"] = None
-    ms_e2e = timed(True, args.steps, args.warmup + args.steps)
+    for i in range(2):  # untimed: the staging buffers of the host path are allocated and touched once
+        step(args.warmup + args.steps + i, True)
+    ms_e2e = timed(True, args.steps, args.warmup + args.steps + 2)
     ms_aug = None
     if cfg["kind"] == "clip" and len(cfg["crops"]) == 1 and not args.no_augment:
         # SURVEY.md 8d "second number with augmentations on": same e2e loop, the batch produced by the device
