@@ -40,8 +40,8 @@ SIGNATURES = {
     "atst_bn_relu_backward_apply": [P, P, P, P, P, P, P, P, F, P, I, I, I, P],
     "atst_byol_loss": [P, P, I, I, P, P, P],
     "atst_byol_finalize": [P, F, F, I, I, P, P],
-    "atst_ema_update": [P, P, F, L, P],
-    "atst_adamw_step": [P, P, P, P, L, I, F, F, F, F, F, F, P],
+    "atst_ema_update": [P, P, F, P, L, P],
+    "atst_adamw_step": [P, P, P, P, L, I, F, F, F, F, F, F, P, P],
     "atst_mixup_forward": [P, I, P, I, P, P, P, P, P, I, I, P],
     "atst_resize_crop_forward": [P, P, P, I, I, I, I, I, P],
     "atst_gather_rows": [P, P, P, I, I, P],

@@ -183,12 +183,12 @@ int atst_byol_finalize(const float* acc_ws, float n_student_rows, float n_teache
                        float* out3, void* stream) {
   return byol_finalize(acc_ws, n_student_rows, n_teacher_rows, ncrops, B, out3, ST(stream));
 }
-int atst_ema_update(float* k, const float* q, float m, long long n, void* stream) {
-  return ema_update(k, q, m, n, ST(stream));
+int atst_ema_update(float* k, const float* q, float m, const float* m_dev, long long n, void* stream) {
+  return ema_update(k, q, m, m_dev, n, ST(stream));
 }
 int atst_adamw_step(float* p, const float* g, float* m, float* v, long long n, int step, float lr, float wd,
-                    float beta1, float beta2, float eps, float grad_scale, void* stream) {
-  return adamw_step(p, g, m, v, n, step, lr, wd, beta1, beta2, eps, grad_scale, ST(stream));
+                    float beta1, float beta2, float eps, float grad_scale, const float* dyn, void* stream) {
+  return adamw_step(p, g, m, v, n, step, lr, wd, beta1, beta2, eps, grad_scale, dyn, ST(stream));
 }
 int atst_mixup_forward(const float* x, int x_T, const float* bank, int bank_T, const int* idx, const int* zlen,
                        const int* start, const float* alpha, float* out, int Hm, int B, void* stream) {

@@ -108,7 +108,10 @@ __global__ void byol_finalize_kernel(const float* __restrict__ loss_acc, const f
 }
 
 // k = m*k + (1-m)*q over a flat buffer
-__global__ void ema_kernel(float* __restrict__ k, const float* __restrict__ q, float m, long long n4) {
+// (m_dev: the momentum read from device memory, so that a CUDA graph of the step can be replayed with a new value)
+__global__ void ema_kernel(float* __restrict__ k, const float* __restrict__ q, float m, const float* __restrict__ m_dev,
+                           long long n4) {
+  if (m_dev != nullptr) m = *m_dev;
   const float om = 1.0f - m;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -121,8 +124,12 @@ __global__ void ema_kernel(float* __restrict__ k, const float* __restrict__ q, f
 
 // transformers-4.x AdamW: m,v update; p -= lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps); then p -= lr*wd*p
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                             float* __restrict__ v, long long n, float step_size, float lr_wd, float b1, float b2,
-                             float eps, float grad_scale) {
+                             float* __restrict__ v, long long n, float step_size, float lr_wd,
+                             const float* __restrict__ dyn, float b1, float b2, float eps, float grad_scale) {
+  if (dyn != nullptr) {  // {step_size, lr * wd} of this step from device memory (CUDA-graph replay)
+    step_size = dyn[0];
+    lr_wd = dyn[1];
+  }
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float gr = g[i] * grad_scale;
@@ -153,21 +160,22 @@ int byol_finalize(const float* acc_ws, float n_student_rows, float n_teacher_row
                                           static_cast<float>(2 * ncrops - 2) * B, out3);
   return atst_check_launch("byol_finalize_kernel");
 }
-int ema_update(float* k, const float* q, float m, long long n, cudaStream_t st) {
+int ema_update(float* k, const float* q, float m, const float* m_dev, long long n, cudaStream_t st) {
   ATST_REQUIRE(n % 4 == 0, "ema_update: n %% 4 != 0");
   long long g = (n / 4 + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
-  ema_kernel<<<static_cast<int>(g), 256, 0, st>>>(k, q, m, n / 4);
+  ema_kernel<<<static_cast<int>(g), 256, 0, st>>>(k, q, m, m_dev, n / 4);
   return atst_check_launch("ema_kernel");
 }
 int adamw_step(float* p, const float* g, float* m, float* v, long long n, int step, float lr, float wd, float b1,
-               float b2, float eps, float grad_scale, cudaStream_t st) {
-  ATST_REQUIRE(step >= 1, "adamw_step: step counts from 1");
+               float b2, float eps, float grad_scale, const float* dyn, cudaStream_t st) {
+  ATST_REQUIRE(step >= 1 || dyn != nullptr, "adamw_step: step counts from 1");
+  if (step < 1) step = 1;
   const double bc1 = 1.0 - pow(static_cast<double>(b1), step), bc2 = 1.0 - pow(static_cast<double>(b2), step);
   const float step_size = static_cast<float>(lr * sqrt(bc2) / bc1);
   long long gr = (n + 255) / 256;
   if (gr > 148 * 16) gr = 148 * 16;
-  adamw_kernel<<<static_cast<int>(gr), 256, 0, st>>>(p, g, m, v, n, step_size, lr * wd, b1, b2, eps, grad_scale);
+  adamw_kernel<<<static_cast<int>(gr), 256, 0, st>>>(p, g, m, v, n, step_size, lr * wd, dyn, b1, b2, eps, grad_scale);
   return atst_check_launch("adamw_kernel");
 }
 

@@ -47,7 +47,7 @@ int byol_loss(const float* student, const float* teacher, int ncrops, int B, flo
               cudaStream_t st);
 int byol_finalize(const float* acc_ws, float n_student_rows, float n_teacher_rows, int ncrops, int B, float* out3,
                   cudaStream_t st);
-int ema_update(float* k, const float* q, float m, long long n, cudaStream_t st);
+int ema_update(float* k, const float* q, float m, const float* m_dev, long long n, cudaStream_t st);
 int adamw_step(float* p, const float* g, float* m, float* v, long long n, int step, float lr, float wd, float b1,
-               float b2, float eps, float grad_scale, cudaStream_t st);
+               float b2, float eps, float grad_scale, const float* dyn, cudaStream_t st);
 }  // namespace atst

@@ -194,6 +194,7 @@ class ATST(nn.Module):
         self.teacher.load_state_dict({k: v for k, v in self.student.state_dict().items() if "predictor" not in k})
         self.loss_fn = ByolLoss(ncrops)
         self._rt = None
+        self.ema_device_scalar = None  # 1-element cuda tensor: update_teacher reads m from it (CUDA-graph replay)
 
     def _runtime(self, device):
         if device.type != "cuda":
@@ -216,4 +217,4 @@ class ATST(nn.Module):
         """k <- m*k + (1-m)*q over encoder + projector parameters (not BN buffers, not the predictor)."""
         p = next(self.student.parameters())
         rt = self._runtime(p.device)
-        ops.ema_update(rt.ft.data, rt.fs.data[:rt.fs.ema_count], float(m))
+        ops.ema_update(rt.ft.data, rt.fs.data[:rt.fs.ema_count], float(m), m_dev=self.ema_device_scalar)

@@ -319,15 +319,17 @@ def byol_finalize(acc, n_student_rows, n_teacher_rows, ncrops, B, out=None):
     return out
 
 
-def ema_update(k, q, m):
+def ema_update(k, q, m, m_dev=None):
+    """m_dev (1-element cuda tensor, optional): the momentum is read from it on the device (CUDA-graph replay)."""
     assert k.numel() == q.numel()
-    check(_lib.lib().atst_ema_update(ptr(k), ptr(q), float(m), k.numel(), _lib.stream()), "atst_ema_update")
+    check(_lib.lib().atst_ema_update(ptr(k), ptr(q), float(m), ptr(m_dev), k.numel(), _lib.stream()), "atst_ema_update")
     _count(1)
 
 
-def adamw_step(p, g, m, v, step, lr, wd, beta1=0.9, beta2=0.999, eps=1e-6, grad_scale=1.0):
+def adamw_step(p, g, m, v, step, lr, wd, beta1=0.9, beta2=0.999, eps=1e-6, grad_scale=1.0, dyn=None):
+    """dyn (2-element cuda tensor, optional): {lr * sqrt(1 - beta2^t) / (1 - beta1^t), lr * wd} read on the device."""
     check(_lib.lib().atst_adamw_step(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), int(step), float(lr), float(wd),
-                                     beta1, beta2, eps, float(grad_scale), _lib.stream()), "atst_adamw_step")
+                                     beta1, beta2, eps, float(grad_scale), ptr(dyn), _lib.stream()), "atst_adamw_step")
     _count(1)
 
 

@@ -28,6 +28,9 @@ class FusedHFAdamW(torch.optim.Optimizer):
         self.flat_provider = flat  # callable returning the FlatParams of the student
         self._m = self._v = None
         self._step = 0
+        # [4] cuda tensor {step_size, lr*wd} x {regularised, non-regularised group}: when set (graph.GraphedTrainStep),
+        # the kernels read the step's scalars from it instead of taking them as launch arguments
+        self.device_scalars = None
 
     def _moments(self, fp):
         if self._m is None or self._m.numel() != fp.total or self._m.device != fp.data.device:
@@ -45,9 +48,18 @@ class FusedHFAdamW(torch.optim.Optimizer):
         g_reg, g_noreg = self.param_groups[0], self.param_groups[1]
         for (a, b, reg) in fp.wd_segments():
             grp = g_reg if reg else g_noreg
+            dyn = None if self.device_scalars is None else self.device_scalars[0 if reg else 2:2 if reg else 4]
             ops.adamw_step(fp.data[a:b], fp.grad[a:b], m[a:b], v[a:b], self._step, grp["lr"],
-                           grp["weight_decay"], grp["betas"][0], grp["betas"][1], grp["eps"])
+                           grp["weight_decay"], grp["betas"][0], grp["betas"][1], grp["eps"], dyn=dyn)
         return loss
+
+    def step_scalars(self, step, lr, wd):
+        """the four floats of ``device_scalars`` for optimizer step number ``step`` (1-based)."""
+        out = []
+        for grp, w in ((self.param_groups[0], wd), (self.param_groups[1], 0.0)):
+            b1, b2 = grp["betas"]
+            out += [lr * (1.0 - b2 ** step) ** 0.5 / (1.0 - b1 ** step), lr * w]
+        return out
 
     def zero_grad(self, set_to_none=True):
         # gradients live in one flat buffer that the backward pass rebuilds; nothing to clear per tensor

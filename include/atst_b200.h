@@ -109,10 +109,12 @@ int atst_byol_finalize(const float* acc_ws, float n_student_rows, float n_teache
                        float* out3, void* stream);
 
 /* ---- teacher EMA (audiossl/models/atst/atst.py:29-34) and HF-semantics AdamW
- *      (audiossl/methods/atst/model.py:44-48; transformers 4.x AdamW, eps inside, decay after update) */
-int atst_ema_update(float* k, const float* q, float m, long long n, void* stream);
+ *      (audiossl/methods/atst/model.py:44-48; transformers 4.x AdamW, eps inside, decay after update)
+ *      m_dev / dyn (nullable device pointers): the per-step scalars - EMA momentum; {lr*sqrt(1-b2^t)/(1-b1^t), lr*wd} -
+ *      read from device memory instead of the arguments, so a captured CUDA graph of the step replays with new values */
+int atst_ema_update(float* k, const float* q, float m, const float* m_dev, long long n, void* stream);
 int atst_adamw_step(float* p, const float* g, float* m, float* v, long long n, int step, float lr, float wd,
-                    float beta1, float beta2, float eps, float grad_scale, void* stream);
+                    float beta1, float beta2, float eps, float grad_scale, const float* dyn, void* stream);
 
 /* ---- device-batched augmentations between mel and encoder (audiossl/transforms/byol_a.py:7-49,61-115):
  *   mixup: out[b] = log((1-alpha[b]) e^x[b] + alpha[b] e^bank[idx[b]] + eps), idx[b] < 0 copies x[b]; x [B,Hm,x_T],

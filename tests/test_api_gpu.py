@@ -260,3 +260,71 @@ def test_validation_between_training_steps_keeps_the_runtime_and_accumulation_is
     l2 = lm.training_step(batch, 2)
     with pytest.raises(RuntimeError, match="accumulation"):
         l2.backward()
+
+
+def test_graphed_training_step_matches_eager_steps():
+    """audiossl_b200.graph.GraphedTrainStep: the whole step replayed as one CUDA graph gives the eager loop's losses
+    and parameters over several steps (schedules, Adam bias corrections and the EMA momentum reach the kernels through
+    device memory), and building it leaves the model where it was."""
+    import copy
+    from audiossl_b200.graph import GraphedTrainStep
+    from audiossl_b200.methods.atst.model import ATSTLightningModule
+
+    def make():
+        torch.manual_seed(0)
+        lm = ATSTLightningModule(arch=dict(embed_dim=128, depth=2, num_heads=2), learning_rate=1e-3, warmup_steps=2,
+                                 max_steps=20, ema=0.9, drop_path_rate=0.0)
+        util.load_det(lm.model)
+        lm.cuda().train()
+        opt = lm.configure_optimizers()[0]
+        lm.trainer.optimizers = [opt]
+        return lm, opt
+    batches = []
+    for s in range(4):
+        crops, lengths = util.make_inputs("graph%d" % s, 8, [101, 101], [[101 - (i * 3) % 30 for i in range(8)], [101] * 8])
+        batches.append((([c.cuda() for c in crops], [l.cuda() for l in lengths]), None))
+    # eager reference
+    lm_e, opt_e = make()
+    losses_e = []
+    for s, batch in enumerate(batches):
+        lm_e.global_step = s
+        loss = lm_e.training_step(batch, s)
+        opt_e.zero_grad()
+        loss.backward()
+        opt_e.step()
+        lm_e.on_train_batch_end(None, None, s)
+        losses_e.append(loss.item())
+    # graphed
+    lm_g, opt_g = make()
+    before = {k: v.detach().clone() for k, v in lm_g.state_dict().items()}
+    step = GraphedTrainStep(lm_g, opt_g, batches[0])
+    for k, v in lm_g.state_dict().items():
+        assert torch.equal(v, before[k]), "building the graph changed " + k
+    assert opt_g._step == 0
+    losses_g = [step(batch, s).item() for s, batch in enumerate(batches)]
+    # same kernels, same inputs: the first steps agree to fp32 noise; after that the atomically accumulated weight
+    # gradients (order differs from launch to launch) are amplified by Adam's normalisation of tiny gradients
+    np.testing.assert_allclose(losses_g[:2], losses_e[:2], rtol=2e-5)
+    np.testing.assert_allclose(losses_g, losses_e, rtol=1e-3)
+    assert opt_g._step == 4
+    sd_e, sd_g = lm_e.state_dict(), lm_g.state_dict()
+    worst = 0.0
+    for k in sd_e:
+        if not sd_e[k].dtype.is_floating_point:
+            assert torch.equal(sd_e[k], sd_g[k]), k
+            continue
+        moved = (sd_e[k] - before[k]).norm().item()
+        diff = (sd_e[k] - sd_g[k]).norm().item()
+        if moved > 0:
+            worst = max(worst, diff / moved)
+        else:
+            assert diff == 0.0, k
+    assert worst < 0.1, worst  # (same amplification; a wrong schedule / bias correction would be off by O(1))
+    # back to eager on the same objects
+    step.release()
+    lm_g.global_step = 4
+    loss = lm_g.training_step(batches[0], 4)
+    opt_g.zero_grad()
+    loss.backward()
+    opt_g.step()
+    assert np.isfinite(loss.item()) and opt_g._step == 5
