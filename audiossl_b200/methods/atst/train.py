@@ -30,6 +30,11 @@ def save_checkpoint(path, lm, opt, step, hparams):
 
 
 def main(args):
+    return run(args, ATSTLightningModule, ATSTDataModule, ("std_cls_s", "std_cls_t"))
+
+
+def run(args, module_cls, data_cls, std_names):
+    """the training loop shared by the ATST-clip and ATST-Frame launchers"""
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -42,8 +47,8 @@ def main(args):
     args.learning_rate = args.learning_rate * args.nproc * args.batch_size_per_gpu / 256
     dict_args = vars(args)
     torch.manual_seed(0)  # identical initial weights on every rank (DDP broadcasts rank 0's; same effect)
-    model = ATSTLightningModule(**dict_args).to(dev).train()
-    data = ATSTDataModule(device=dev, **dict_args)
+    model = module_cls(**dict_args).to(dev).train()
+    data = data_cls(device=dev, **dict_args)
     opt = model.configure_optimizers()[0]
     model.trainer.optimizers = [opt]
     step = 0
@@ -71,7 +76,7 @@ def main(args):
             if rank == 0 and step % args.log_every == 0:
                 dt = time.time() - t0
                 print("step %d  loss %.4f  std_s %.3f  std_t %.3f  lr %.2e  %.0f clips/s" % (
-                    step, float(loss.detach()), float(model.logged["std_cls_s"]), float(model.logged["std_cls_t"]),
+                    step, float(loss.detach()), float(model.logged[std_names[0]]), float(model.logged[std_names[1]]),
                     model.logged["lr"], seen / dt), flush=True)
                 t0, seen = time.time(), 0
             if rank == 0 and (step % args.save_every == 0 or step == args.max_steps):

@@ -177,7 +177,7 @@ def test_data_module_and_launcher_on_synthetic_clips(tmp_path):
     ck = torch.load(str(tmp_path / "last.ckpt"), map_location="cpu", weights_only=False)
     assert ck["global_step"] == 3 and ck["hyper_parameters"]["arch"] == "small"
     assert set(ck["state_dict"]) == set(lm.state_dict()) and len(ck["optimizer_states"][0]["state"]) > 100
-    assert np.isfinite(float(lm.logged["loss"])) and abs(ck["hyper_parameters"]["learning_rate"] - 5e-4 * 4 / 256) < 1e-12
+    assert np.isfinite(float(lm.logged["loss"].detach())) and abs(ck["hyper_parameters"]["learning_rate"] - 5e-4 * 4 / 256) < 1e-12
     # resume: picks up at step 3 and runs to 4
     args2 = T.build_parser().parse_args(["--save_path", str(tmp_path), "--nproc", "1", "--arch", "small",
                                          "--batch_size_per_gpu", "4", "--num_workers", "0", "--synthetic_clips", "16",
@@ -328,3 +328,23 @@ def test_graphed_training_step_matches_eager_steps():
     loss.backward()
     opt_g.step()
     assert np.isfinite(loss.item()) and opt_g._step == 5
+
+
+def test_frame_launcher_on_synthetic_clips(tmp_path):
+    """the atstframe/train.py-equivalent launcher: synthetic clips -> pinned H2D -> device transform with block masks
+    -> FrameATSTLightningModule steps -> checkpoint."""
+    from audiossl_b200.methods.atstframe import train as T
+    args = T.build_parser().parse_args(["--save_path", str(tmp_path), "--nproc", "1", "--arch", "small",
+                                        "--batch_size_per_gpu", "4", "--num_workers", "0", "--synthetic_clips", "8",
+                                        "--anchor_len", "2.0", "--mask_type", "block", "--mask_ratio", "0.65",
+                                        "--max_steps", "2", "--warmup_steps", "1", "--log_every", "1",
+                                        "--save_every", "2"])
+    lm = T.main(args)
+    ck = torch.load(str(tmp_path / "last.ckpt"), map_location="cpu", weights_only=False)
+    assert ck["global_step"] == 2 and np.isfinite(float(lm.logged["loss"].detach()))
+    assert "model.student.encoder.norm_frame.weight" in ck["state_dict"]
+    # the checkpoint is what load_model of the embedding API reads
+    from audiossl_b200.methods.atstframe import embedding as E
+    enc = E.load_model(str(tmp_path / "last.ckpt"))
+    emb = E.get_scene_embedding(torch.randn(2, 1, 32000, device="cuda") * 0.1, enc)
+    assert tuple(emb.shape) == (2, 12 * 384) and torch.isfinite(emb).all()
