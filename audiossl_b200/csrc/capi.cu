@@ -63,7 +63,8 @@ int atst_gemm_nt(const float* A, int lda, const float* B, int ldb, float* C, int
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = bias; p.epi = epi; p.resid = resid; p.ldr = ldr;
   p.aux = aux; p.ldaux = ldaux; p.rowscale = rowscale; p.rows_per_seq = rows_per_seq > 0 ? rows_per_seq : 1;
   p.round_out = round_out;
-  ATST_REQUIRE((epi >= EPI_STORE && epi <= EPI_RELU) || epi == EPI_DBG_NOSTORE || epi == EPI_DBG_NOLOAD,
+  ATST_REQUIRE((epi >= EPI_STORE && epi <= EPI_RELU) || epi == EPI_GELU_H || epi == EPI_DBG_NOSTORE ||
+                   epi == EPI_DBG_NOLOAD,
                "atst_gemm_nt: bad epilogue %d", epi);
   ATST_REQUIRE(!(epi == EPI_RESID && resid == nullptr), "atst_gemm_nt: EPI_RESID needs resid");
   ATST_REQUIRE(!(epi == EPI_DGELU && aux == nullptr), "atst_gemm_nt: EPI_DGELU needs aux");
@@ -77,8 +78,9 @@ int atst_gemm_nn(const float* A, int lda, const float* B, int ldb, float* C, int
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.epi = epi; p.aux = aux; p.ldaux = ldaux;
   p.rowscale = rowscale; p.rows_per_seq = rows_per_seq > 0 ? rows_per_seq : 1; p.round_out = round_out;
   p.colsum = colsum_out;
-  ATST_REQUIRE(epi == EPI_STORE || epi == EPI_DGELU || epi == EPI_SCALE, "atst_gemm_nn: bad epilogue %d", epi);
-  ATST_REQUIRE(!(epi == EPI_DGELU && aux == nullptr), "atst_gemm_nn: EPI_DGELU needs aux");
+  ATST_REQUIRE(epi == EPI_STORE || epi == EPI_DGELU || epi == EPI_DGELU_H || epi == EPI_SCALE,
+               "atst_gemm_nn: bad epilogue %d", epi);
+  ATST_REQUIRE(!((epi == EPI_DGELU || epi == EPI_DGELU_H) && aux == nullptr), "atst_gemm_nn: EPI_DGELU needs aux");
   return gemm_nn(A, lda, B, ldb, p, ST(stream));
 }
 

@@ -13,6 +13,8 @@ enum GemmEpilogue : int {
   EPI_SCALE = 4,   // C = rowscale[row / rows_per_seq] * acc
   EPI_RELU = 5,    // C = max(acc + bias, 0)
   EPI_ATOMIC = 6,  // C += acc   (split-K partial sums, red.global.add)
+  EPI_GELU_H = 10,   // aux (fp16, ldaux in halfs) = gelu'(acc + bias) ; C = gelu_erf(acc + bias)   (pair kernel only)
+  EPI_DGELU_H = 11,  // C = acc * aux (fp16: the derivative stored by EPI_GELU_H)                   (pair kernel only)
   EPI_DBG_NOSTORE = 8,  // profiling aid: full epilogue without the global stores
   EPI_DBG_NOLOAD = 9,   // profiling aid: epilogue without the TMEM loads (stores zeros)
 };
@@ -24,7 +26,8 @@ struct GemmParams {
   const float* bias = nullptr;      // [N] or null
   const float* resid = nullptr;     // [M, ldr]
   int ldr = 0;
-  float* aux = nullptr;             // [M, ldaux] pre-activation (written by EPI_GELU, read by EPI_DGELU)
+  float* aux = nullptr;             // [M, ldaux] pre-activation (written by EPI_GELU, read by EPI_DGELU); the _H
+                                    // epilogues keep gelu'(pre-activation) there instead, as fp16 (a __half*)
   int ldaux = 0;
   const float* rowscale = nullptr;  // per-sequence DropPath scale (mask / keep_prob) or null
   int rows_per_seq = 1;

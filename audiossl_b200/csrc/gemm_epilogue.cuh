@@ -35,6 +35,22 @@ __device__ __forceinline__ GeluParts gelu_parts(float u) {
   return g;
 }
 __device__ __forceinline__ float gelu_exact(float u) { return u * gelu_parts(u).cdf; }
+// two fp32 -> one packed f16x2 word (round to nearest even), `lo` in the low half = the lower address; and back
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void unpack_half2(uint32_t w, float& lo, float& hi) {
+  asm("{\n\t"
+      ".reg .f16 l, h;\n\t"
+      "mov.b32 {l, h}, %2;\n\t"
+      "cvt.f32.f16 %0, l;\n\t"
+      "cvt.f32.f16 %1, h;\n\t"
+      "}"
+      : "=f"(lo), "=f"(hi)
+      : "r"(w));
+}
 __device__ __forceinline__ float gelu_grad(float u) {
   const GeluParts g = gelu_parts(u);
   return fmaf(u, g.pdf, g.cdf);
@@ -56,7 +72,7 @@ __device__ __forceinline__ float gelu_grad(float u) {
 // a quad transpose (same time), a shared-memory staging tile with TMA loads / stores (slower: the shared-memory port
 // belongs to TMA + UMMA), 32- or 16-column accumulator loads in flight with an early release of the stage (plain
 // shapes +5 %, fused shapes -20 %: the unthrottled main loop takes the link from the epilogue that is the bottleneck).
-template <int BLOCK_N, int EPI_THREADS, class Release>
+template <int BLOCK_N, int EPI_THREADS, bool HALF_SIDE = false, class Release>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n0, bool empty_split, uint32_t taddr,
                                               float* sbias, int ew, int lane, int epi_tid, int g0, int g1,
                                               uint64_t* tfull_bar, uint32_t acc_phase, Release release,
@@ -189,6 +205,100 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
           release();
         }
       }
+    }
+    return;
+  }
+  if constexpr (HALF_SIDE) {
+    // (own kernel instantiation: the loops below are compiled out of it, and this one out of theirs, so neither
+    // costs the other registers.)  The student's MLP with an fp16 side stream: EPI_GELU_H stores gelu'(pre-activation) - from the same cdf / pdf as
+    // the GELU itself - and EPI_DGELU_H multiplies by it.  Same pipeline as the loop below (8-column accumulator loads
+    // one ahead), its own copy so that the carried words cost the other epilogues no registers.  The side stream moves
+    // as ONE 32-byte sector per PAIR of groups (16 halfs): the even group of a pair loads / the odd group stores the
+    // sector, `hp` carries the other group's four packed words in between.  g0 even, N % 16 == 0 (host-checked).
+    const bool fwd = p.epi == EPI_GELU_H;  // warp-uniform
+    uint16_t* haux = (p.aux != nullptr && row_ok)
+                         ? reinterpret_cast<uint16_t*>(p.aux) + static_cast<size_t>(gm) * p.ldaux + n0 : nullptr;
+    if (!fwd && haux != nullptr) {
+      for (int g = g0; g < g1; g += 8)
+        if (g * 8 < ncols) prefetch_l2(haux + g * 8);
+    }
+    uint32_t ra[8], rb[8], hp[4] = {0u, 0u, 0u, 0u};
+    float sh[2][8];  // the 16 halfs of a pair of groups, fetched two pairs ahead
+    auto fetch_pair = [&](int g, float (&sd)[8]) {  // g even: the halfs of groups g and g + 1
+      if (!fwd && haux != nullptr && g < g1 && g * 8 < ncols) ld_global_v8(reinterpret_cast<const float*>(haux + g * 8), sd);
+    };
+    auto finish_h = [&](int g, const uint32_t (&r)[8], const float (&sd)[8], const bool even) {
+      if (g * 8 >= ncols || !row_ok) return;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[e]);
+      if (fwd) {
+        if (p.bias != nullptr) {
+          const float4 b0 = *reinterpret_cast<const float4*>(sbias + g * 8);
+          const float4 b1 = *reinterpret_cast<const float4*>(sbias + g * 8 + 4);
+          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        }
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const GeluParts a = gelu_parts(v[2 * i]), b = gelu_parts(v[2 * i + 1]);
+          w[i] = pack_half2(fmaf(v[2 * i], a.pdf, a.cdf), fmaf(v[2 * i + 1], b.pdf, b.cdf));
+          v[2 * i] *= a.cdf;
+          v[2 * i + 1] *= b.cdf;
+        }
+        if (even) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) hp[i] = w[i];
+        } else if (haux != nullptr) {
+          asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(haux + (g - 1) * 8), "r"(hp[0]),
+                       "r"(hp[1]), "r"(hp[2]), "r"(hp[3]), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                       : "memory");
+        }
+      } else {
+        if (even) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) hp[i] = __float_as_uint(sd[4 + i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float lo, hi;
+          unpack_half2(even ? __float_as_uint(sd[i]) : hp[i], lo, hi);
+          v[2 * i] *= lo;
+          v[2 * i + 1] *= hi;
+        }
+      }
+      if (p.round_out) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = round_tf32(v[e]);
+      }
+      st_global_v8(c_row + g * 8, v);
+    };
+    fetch_pair(g0, sh[0]);
+    fetch_pair(g0 + 2, sh[1]);
+    tmem_ld_32x8(taddr + g0 * 8, ra);
+#pragma unroll 1
+    for (int g = g0; g < g1; g += 4) {
+      tmem_ld_wait();
+      tmem_ld_32x8(taddr + (g + 1) * 8, rb);
+      finish_h(g, ra, sh[0], true);
+      fetch_pair(g + 4, sh[0]);
+      tmem_ld_wait();
+      tmem_ld_32x8(taddr + (g + 2) * 8, ra);
+      finish_h(g + 1, rb, sh[0], false);
+      tmem_ld_wait();
+      tmem_ld_32x8(taddr + (g + 3) * 8, rb);
+      finish_h(g + 2, ra, sh[1], true);
+      fetch_pair(g + 6, sh[1]);
+      tmem_ld_wait();
+      if (g + 4 < g1) {
+        tmem_ld_32x8(taddr + (g + 4) * 8, ra);
+      } else {  // this warp's last TMEM load of the tile has completed
+        tc_fence_before();
+        __syncwarp();
+        release();
+      }
+      finish_h(g + 3, rb, sh[1], false);
     }
     return;
   }

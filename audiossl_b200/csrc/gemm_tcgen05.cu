@@ -481,6 +481,13 @@ static int check_output_layout(const GemmParams& p, const char* who) {
   ATST_REQUIRE(p.aux == nullptr || (p.ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(p.aux) & 31) == 0),
                "%s: aux must be 32-byte aligned with ldaux %% 8 == 0", who);
   ATST_REQUIRE(p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0, "%s: bias must be 16-byte aligned", who);
+  if (p.epi == EPI_GELU_H || p.epi == EPI_DGELU_H) {
+    // fp16 side stream: one 32-byte sector per pair of 8-column groups, CTA-pair kernel's epilogue only
+    const bool wide = (p.N % 256 == 0) || p.N > 1024;
+    ATST_REQUIRE(wide && g_cta_pair, "%s: the fp16 GELU' epilogues need the CTA-pair kernel (N %% 256 == 0 or N > 1024)", who);
+    ATST_REQUIRE(p.N % 16 == 0 && (p.aux == nullptr || p.ldaux % 16 == 0),
+                 "%s: fp16 aux needs N and ldaux multiples of 16 (N=%d ldaux=%d)", who, p.N, p.ldaux);
+  }
   return ATST_OK;
 }
 

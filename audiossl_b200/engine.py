@@ -22,8 +22,19 @@ from . import ops
 #                  bit 2: the backward fuses GELU' into the fc2 dgrad epilogue; bit 3: that epilogue also takes the
 #                         fc1 bias gradient (column sums) instead of a separate pass over du - measured slower
 #                         (the butterflies + red.global.add cost the dgrad GEMM ~0.9 ms to save a 0.27 ms pass): off
+#                  bit 4: (with bits 1 and 2) what the student keeps for the backward pass is gelu'(u) as fp16 - the same
+#                         10-bit mantissa the TF32 rounding of du leaves anyway - instead of the fp32 pre-activation u:
+#                         the second stream of the fc1 and fc2-dgrad epilogues is half the bytes and the dgrad epilogue
+#                         has no GELU math left.  Never in the 3xTF32 validation build.
 _FG = int(os.environ.get("ATST_FUSE_GELU", "7"))
 FUSE_GELU_NOSAVE, FUSE_GELU, FUSE_DGELU, FUSE_COLSUM = bool(_FG & 1), bool(_FG & 2), bool(_FG & 4), bool(_FG & 8)
+HALF_DGELU = bool(_FG & 16) and FUSE_GELU and FUSE_DGELU
+
+
+def half_dgelu():
+    """whether the student's MLP keeps fp16 gelu'(u) (the parity tests configure their emulation with this)"""
+    from . import _lib
+    return HALF_DGELU and not _lib.is_precise()
 # The projector / predictor heads (< 0.1 % of the flops) run as error-compensated 3xTF32 products on unrounded fp32
 # operands: their train-mode BatchNorm over a few hundred rows doubles whatever rounding error enters it, and the BYOL
 # gradient behind it is the ill-conditioned part of the step (DESIGN.md section 3).  ATST_HEADS_3XTF32=0: plain TF32.
@@ -121,7 +132,8 @@ class EncoderEngine:
         for i in range(self.depth):
             b = "%sblocks.%d." % (px, i)
             dbg("x_in", i, x)
-            lt = (lambda name, shape, i=i: ws.get("%s/L%d/%s" % (tag, i if save else 0, name), shape))
+            lt = (lambda name, shape, dtype=torch.float32, i=i:
+                  ws.get("%s/L%d/%s" % (tag, i if save else 0, name), shape, dtype))
             h, mean1, rstd1 = self._ln(x, fp.p(b + "norm1.weight"), fp.p(b + "norm1.bias"), M, lt("h", (M, D)),
                                        lt("mean1", (M,)), lt("rstd1", (M,)))
             qkv = ops.gemm_nt(h, fp.c(b + "attn.qkv.weight"), round_out=True, out=lt("qkv", (M, 3 * D)))
@@ -137,6 +149,10 @@ class EncoderEngine:
             if not save and FUSE_GELU_NOSAVE:
                 g = ops.gemm_nt(h2, fp.c(b + "mlp.fc1.weight"), bias=fp.p(b + "mlp.fc1.bias"), epi=ops.EPI_GELU,
                                 aux=None, round_out=True, out=lt("g", (M, 4 * D)))
+            elif save and FUSE_GELU and half_dgelu():
+                u = lt("gp", (M, 4 * D), torch.float16)   # gelu'(pre-activation), not the pre-activation
+                g = ops.gemm_nt(h2, fp.c(b + "mlp.fc1.weight"), bias=fp.p(b + "mlp.fc1.bias"), epi=ops.EPI_GELU_H,
+                                aux=u, round_out=True, out=lt("g", (M, 4 * D)))
             elif save and FUSE_GELU:
                 u = lt("u", (M, 4 * D))
                 g = ops.gemm_nt(h2, fp.c(b + "mlp.fc1.weight"), bias=fp.p(b + "mlp.fc1.bias"), epi=ops.EPI_GELU,
@@ -220,7 +236,8 @@ class EncoderEngine:
             # ---- MLP branch: x2 = x1 + s * (g W2^T + b2); dys = tf32(s * dx), fc2.bias gradient already accumulated
             ops.gemm_tn_acc(dys, L["g"], fp.g(b + "mlp.fc2.weight"))
             if FUSE_DGELU:
-                du = ops.gemm_nn(dys, fp.c(b + "mlp.fc2.weight"), epi=ops.EPI_DGELU, aux=L["u"], round_out=True,
+                du = ops.gemm_nn(dys, fp.c(b + "mlp.fc2.weight"),
+                                 epi=ops.EPI_DGELU_H if L["u"].dtype == torch.float16 else ops.EPI_DGELU, aux=L["u"], round_out=True,
                                  out=t("du", (M, 4 * D)), colsum_out=fp.g(b + "mlp.fc1.bias") if FUSE_COLSUM else None)
                 if not FUSE_COLSUM:
                     ops.colsum_acc(du, fp.g(b + "mlp.fc1.bias"))

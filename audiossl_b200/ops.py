@@ -9,6 +9,7 @@ from . import _lib
 from ._lib import check, ptr
 
 EPI_STORE, EPI_GELU, EPI_DGELU, EPI_RESID, EPI_SCALE, EPI_RELU = 0, 1, 2, 3, 4, 5
+EPI_GELU_H, EPI_DGELU_H = 10, 11  # aux = fp16 gelu'(pre-activation) instead of the fp32 pre-activation
 
 # launch accounting for bench.py: kernels launched through the C ABI, algorithmic GEMM flops, and (optionally)
 # a CUDA-event pair around every GEMM launch to measure the dominant kernel in place
@@ -99,6 +100,15 @@ def mel_forward(wav, win_length=1024, normalize=True, out=None, clip_start=None,
     return out.reshape(*lead, 64, T)
 
 
+def _aux_bytes(aux, epi):
+    if aux is None:
+        return 0.0
+    want = torch.float16 if epi in (EPI_GELU_H, EPI_DGELU_H) else torch.float32
+    if aux.dtype != want:
+        raise TypeError("epilogue %d takes a %s aux tensor, got %s" % (epi, want, aux.dtype))
+    return float(aux.numel() * aux.element_size())
+
+
 def gemm_nt(A, B, bias=None, epi=EPI_STORE, resid=None, aux=None, rowscale=None, rows_per_seq=1, round_out=False,
             out=None, precise=False):
     """out[M,N] = epi(A[M,K] @ B[N,K]^T + bias).  precise: error-compensated 3xTF32 product of UNROUNDED fp32 operands
@@ -111,7 +121,7 @@ def gemm_nt(A, B, bias=None, epi=EPI_STORE, resid=None, aux=None, rowscale=None,
     if _lib.is_precise() or precise:
         A, B, K = _split3(A, 0, False), _split3(B, 1, False), 3 * K
     _t = _GemmTimer(2.0 * M * N * K, ("nt %dx%dx%d e%d", (M, N, K, epi)),
-                   4.0 * (M * K + N * K + M * N * (1 + (resid is not None) + (aux is not None))))
+                   4.0 * (M * K + N * K + M * N * (1 + (resid is not None))) + _aux_bytes(aux, epi))
     check(_lib.lib().atst_gemm_nt(ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(out), out.stride(0), M, N, K,
                                   ptr(bias), epi, ptr(resid), resid.stride(0) if resid is not None else 0,
                                   ptr(aux), aux.stride(0) if aux is not None else 0, ptr(rowscale), rows_per_seq,
@@ -131,7 +141,7 @@ def gemm_nn(A, W, epi=EPI_STORE, aux=None, rowscale=None, rows_per_seq=1, round_
         out = torch.empty((M, N), device=A.device, dtype=torch.float32)
     if _lib.is_precise() or precise:
         A, W, K = _split3(A, 0, False), _split3(W, 1, True), 3 * K
-    _t = _GemmTimer(2.0 * M * N * K, ("nn %dx%dx%d e%d", (M, N, K, epi)), 4.0 * (M * K + N * K + M * N * (1 + (aux is not None))))
+    _t = _GemmTimer(2.0 * M * N * K, ("nn %dx%dx%d e%d", (M, N, K, epi)), 4.0 * (M * K + N * K + M * N) + _aux_bytes(aux, epi))
     check(_lib.lib().atst_gemm_nn(ptr(A), A.stride(0), ptr(W), W.stride(0), ptr(out), out.stride(0), M, N, K, epi,
                                   ptr(aux), aux.stride(0) if aux is not None else 0, ptr(rowscale), rows_per_seq,
                                   1 if round_out else 0, ptr(colsum_out), _lib.stream()), "atst_gemm_nn")

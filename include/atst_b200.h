@@ -44,6 +44,8 @@ int atst_mel_forward(const float* wav, int B, int n, long long wav_stride, const
  *      audiossl/models/atst/byol.py:6-22.
  *   epi: 0 store(+bias) | 1 bias+GELU (aux <- pre-activation) | 2 acc*gelu'(aux) | 3 resid + rowscale*(acc+bias)
  *        | 4 rowscale*acc | 5 relu(acc+bias)
+ *        | 10 bias+GELU with aux <- gelu'(pre-activation) stored as fp16 (aux is a __half*, ldaux in halfs)
+ *        | 11 acc*aux with that fp16 derivative (10 / 11: N, ldaux multiples of 16; N % 256 == 0 or N > 1024)
  *   rowscale: per-sequence DropPath scale (mask/keep_prob) indexed by row / rows_per_seq, or NULL. */
 int atst_gemm_nt(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K,
                  const float* bias, int epi, const float* resid, int ldr, float* aux, int ldaux,

@@ -131,26 +131,30 @@ def mel_feature(wav, win_length=N_FFT, dtype=np.float32):
 #   * attention: Q, K, V (the qkv GEMM stores rounded values), the un-normalised probabilities exp(s - max) that
 #     multiply V, the stored output O, and in the backward pass dO, P, dS and the stored dQ / dK / dV.
 # Everything else (LayerNorm, softmax statistics, GELU, BatchNorm, loss, residual stream) stays fp32, as on the GPU.
+#   * ``gelu_half=True`` (engine.half_dgelu(), ATST_FUSE_GELU bit 4): the student's MLP keeps gelu'(u) as fp16 for the
+#     backward pass instead of the fp32 pre-activation u (gemm_epilogue.cuh EPI_GELU_H / EPI_DGELU_H); the forward
+#     pass is unchanged.
 # With emulation off nothing below changes the reference arithmetic.
 _EMULATE_TF32 = False
 _EMULATE_HEADS = True
+_EMULATE_GELU_H = False
 
 
 class tf32_emulation:
     """``heads=False`` leaves the projector / predictor Linears in fp32: the CUDA path runs those (< 0.1 % of the
     flops) as error-compensated 3xTF32 products (hi/lo operand split), i.e. fp32 to ~1e-6."""
 
-    def __init__(self, on=True, heads=True):
-        self.on, self.heads = on, heads
+    def __init__(self, on=True, heads=True, gelu_half=False):
+        self.on, self.heads, self.gelu_half = on, heads, gelu_half
 
     def __enter__(self):
-        global _EMULATE_TF32, _EMULATE_HEADS
-        self.prev = (_EMULATE_TF32, _EMULATE_HEADS)
-        _EMULATE_TF32, _EMULATE_HEADS = self.on, self.heads
+        global _EMULATE_TF32, _EMULATE_HEADS, _EMULATE_GELU_H
+        self.prev = (_EMULATE_TF32, _EMULATE_HEADS, _EMULATE_GELU_H)
+        _EMULATE_TF32, _EMULATE_HEADS, _EMULATE_GELU_H = self.on, self.heads, bool(self.on and self.gelu_half)
 
     def __exit__(self, *exc):
-        global _EMULATE_TF32, _EMULATE_HEADS
-        _EMULATE_TF32, _EMULATE_HEADS = self.prev
+        global _EMULATE_TF32, _EMULATE_HEADS, _EMULATE_GELU_H
+        _EMULATE_TF32, _EMULATE_HEADS, _EMULATE_GELU_H = self.prev
 
 
 def rna_tf32(x):
@@ -180,6 +184,29 @@ def linear(x, w, b=None):
     if _EMULATE_TF32:
         return _LinearTF32.apply(x, w, b)
     return F.linear(x, w, b)
+
+
+class _GeluHalfGrad(torch.autograd.Function):
+    """exact GELU (audiossl/modules/transformer.py:77-92, nn.GELU) whose backward multiplies by
+    gelu'(u) = Phi(u) + u phi(u) rounded to fp16 - what EPI_GELU_H stores and EPI_DGELU_H reads."""
+
+    @staticmethod
+    def forward(ctx, u):
+        cdf = 0.5 * (1.0 + torch.erf(u * 0.7071067811865476))
+        pdf = 0.3989422804014327 * torch.exp(-0.5 * u * u)
+        ctx.save_for_backward((cdf + u * pdf).to(torch.float16))
+        return F.gelu(u)
+
+    @staticmethod
+    def backward(ctx, g):
+        (gp,) = ctx.saved_tensors
+        return g * gp.to(torch.float32)
+
+
+def gelu(u):
+    if _EMULATE_TF32 and _EMULATE_GELU_H and u.requires_grad:
+        return _GeluHalfGrad.apply(u)
+    return F.gelu(u)
 
 
 class OLinear(nn.Linear):
@@ -274,7 +301,7 @@ class OracleBlock(nn.Module):
         if dp_scale is not None:
             y = y * dp_scale[0][:, None, None]
         x = x + y
-        z = linear(F.gelu(linear(self.norm2(x), self.mlp.fc1.weight, self.mlp.fc1.bias)), self.mlp.fc2.weight,
+        z = linear(gelu(linear(self.norm2(x), self.mlp.fc1.weight, self.mlp.fc1.bias)), self.mlp.fc2.weight,
                    self.mlp.fc2.bias)
         if dp_scale is not None:
             z = z * dp_scale[1][:, None, None]

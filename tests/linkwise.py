@@ -156,8 +156,8 @@ def check_step(model, ref, crops, lengths, masks=None, dp_teacher=None, dp_stude
     passes_t = pass_info(ref.teacher, groups_t, dp_teacher, "t", False)
     passes_s = pass_info(ref.student, groups_s, dp_student, "s", True)
 
-    from audiossl_b200.engine import HEADS_3X  # the heads run as 3xTF32 (~fp32) products unless switched off
-    with O.tf32_emulation(True, heads=not HEADS_3X):
+    from audiossl_b200.engine import HEADS_3X, half_dgelu  # the heads run as 3xTF32 (~fp32) products unless switched off
+    with O.tf32_emulation(True, heads=not HEADS_3X, gelu_half=half_dgelu()):
         # ------------------------------------------------------------------ forward links, both networks
         enc_out = {"t": [], "s": []}
         plens = {}

@@ -108,6 +108,59 @@ def test_schedules_and_param_groups():
     assert reg == list(g["reg"]) and noreg == list(g["noreg"])
 
 
+def test_hf_adamw_restatement_against_torch_adam():
+    """transformers-4.x AdamW is absent from the image (parity unpinned), but its published update is an
+    exact re-parametrisation of torch's Adam: HF puts eps beside the UNcorrected sqrt(v) and folds both bias corrections
+    into the step size, torch divides sqrt(v) by sqrt(1 - b2^t) first - so one HF step with eps equals one torch.optim.Adam
+    step with eps / sqrt(1 - b2^t) - followed by HF's decoupled decay p -= lr * wd * p on the UPDATED weights.  An
+    independent implementation of the Adam half, five steps with the schedule's changing lr / wd."""
+    torch.manual_seed(3)
+    p0 = torch.randn(64, 48, dtype=torch.float64)
+    grads = [torch.randn_like(p0) * (0.3 + 0.2 * t) for t in range(5)]
+    lrs, wds = [1e-3, 8e-4, 5e-4, 5e-4, 1e-4], [0.04, 0.05, 0.1, 0.2, 0.4]
+    b1, b2, eps = 0.9, 0.999, 1e-6
+    p_or, m, v = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    p_t = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([p_t], lr=1.0, betas=(b1, b2), eps=eps, weight_decay=0.0)
+    for t, (g, lr, wd) in enumerate(zip(grads, lrs, wds), start=1):
+        O.hf_adamw_step(p_or, g, m, v, t, lr, wd, b1, b2, eps)
+        for grp in opt.param_groups:
+            grp["lr"], grp["eps"] = lr, eps / (1.0 - b2 ** t) ** 0.5
+        p_t.grad = g.clone()
+        opt.step()
+        with torch.no_grad():
+            p_t.mul_(1.0 - lr * wd)
+        np.testing.assert_allclose(p_or.numpy(), p_t.detach().numpy(), rtol=1e-12, atol=1e-14)
+    st = opt.state[p_t]
+    np.testing.assert_allclose(m.numpy(), st["exp_avg"].numpy(), rtol=1e-11)
+    np.testing.assert_allclose(v.numpy(), st["exp_avg_sq"].numpy(), rtol=1e-11)
+    # and what distinguishes it from torch.optim.AdamW (decay BEFORE the update, eps beside the corrected sqrt(v))
+    q = torch.nn.Parameter(p0.clone())
+    ow = torch.optim.AdamW([q], lr=lrs[0], betas=(b1, b2), eps=eps, weight_decay=wds[0])
+    q.grad = grads[0].clone()
+    ow.step()
+    p1, m1, v1 = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    O.hf_adamw_step(p1, grads[0], m1, v1, 1, lrs[0], wds[0], b1, b2, eps)
+    d = (p1 - q.detach()).abs().max().item()
+    assert 1e-9 < d < 1e-3, d   # close, not equal: decay order (O(lr^2 wd)) and where eps sits (small |g| elements)
+
+
+def test_gelu_half_emulation_only_touches_the_backward():
+    """tf32_emulation(gelu_half=True) = the CUDA path's fp16 gelu'(u) side stream: same forward, a backward that differs
+    from the exact derivative by at most half an fp16 ulp of a value <= 1.13."""
+    u = (torch.randn(64, 96, generator=torch.Generator().manual_seed(5)) * 2.5).requires_grad_(True)
+    d = torch.randn(64, 96, generator=torch.Generator().manual_seed(6))
+    y0 = torch.nn.functional.gelu(u)
+    (g0,) = torch.autograd.grad(y0, u, d)
+    with O.tf32_emulation(True, gelu_half=True):
+        y1 = O.gelu(u)
+        (g1,) = torch.autograd.grad(y1, u, d)
+    with O.tf32_emulation(True):
+        (g2,) = torch.autograd.grad(O.gelu(u), u, d)
+    assert torch.equal(y0, y1) and torch.equal(g0, g2)
+    assert 0 < (g1 - g0).abs().max().item() and ((g1 - g0).abs() <= d.abs() * (2.0 ** -11 + 1e-6)).all()
+
+
 def frame_masks(tag, B, P):
     m = detfill.det_array(tag + "/mask", (B, P), 1.0, "uniform") > 0.0
     m[:, 0] = True

@@ -264,6 +264,44 @@ def test_gelu_fused_epilogues_match_torch(M, N, K):
     assert rel(cs, 1.0 + du.double().sum(0)) < 1e-5  # column sums of the stored values, accumulated
 
 
+@pytest.mark.parametrize("M,N,K", [(300, 512, 128), (1003, 1536, 384), (515, 256, 64), (40037, 3072, 768), (777, 1040, 96)])
+def test_gelu_fp16_derivative_epilogues(M, N, K):
+    """fc1 epilogue that stores gelu'(u) as fp16 beside gelu(u) (EPI_GELU_H) and the fc2 dgrad that multiplies by it
+    (EPI_DGELU_H): the forward output is the fp32-side-stream epilogue's, the stored derivative is the
+    fp16 rounding of Phi(u) + u phi(u), and du equals the product with exactly that stored value.  Ragged row counts,
+    a partial last N tile (1040 = 4 * 256 + 16) and more tiles than CTA pairs."""
+    from audiossl_b200 import ops
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(2)
+    A = ops.round_tf32(torch.randn(M, K, device="cuda"))
+    W = ops.round_tf32(torch.randn(N, K, device="cuda") * 0.1)
+    b = torch.randn(N, device="cuda")
+    u = torch.empty(M, N, device="cuda")
+    g_ref = ops.gemm_nt(A, W, bias=b, epi=ops.EPI_GELU, aux=u, round_out=True)
+    gp = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float16)
+    g = ops.gemm_nt(A, W, bias=b, epi=ops.EPI_GELU_H, aux=gp, round_out=True)
+    assert rel(g, g_ref) < 1e-6  # same arithmetic (u * cdf) in both epilogues
+    ud = u.double()
+    gp_ref = 0.5 * (1 + torch.erf(ud * 0.7071067811865476)) + ud * torch.exp(-0.5 * ud * ud) * 0.3989422804014327
+    assert torch.isfinite(gp.float()).all()
+    err = (gp.double() - gp_ref).abs()
+    # half an fp16 ulp of a value of magnitude <= 1.13 (2^-11) plus the 1.5e-7 of the erf approximation
+    assert err.max().item() < 2.0 ** -11 + 1e-6, err.max().item()
+    K2 = 128
+    dy = ops.round_tf32(torch.randn(M, K2, device="cuda"))
+    W2 = ops.round_tf32(torch.randn(K2, N, device="cuda") * 0.1)
+    du = ops.gemm_nn(dy, W2, epi=ops.EPI_DGELU_H, aux=gp, round_out=True)
+    du_ref = ops.round_tf32(((dy.double() @ W2.double()) * gp.double()).float())
+    # (fp32 vs fp64 accumulation moves a few 1e-4 of the elements across a TF32 rounding boundary: ~1e-5 in norm)
+    assert rel(du, du_ref) < 5e-5, rel(du, du_ref)
+    # and against autograd's exact derivative: the fp16 rounding is all that separates them (2^-11 / sqrt(3) rms)
+    ur = u.clone().requires_grad_(True)
+    torch.nn.functional.gelu(ur).backward(dy @ W2)
+    assert rel(du, ur.grad) < 6e-4
+    with pytest.raises(TypeError):
+        ops.gemm_nn(dy, W2, epi=ops.EPI_DGELU_H, aux=u, round_out=True)
+
+
 @pytest.mark.parametrize("M,N,K,rps", [(2008, 768, 768, 251), (156, 128, 128, 26), (50003, 768, 768, 7), (2008, 3072, 768, 251)])
 def test_residual_epilogue_at_ragged_row_counts(M, N, K, rps):
     """proj / fc2 epilogue  C = resid + rowscale[seq] * (A W^T + bias)  when the last 32-row group of the matrix is

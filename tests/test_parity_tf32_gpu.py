@@ -23,7 +23,7 @@ import numpy as np
 import pytest
 import torch
 
-from audiossl_b200.engine import HEADS_3X
+from audiossl_b200.engine import HEADS_3X, half_dgelu
 from tests import linkwise, util
 
 pytestmark = pytest.mark.gpu
@@ -94,7 +94,7 @@ def test_end_to_end_distance_is_the_tf32_distance():
         for p in ref.parameters():
             p.grad = None
         r2 = oracle_like(m)  # fresh BatchNorm buffers
-        with O.tf32_emulation(emulate, heads=not HEADS_3X):
+        with O.tf32_emulation(emulate, heads=not HEADS_3X, gelu_half=half_dgelu()):
             t = r2.teacher(crops[:2], lengths[:2])
             s = r2.student(crops, lengths)
             l, _, _ = O.byol_loss(s, t, 2)
@@ -292,7 +292,7 @@ def _three_steps(lm, ref, batches, frame, loss_rtol=5e-3, emulate=True):
         lm.on_train_batch_end(None, None, step)
         for p in ref.student.parameters():
             p.grad = None
-        with O.tf32_emulation(emulate, heads=not HEADS_3X):
+        with O.tf32_emulation(emulate, heads=not HEADS_3X, gelu_half=half_dgelu()):
             rl = ref(*batch)[0]
             rl.backward()
         lr, wd = lm.mylr_scheduler[step], lm.wd_scheduler[step]
