@@ -126,7 +126,7 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
 
 }  // namespace
 
-template <bool A_MN, bool B_MN, bool EPI_H = false>
+template <bool A_MN, bool B_MN, int ECLS = ECLS_GENERIC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 gemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
   extern __shared__ uint8_t smem_raw2[];
@@ -274,7 +274,7 @@ gemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int tidx = (tile - first_tile) / tile_step;  // this CTA's tile counter
       const bool tr = p.trace != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0 && tidx >= 8 && tidx < 12;
       if (tr) p.trace[8 * (tidx - 8) + 0] = clock64();  // epilogue warp arrives at the tile
-      epilogue_tile<kBN, 32 * kEpiWarps2, EPI_H>(p, m0, n0, empty_split, tmem_base + acc * kBN, smem_bias + acc * 256, ew, lane,
+      epilogue_tile<kBN, 32 * kEpiWarps2, ECLS>(p, m0, n0, empty_split, tmem_base + acc * kBN, smem_bias + acc * 256, ew, lane,
                                           epi_tid, chalf * kGroupsPerWarp, (chalf + 1) * kGroupsPerWarp, &tfull_bar[acc],
                                           acc_phase, release, tr ? p.trace + 8 * (tidx - 8) : nullptr);
       if (tr) p.trace[8 * (tidx - 8) + 3] = clock64();  // tile stored
@@ -299,10 +299,10 @@ int make_map_mnmajor_pub(CUtensorMap* map, const float* ptr, int tokens, int fea
 int gemm_num_sms();
 long long* gemm_trace_ptr();
 
-template <bool A_MN, bool B_MN, bool EPI_H = false>
+template <bool A_MN, bool B_MN, int ECLS = ECLS_GENERIC>
 static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   static bool configured = false;
-  auto kfn = gemm2_tf32_kernel<A_MN, B_MN, EPI_H>;
+  auto kfn = gemm2_tf32_kernel<A_MN, B_MN, ECLS>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2);
     if (e != cudaSuccess) { atst_set_error("cudaFuncSetAttribute(gemm2): %s", cudaGetErrorString(e)); return ATST_ERR_CUDA; }
@@ -330,16 +330,27 @@ int gemm2_launch(int a_mn, int b_mn, const float* A, int lda, int a_rows, int a_
   if (b_mn) rc = make_map_mnmajor_pub(&tb, B, b_rows, b_cols, ldb, kBNHalf, p.mn_tma_swizzle);
   else      rc = make_map_kmajor_pub(&tb, B, b_rows, b_cols, ldb, kBNHalf);
   if (rc) return rc;
-  // fp16 GELU' side stream (EPI_GELU_H forward, EPI_DGELU_H dgrad): own instantiations of the kernel
-  if (p.epi == EPI_GELU_H && !a_mn && !b_mn) return launch2<false, false, true>(ta, tb, p, stream);
-  if (p.epi == EPI_DGELU_H && !a_mn && b_mn) return launch2<false, true, true>(ta, tb, p, stream);
-  if (p.epi == EPI_GELU_H || p.epi == EPI_DGELU_H) {
-    atst_set_error("gemm2: epilogue %d is not available for this operand layout", p.epi);
-    return ATST_ERR_ARG;
+  // one instantiation per (operand layout, epilogue class) in use; everything else goes to the generic epilogue
+  const bool simple = p.colsum == nullptr;
+  const bool plain = simple && (p.epi == EPI_STORE || p.epi == EPI_SCALE || p.epi == EPI_RELU || p.epi == EPI_ATOMIC);
+  if (!a_mn && !b_mn) {  // NT: forward
+    if (p.epi == EPI_GELU_H) return p.aux != nullptr ? launch2<false, false, ECLS_HALF_FWD>(ta, tb, p, stream)
+                                                     : launch2<false, false, ECLS_GELU>(ta, tb, p, stream);
+    if (p.epi == EPI_GELU && p.aux == nullptr && simple) return launch2<false, false, ECLS_GELU>(ta, tb, p, stream);
+    if (p.epi == EPI_RESID && simple) return launch2<false, false, ECLS_RESID>(ta, tb, p, stream);
+    if (plain) return launch2<false, false, ECLS_PLAIN>(ta, tb, p, stream);
+    if (p.epi == EPI_DGELU_H) { atst_set_error("gemm2: EPI_DGELU_H belongs to the dgrad (NN) GEMM"); return ATST_ERR_ARG; }
+    return launch2<false, false>(ta, tb, p, stream);
   }
-  if (!a_mn && !b_mn) return launch2<false, false>(ta, tb, p, stream);
-  if (!a_mn && b_mn) return launch2<false, true>(ta, tb, p, stream);
-  return launch2<true, true>(ta, tb, p, stream);
+  if (!a_mn && b_mn) {  // NN: dgrad
+    if (p.epi == EPI_DGELU_H) return launch2<false, true, ECLS_HALF_BWD>(ta, tb, p, stream);
+    if (p.epi == EPI_GELU_H) { atst_set_error("gemm2: EPI_GELU_H belongs to the forward (NT) GEMM"); return ATST_ERR_ARG; }
+    if (plain) return launch2<false, true, ECLS_PLAIN>(ta, tb, p, stream);
+    return launch2<false, true>(ta, tb, p, stream);
+  }
+  // TN: wgrad, always split-K accumulation
+  if (!plain) { atst_set_error("gemm2: epilogue %d is not available for the wgrad (TN) GEMM", p.epi); return ATST_ERR_ARG; }
+  return launch2<true, true, ECLS_PLAIN>(ta, tb, p, stream);
 }
 
 }  // namespace atst

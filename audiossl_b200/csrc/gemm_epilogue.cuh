@@ -72,19 +72,42 @@ __device__ __forceinline__ float gelu_grad(float u) {
 // a quad transpose (same time), a shared-memory staging tile with TMA loads / stores (slower: the shared-memory port
 // belongs to TMA + UMMA), 32- or 16-column accumulator loads in flight with an early release of the stage (plain
 // shapes +5 %, fused shapes -20 %: the unthrottled main loop takes the link from the epilogue that is the bottleneck).
-template <int BLOCK_N, int EPI_THREADS, bool HALF_SIDE = false, class Release>
+//
+// ECLS: the epilogue class this instantiation is compiled for.  The runtime `switch (p.epi)` form of every epilogue in
+// one kernel (ECLS_GENERIC, kept for the rarely used variants) costs all of them its registers (96 with spills) and its
+// code: the same fc1 + GELU epilogue without a side stream runs at 0.985 ms per config-2 launch compiled alone
+// against 1.098 ms inside the generic kernel (tools/ab_gelu_half.py; plain fc1: 0.962 ms).
+enum EpiClass : int {
+  ECLS_GENERIC = 0,   // any p.epi at run time (fp32 pre-activation side streams, column sums)
+  ECLS_PLAIN = 1,     // one output stream: EPI_STORE / EPI_SCALE / EPI_RELU / EPI_ATOMIC (+ bias, rounding)
+  ECLS_RESID = 2,     // EPI_RESID
+  ECLS_GELU = 3,      // EPI_GELU without a stored pre-activation (teacher / inference fc1)
+  ECLS_HALF_FWD = 4,  // EPI_GELU_H
+  ECLS_HALF_BWD = 5,  // EPI_DGELU_H
+};
+
+template <int BLOCK_N, int EPI_THREADS, int ECLS = ECLS_GENERIC, class Release>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n0, bool empty_split, uint32_t taddr,
                                               float* sbias, int ew, int lane, int epi_tid, int g0, int g1,
                                               uint64_t* tfull_bar, uint32_t acc_phase, Release release,
                                               long long* trace = nullptr) {
-  const float* side_ptr = (p.epi == EPI_RESID) ? p.resid : ((p.epi == EPI_DGELU) ? p.aux : nullptr);
-  const int side_ld = (p.epi == EPI_RESID) ? p.ldr : p.ldaux;
+  constexpr bool kGeneric = ECLS == ECLS_GENERIC;
+  constexpr bool kHalf = ECLS == ECLS_GELU || ECLS == ECLS_HALF_FWD || ECLS == ECLS_HALF_BWD;
+  const float* side_ptr = nullptr;
+  int side_ld = 0;
+  if constexpr (ECLS == ECLS_RESID) {
+    side_ptr = p.resid;
+    side_ld = p.ldr;
+  } else if constexpr (kGeneric) {
+    side_ptr = (p.epi == EPI_RESID) ? p.resid : ((p.epi == EPI_DGELU) ? p.aux : nullptr);
+    side_ld = (p.epi == EPI_RESID) ? p.ldr : p.ldaux;
+  }
   const int gm = m0 + ew * 32 + lane;
   const bool row_ok = gm < p.M && !empty_split;
   const float rs = (p.rowscale != nullptr && row_ok) ? p.rowscale[gm / p.rows_per_seq] : 1.0f;
   const float* side_row = (side_ptr && row_ok) ? side_ptr + static_cast<size_t>(gm) * side_ld + n0 : nullptr;
   float* c_row = p.C + static_cast<size_t>(gm) * p.ldc + n0;
-  float* aux_row = (p.epi == EPI_GELU && p.aux != nullptr) ? p.aux + static_cast<size_t>(gm) * p.ldaux + n0 : nullptr;
+  float* aux_row = (kGeneric && p.epi == EPI_GELU && p.aux != nullptr) ? p.aux + static_cast<size_t>(gm) * p.ldaux + n0 : nullptr;
   const int ncols = min(BLOCK_N, p.N - n0);  // valid columns of this tile (multiple of 8)
   // while this tile's main loop is still running: pull the side-input rows into L2 and stage the bias slice
   if (side_row != nullptr) {
@@ -105,7 +128,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
   auto fetch_side = [&](int g, float (&sd)[8]) {
     if (side_row != nullptr && g < g1 && g * 8 < ncols) ld_global_v8(side_row + g * 8, sd);
   };
-  const bool do_colsum = p.colsum != nullptr;  // warp-uniform
+  const bool do_colsum = kGeneric && p.colsum != nullptr;  // warp-uniform
   auto finish = [&](int g, const uint32_t (&r)[8], const float (&sd)[8]) {
     if (g * 8 >= ncols || (!row_ok && !do_colsum)) return;
     float v[8];
@@ -117,7 +140,19 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
       v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
       v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
     }
-    switch (p.epi) {
+    if constexpr (ECLS == ECLS_RESID) {  // C <- resid + rowscale[seq] * (acc + bias)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = fmaf(rs, v[e], sd[e]);
+    } else if constexpr (ECLS == ECLS_PLAIN) {
+      if (p.epi == EPI_SCALE) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] *= rs;
+      } else if (p.epi == EPI_RELU) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+      }
+    } else {
+      switch (p.epi) {
       case EPI_GELU:  // aux (nullable: the teacher keeps no pre-activation) <- pre-activation, C <- gelu
         if (aux_row != nullptr) st_global_v8(aux_row + g * 8, v);
 #pragma unroll
@@ -141,6 +176,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
         break;
       default:
         break;
+      }
     }
     if (p.round_out) {
 #pragma unroll
@@ -148,7 +184,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
     }
     float* cp = c_row + g * 8;
     if (row_ok) {
-      if (p.epi == EPI_ATOMIC) {
+      if (ECLS != ECLS_RESID && p.epi == EPI_ATOMIC) {
         red_add_v4(cp, v[0], v[1], v[2], v[3]);
         red_add_v4(cp + 4, v[4], v[5], v[6], v[7]);
       } else {
@@ -167,56 +203,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
       if (lane < 8) atomicAdd(p.colsum + n0 + g * 8 + lane, mine);
     }
   };
-  // warp-uniform by construction (parameters only): the two forms below use .sync.aligned TMEM loads and each calls
-  // release() once per warp, so a warp must never split between them - with the per-thread side_row in this test, a
-  // warp straddling the last valid row of a residual epilogue did (rows past M have no side pointer), which
-  // double-released the accumulator stage and hung the kernel for M % 32 != 0
-  const bool one_stream = side_ptr == nullptr && p.epi != EPI_GELU && p.epi != EPI_DGELU;
-  if (one_stream) {
-    // Plain epilogues (one global stream, no GELU math): the tile period is the main loop, and what matters is handing
-    // the accumulator stage back early - a tcgen05.ld takes ~1500 cycles under a running main loop, so eight dependent
-    // 8-column loads hold the stage for ~12 000 cycles and the MMA issuer waits ~2500 cycles per tile for a free one.
-    // Two 16-column loads in flight, the next pair issued while this one is stored, release after the last wait
-    // (+5 % on these shapes; the fused epilogues below lose 20 % with it and keep the sequential form).
-    uint32_t wa[16], wb[16];
-    float none[8];
-    tmem_ld_32x16(taddr + g0 * 8, wa);
-    tmem_ld_32x16(taddr + g0 * 8 + 16, wb);
-    tmem_ld_wait();
-    if (g0 + 4 >= g1) {
-      tc_fence_before();
-      __syncwarp();
-      release();
-    }
-#pragma unroll 1
-    for (int g = g0; g < g1; g += 4) {
-      const bool more = g + 4 < g1;
-      finish(g, *reinterpret_cast<const uint32_t(*)[8]>(&wa[0]), none);
-      finish(g + 1, *reinterpret_cast<const uint32_t(*)[8]>(&wa[8]), none);
-      if (more) tmem_ld_32x16(taddr + (g + 4) * 8, wa);
-      finish(g + 2, *reinterpret_cast<const uint32_t(*)[8]>(&wb[0]), none);
-      finish(g + 3, *reinterpret_cast<const uint32_t(*)[8]>(&wb[8]), none);
-      if (more) {
-        tmem_ld_32x16(taddr + (g + 6) * 8, wb);
-        tmem_ld_wait();
-        if (g + 8 >= g1) {  // this warp's last TMEM load of the tile has completed
-          tc_fence_before();
-          __syncwarp();
-          release();
-        }
-      }
-    }
-    return;
-  }
-  if constexpr (HALF_SIDE) {
-    // (own kernel instantiation: the loops below are compiled out of it, and this one out of theirs, so neither
-    // costs the other registers.)  The student's MLP with an fp16 side stream: EPI_GELU_H stores gelu'(pre-activation) - from the same cdf / pdf as
-    // the GELU itself - and EPI_DGELU_H multiplies by it.  Same pipeline as the loop below (8-column accumulator loads
-    // one ahead), its own copy so that the carried words cost the other epilogues no registers.  The side stream moves
+  if constexpr (kHalf) {
+    // The student's MLP with an fp16 side stream (own kernel instantiation: the loops below are compiled out of it and
+    // this one out of theirs, so neither costs the other registers): EPI_GELU_H stores gelu'(pre-activation) - from the
+    // same cdf / pdf as the GELU itself - and EPI_DGELU_H multiplies by it.  Same pipeline as the two-stream loop at
+    // the end (8-column accumulator loads one ahead).  The side stream moves
     // as ONE 32-byte sector per PAIR of groups (16 halfs): the even group of a pair loads / the odd group stores the
     // sector, `hp` carries the other group's four packed words in between.  g0 even, N % 16 == 0 (host-checked).
-    const bool fwd = p.epi == EPI_GELU_H;  // warp-uniform
-    uint16_t* haux = (p.aux != nullptr && row_ok)
+    constexpr bool fwd = ECLS != ECLS_HALF_BWD;
+    constexpr bool deriv = ECLS == ECLS_HALF_FWD;  // ECLS_GELU: the same loop without the side stream
+    uint16_t* haux = (ECLS != ECLS_GELU && p.aux != nullptr && row_ok)
                          ? reinterpret_cast<uint16_t*>(p.aux) + static_cast<size_t>(gm) * p.ldaux + n0 : nullptr;
     if (!fwd && haux != nullptr) {
       for (int g = g0; g < g1; g += 8)
@@ -239,15 +235,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
           v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
           v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
         }
-        uint32_t w[4];
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const GeluParts a = gelu_parts(v[2 * i]), b = gelu_parts(v[2 * i + 1]);
-          w[i] = pack_half2(fmaf(v[2 * i], a.pdf, a.cdf), fmaf(v[2 * i + 1], b.pdf, b.cdf));
+          if constexpr (deriv) w[i] = pack_half2(fmaf(v[2 * i], a.pdf, a.cdf), fmaf(v[2 * i + 1], b.pdf, b.cdf));
           v[2 * i] *= a.cdf;
           v[2 * i + 1] *= b.cdf;
         }
-        if (even) {
+        if constexpr (!deriv) {
+        } else if (even) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) hp[i] = w[i];
         } else if (haux != nullptr) {
@@ -299,6 +296,50 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
         release();
       }
       finish_h(g + 3, rb, sh[1], false);
+    }
+    return;
+  }
+  // warp-uniform by construction (parameters only): the two forms below use .sync.aligned TMEM loads and each calls
+  // release() once per warp, so a warp must never split between them - with the per-thread side_row in this test, a
+  // warp straddling the last valid row of a residual epilogue did (rows past M have no side pointer), which
+  // double-released the accumulator stage and hung the kernel for M % 32 != 0
+  bool one_stream;
+  if constexpr (ECLS == ECLS_PLAIN) one_stream = true;
+  else if constexpr (ECLS == ECLS_RESID) one_stream = false;
+  else one_stream = side_ptr == nullptr && p.epi != EPI_GELU && p.epi != EPI_DGELU;
+  if (one_stream) {
+    // Plain epilogues (one global stream, no GELU math): the tile period is the main loop, and what matters is handing
+    // the accumulator stage back early - a tcgen05.ld takes ~1500 cycles under a running main loop, so eight dependent
+    // 8-column loads hold the stage for ~12 000 cycles and the MMA issuer waits ~2500 cycles per tile for a free one.
+    // Two 16-column loads in flight, the next pair issued while this one is stored, release after the last wait
+    // (+5 % on these shapes; the fused epilogues below lose 20 % with it and keep the sequential form).
+    uint32_t wa[16], wb[16];
+    float none[8];
+    tmem_ld_32x16(taddr + g0 * 8, wa);
+    tmem_ld_32x16(taddr + g0 * 8 + 16, wb);
+    tmem_ld_wait();
+    if (g0 + 4 >= g1) {
+      tc_fence_before();
+      __syncwarp();
+      release();
+    }
+#pragma unroll 1
+    for (int g = g0; g < g1; g += 4) {
+      const bool more = g + 4 < g1;
+      finish(g, *reinterpret_cast<const uint32_t(*)[8]>(&wa[0]), none);
+      finish(g + 1, *reinterpret_cast<const uint32_t(*)[8]>(&wa[8]), none);
+      if (more) tmem_ld_32x16(taddr + (g + 4) * 8, wa);
+      finish(g + 2, *reinterpret_cast<const uint32_t(*)[8]>(&wb[0]), none);
+      finish(g + 3, *reinterpret_cast<const uint32_t(*)[8]>(&wb[8]), none);
+      if (more) {
+        tmem_ld_32x16(taddr + (g + 6) * 8, wb);
+        tmem_ld_wait();
+        if (g + 8 >= g1) {  // this warp's last TMEM load of the tile has completed
+          tc_fence_before();
+          __syncwarp();
+          release();
+        }
+      }
     }
     return;
   }

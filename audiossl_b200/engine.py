@@ -26,7 +26,7 @@ from . import ops
 #                         10-bit mantissa the TF32 rounding of du leaves anyway - instead of the fp32 pre-activation u:
 #                         the second stream of the fc1 and fc2-dgrad epilogues is half the bytes and the dgrad epilogue
 #                         has no GELU math left.  Never in the 3xTF32 validation build.
-_FG = int(os.environ.get("ATST_FUSE_GELU", "7"))
+_FG = int(os.environ.get("ATST_FUSE_GELU", "23"))
 FUSE_GELU_NOSAVE, FUSE_GELU, FUSE_DGELU, FUSE_COLSUM = bool(_FG & 1), bool(_FG & 2), bool(_FG & 4), bool(_FG & 8)
 HALF_DGELU = bool(_FG & 16) and FUSE_GELU and FUSE_DGELU
 

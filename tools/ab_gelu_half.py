@@ -25,15 +25,25 @@ u = torch.empty(M, 4 * D, device="cuda")
 gp = torch.empty(M, 4 * D, device="cuda", dtype=torch.float16)
 g = torch.empty(M, 4 * D, device="cuda")
 du = torch.empty(M, 4 * D, device="cuda")
+Wp = ops.round_tf32(torch.randn(D, D, device="cuda") * 0.05)
+bp = torch.randn(D, device="cuda")
+x1 = torch.empty(M, D, device="cuda")
+Wq = ops.round_tf32(torch.randn(3 * D, D, device="cuda") * 0.05)
+qkv = torch.empty(M, 3 * D, device="cuda")
 
 variants = {
     "fc1 plain (u only)": lambda: ops.gemm_nt(h, W1, bias=b1, out=u),
     "fc1 + GELU, no side stream (teacher)": lambda: ops.gemm_nt(h, W1, bias=b1, epi=ops.EPI_GELU, aux=None, round_out=True, out=g),
     "fc1 + GELU, u fp32": lambda: ops.gemm_nt(h, W1, bias=b1, epi=ops.EPI_GELU, aux=u, round_out=True, out=g),
     "fc1 + GELU, gelu' fp16": lambda: ops.gemm_nt(h, W1, bias=b1, epi=ops.EPI_GELU_H, aux=gp, round_out=True, out=g),
+    "fc1 + GELU, no side stream, compact kernel": lambda: ops.gemm_nt(h, W1, bias=b1, epi=ops.EPI_GELU_H, aux=None, round_out=True, out=g),
     "fc2 dgrad plain": lambda: ops.gemm_nn(dy, W2, round_out=True, out=du),
     "fc2 dgrad * gelu'(u fp32)": lambda: ops.gemm_nn(dy, W2, epi=ops.EPI_DGELU, aux=u, round_out=True, out=du),
     "fc2 dgrad * gelu' fp16": lambda: ops.gemm_nn(dy, W2, epi=ops.EPI_DGELU_H, aux=gp, round_out=True, out=du),
+    "proj plain (N = K = 768)": lambda: ops.gemm_nt(h, Wp, bias=bp, out=x1),
+    "proj + residual": lambda: ops.gemm_nt(h, Wp, bias=bp, epi=ops.EPI_RESID, resid=dy, out=x1),
+    "fc2 + residual (K = 3072)": lambda: ops.gemm_nt(g, W2, bias=bp, epi=ops.EPI_RESID, resid=dy, out=x1),
+    "qkv plain (N = 2304)": lambda: ops.gemm_nt(h, Wq, round_out=True, out=qkv),
 }
 for f in variants.values():  # warm-up (tensor maps, instruction cache, clocks)
     for _ in range(3):
@@ -48,8 +58,10 @@ for _ in range(reps):
         e1.record()
         e1.synchronize()
         times[k].append(e0.elapsed_time(e1))
-flop = 2.0 * M * 4 * D * D
+flops = {k: 2.0 * M * 4 * D * D for k in variants}
+flops["proj plain (N = K = 768)"] = flops["proj + residual"] = 2.0 * M * D * D
+flops["qkv plain (N = 2304)"] = 2.0 * M * 3 * D * D
 for k, t in times.items():
     t = sorted(t)
     med = t[len(t) // 2]
-    print("%-40s  median %.3f ms  (min %.3f)  %.0f TFLOP/s" % (k, med, t[0], flop / med * 1e-9))
+    print("%-44s  median %.3f ms  (min %.3f)  %.0f TFLOP/s" % (k, med, t[0], flops[k] / med * 1e-9))
