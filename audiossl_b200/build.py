@@ -24,6 +24,7 @@ VARIANTS = {
     "precise": dict(lib="libatst_b200_precise.so", defs=["-DATST_PRECISE"], extra=[]),
     "debug": dict(lib="libatst_b200_debug.so", defs=["-DATST_DEBUG_ABI"], extra=["probe.cu"]),
 }
+# experiment builds: python -m audiossl_b200.build --exp NAME=-DMACRO=1[,-D...] writes libatst_b200_exp_NAME.so
 
 
 def lib_path(variant=""):
@@ -77,4 +78,9 @@ def build(force=False, verbose=False, debug=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, debug="--debug" in sys.argv))
+    if "--exp" in sys.argv:
+        name, defs = sys.argv[sys.argv.index("--exp") + 1].split("=", 1)
+        VARIANTS["exp_" + name] = dict(lib="libatst_b200_exp_%s.so" % name, defs=defs.split(","), extra=[])
+        print(build_variant("exp_" + name, True, "-v" in sys.argv))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, debug="--debug" in sys.argv))

@@ -27,11 +27,21 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+#ifndef ATST_RNA_INT
+#define ATST_RNA_INT 0
+#endif
 // cvt.rna.tf32.f32: 10 mantissa bits, nearest, ties away from zero
 __device__ __forceinline__ float cvt_rna_tf32(float x) {
+#if ATST_RNA_INT
+  // the same rounding as two integer instructions (add half an ulp of the 10-bit mantissa to the magnitude, clear
+  // the 13 low bits); cvt.rna.tf32.f32 compiles to FSETP + predicated IADD + LOP3 on sm_100 to leave NaN payloads
+  // alone - identical results for every finite input and for infinities
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+#else
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
+#endif
 }
 // What a producer applies to a value it hands to a tensor-core product.  Default build: round to TF32.  The
 // validation build (-DATST_PRECISE, libatst_b200_precise.so) keeps fp32 here: its products are error-compensated

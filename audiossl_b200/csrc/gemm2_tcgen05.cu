@@ -113,13 +113,18 @@ __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
                "h"(mask)
                : "memory");
 }
-// arrive on the barrier at this smem offset in CTA 0 of the pair (works from either CTA)
+// arrive on the barrier at this smem offset in CTA 0 of the pair (works from either CTA).  Default semantics
+// (.release.cta): what is handed over is "this warp's tcgen05.ld of the stage have completed", ordered by
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync, not memory.  The .release.cluster form compiled to
+// MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front of the arrive, i.e. every epilogue warp waited for its outstanding
+// global stores to drain before the MMA issuer got the accumulator stage back (ncu: "membar" was 13 % of the stall
+// cycles of the plain epilogue, profiles/r02_ncu_epilogue_classes.txt).
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile(
       "{\n\t"
       ".reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
       "}" ::"r"(smem_u32(bar))
       : "memory");
 }

@@ -5,6 +5,10 @@
 #include "common.cuh"
 #include "gemm.h"
 
+#ifndef ATST_EPI_X16
+#define ATST_EPI_X16 0   // 1: the two-stream epilogues fetch 16 accumulator columns per tcgen05.ld (single buffer)
+#endif
+
 namespace atst {
 
 // erf by Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, far below the TF32 operand rounding of the next GEMM):
@@ -271,6 +275,33 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
       }
       st_global_v8(c_row + g * 8, v);
     };
+#if ATST_EPI_X16
+    {
+      uint32_t r16[16];
+      fetch_pair(g0, sh[0]);
+      fetch_pair(g0 + 2, sh[1]);
+      tmem_ld_32x16(taddr + g0 * 8, r16);
+#pragma unroll 1
+      for (int g = g0; g < g1; g += 4) {
+        tmem_ld_wait();
+        finish_h(g, *reinterpret_cast<const uint32_t(*)[8]>(&r16[0]), sh[0], true);
+        finish_h(g + 1, *reinterpret_cast<const uint32_t(*)[8]>(&r16[8]), sh[0], false);
+        tmem_ld_32x16(taddr + (g + 2) * 8, r16);
+        fetch_pair(g + 4, sh[0]);
+        tmem_ld_wait();
+        if (g + 4 >= g1) {  // this warp's last TMEM load of the tile has completed
+          tc_fence_before();
+          __syncwarp();
+          release();
+        }
+        finish_h(g + 2, *reinterpret_cast<const uint32_t(*)[8]>(&r16[0]), sh[1], true);
+        finish_h(g + 3, *reinterpret_cast<const uint32_t(*)[8]>(&r16[8]), sh[1], false);
+        if (g + 4 < g1) tmem_ld_32x16(taddr + (g + 4) * 8, r16);
+        fetch_pair(g + 6, sh[1]);
+      }
+      return;
+    }
+#endif
     fetch_pair(g0, sh[0]);
     fetch_pair(g0 + 2, sh[1]);
     tmem_ld_32x8(taddr + g0 * 8, ra);
@@ -343,6 +374,41 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
     }
     return;
   }
+#if ATST_EPI_X16
+  // 16 accumulator columns per tcgen05.ld, one buffer: a load is ~1500 cycles under a running main loop whatever its
+  // width, so four round trips per 64-column slice instead of eight; the next load is issued as soon as the two groups
+  // of this one have been taken out of the registers.  Side inputs four groups ahead.  (g1 - g0) % 4 == 0
+  {
+    uint32_t r16[16];
+    float sd[4][8];
+    fetch_side(g0, sd[0]);
+    fetch_side(g0 + 1, sd[1]);
+    fetch_side(g0 + 2, sd[2]);
+    fetch_side(g0 + 3, sd[3]);
+    tmem_ld_32x16(taddr + g0 * 8, r16);
+#pragma unroll 1
+    for (int g = g0; g < g1; g += 4) {
+      tmem_ld_wait();
+      finish(g, *reinterpret_cast<const uint32_t(*)[8]>(&r16[0]), sd[0]);
+      finish(g + 1, *reinterpret_cast<const uint32_t(*)[8]>(&r16[8]), sd[1]);
+      tmem_ld_32x16(taddr + (g + 2) * 8, r16);
+      fetch_side(g + 4, sd[0]);
+      fetch_side(g + 5, sd[1]);
+      tmem_ld_wait();
+      if (g + 4 >= g1) {  // this warp's last TMEM load of the tile has completed
+        tc_fence_before();
+        __syncwarp();
+        release();
+      }
+      finish(g + 2, *reinterpret_cast<const uint32_t(*)[8]>(&r16[0]), sd[2]);
+      finish(g + 3, *reinterpret_cast<const uint32_t(*)[8]>(&r16[8]), sd[3]);
+      if (g + 4 < g1) tmem_ld_32x16(taddr + (g + 4) * 8, r16);
+      fetch_side(g + 6, sd[2]);
+      fetch_side(g + 7, sd[3]);
+    }
+    return;
+  }
+#endif
   // accumulator groups are fetched one ahead (tcgen05.wait::ld waits for every outstanding load, so deeper does not
   // help), side inputs three ahead (their L2 / HBM latency is several groups long); (g1 - g0) % 4 == 0
   uint32_t ra[8], rb[8];
