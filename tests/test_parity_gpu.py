@@ -300,6 +300,8 @@ def test_gelu_fp16_derivative_epilogues(M, N, K):
     assert rel(du, ur.grad) < 6e-4
     with pytest.raises(TypeError):
         ops.gemm_nn(dy, W2, epi=ops.EPI_DGELU_H, aux=u, round_out=True)
+    with pytest.raises(RuntimeError):  # the backward epilogue belongs to the dgrad (NN) GEMM
+        ops.gemm_nt(A, W, bias=b, epi=ops.EPI_DGELU_H, aux=gp, round_out=True)
 
 
 @pytest.mark.parametrize("M,N,K,rps", [(2008, 768, 768, 251), (156, 128, 128, 26), (50003, 768, 768, 7), (2008, 3072, 768, 251)])
