@@ -208,12 +208,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
     }
   };
   if constexpr (kHalf) {
-    // The student's MLP with an fp16 side stream (own kernel instantiation: the loops below are compiled out of it and
-    // this one out of theirs, so neither costs the other registers): EPI_GELU_H stores gelu'(pre-activation) - from the
-    // same cdf / pdf as the GELU itself - and EPI_DGELU_H multiplies by it.  Same pipeline as the two-stream loop at
-    // the end (8-column accumulator loads one ahead).  The side stream moves
-    // as ONE 32-byte sector per PAIR of groups (16 halfs): the even group of a pair loads / the odd group stores the
-    // sector, `hp` carries the other group's four packed words in between.  g0 even, N % 16 == 0 (host-checked).
+    // The GELU classes.  ECLS_HALF_FWD / ECLS_HALF_BWD: the student's MLP with an fp16 side stream - the forward epilogue
+    // stores gelu'(pre-activation), from the same cdf / pdf as the GELU itself, and the dgrad epilogue multiplies by it.
+    // ECLS_GELU: the same forward loop without a side stream (teacher / inference).  Same pipeline as the two-stream
+    // loop at the end (8-column accumulator loads one ahead).  The side stream moves as ONE 32-byte sector per PAIR of
+    // groups (16 halfs): the even group of a pair loads / the odd group stores the sector, `hp` carries the other
+    // group's four packed words in between.  g0 even, N % 16 == 0 (host-checked).
     constexpr bool fwd = ECLS != ECLS_HALF_BWD;
     constexpr bool deriv = ECLS == ECLS_HALF_FWD;  // ECLS_GELU: the same loop without the side stream
     uint16_t* haux = (ECLS != ECLS_GELU && p.aux != nullptr && row_ok)
