@@ -66,6 +66,35 @@ def test_ctypes_signatures_match_the_header():
                 assert "long long" in x, (name, x)
 
 
+def test_epilogue_codes_agree_between_the_enum_the_header_and_python():
+    """GemmEpilogue (csrc/gemm.h) is what the C ABI's `epi` argument means: ops.py mirrors it by value and
+    include/atst_b200.h documents every code a caller may pass."""
+    from audiossl_b200 import ops
+    src = open(os.path.join(ROOT, "audiossl_b200", "csrc", "gemm.h")).read()
+    enum = {k: int(v) for k, v in re.findall(r"\b(EPI_[A-Z_]+)\s*=\s*(\d+)", src)}
+    names = ["EPI_STORE", "EPI_GELU", "EPI_DGELU", "EPI_RESID", "EPI_SCALE", "EPI_RELU", "EPI_GELU_H", "EPI_DGELU_H"]
+    for name in names:
+        assert enum[name] == getattr(ops, name), name
+    assert len({enum[n] for n in names}) == len(names)
+    hdr = open(os.path.join(ROOT, "include", "atst_b200.h")).read()
+    for code in (enum["EPI_GELU_H"], enum["EPI_DGELU_H"]):
+        assert re.search(r"\|\s*%d\s" % code, hdr), "epilogue %d is not documented in the public header" % code
+
+
+def test_aux_dtype_is_checked_before_the_library_is_called():
+    """the fp16 gelu' epilogues take a half aux tensor and the fp32 ones a float one: a mismatch would be read with the
+    wrong stride on the device, so it is refused on the host (no GPU needed to see it)."""
+    import torch
+    from audiossl_b200 import ops
+    A, W = torch.zeros(32, 16), torch.zeros(256, 16)
+    with pytest.raises(TypeError):
+        ops.gemm_nt(A, W, epi=ops.EPI_GELU_H, aux=torch.zeros(32, 256))
+    with pytest.raises(TypeError):
+        ops.gemm_nt(A, W, epi=ops.EPI_GELU, aux=torch.zeros(32, 256, dtype=torch.float16))
+    with pytest.raises(TypeError):
+        ops.gemm_nn(torch.zeros(32, 16), torch.zeros(16, 256), epi=ops.EPI_DGELU_H, aux=torch.zeros(32, 256))
+
+
 def test_no_cpu_fallback():
     from audiossl_b200.models.atst import ATST
     from audiossl_b200.transforms import LogMelSpectrogram
