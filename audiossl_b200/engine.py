@@ -31,10 +31,14 @@ FUSE_GELU_NOSAVE, FUSE_GELU, FUSE_DGELU, FUSE_COLSUM = bool(_FG & 1), bool(_FG &
 HALF_DGELU = bool(_FG & 16) and FUSE_GELU and FUSE_DGELU
 
 
-def half_dgelu():
-    """whether the student's MLP keeps fp16 gelu'(u) (the parity tests configure their emulation with this)"""
+def half_dgelu(hidden=None):
+    """whether the student's MLP keeps fp16 gelu'(u) (the parity tests configure their emulation with this).
+    `hidden` (the MLP width 4 D): the fp16 epilogues exist in the CTA-pair GEMM only, i.e. for widths that are a
+    multiple of 256 or above 1024 (and a multiple of 16); other widths keep the fp32 pre-activation."""
     from . import _lib
-    return HALF_DGELU and not _lib.is_precise()
+    if not HALF_DGELU or _lib.is_precise():
+        return False
+    return hidden is None or ((hidden % 256 == 0 or hidden > 1024) and hidden % 32 == 0)
 # The projector / predictor heads (< 0.1 % of the flops) run as error-compensated 3xTF32 products on unrounded fp32
 # operands: their train-mode BatchNorm over a few hundred rows doubles whatever rounding error enters it, and the BYOL
 # gradient behind it is the ill-conditioned part of the step (DESIGN.md section 3).  ATST_HEADS_3XTF32=0: plain TF32.
@@ -149,7 +153,7 @@ class EncoderEngine:
             if not save and FUSE_GELU_NOSAVE:
                 g = ops.gemm_nt(h2, fp.c(b + "mlp.fc1.weight"), bias=fp.p(b + "mlp.fc1.bias"), epi=ops.EPI_GELU,
                                 aux=None, round_out=True, out=lt("g", (M, 4 * D)))
-            elif save and FUSE_GELU and half_dgelu():
+            elif save and FUSE_GELU and half_dgelu(4 * D):
                 u = lt("gp", (M, 4 * D), torch.float16)   # gelu'(pre-activation), not the pre-activation
                 g = ops.gemm_nt(h2, fp.c(b + "mlp.fc1.weight"), bias=fp.p(b + "mlp.fc1.bias"), epi=ops.EPI_GELU_H,
                                 aux=u, round_out=True, out=lt("g", (M, 4 * D)))

@@ -95,6 +95,21 @@ def test_aux_dtype_is_checked_before_the_library_is_called():
         ops.gemm_nn(torch.zeros(32, 16), torch.zeros(16, 256), epi=ops.EPI_DGELU_H, aux=torch.zeros(32, 256))
 
 
+def test_fp16_side_stream_is_only_chosen_for_widths_the_pair_kernel_serves():
+    """engine.half_dgelu(width): the fp16 gelu' epilogues live in the CTA-pair GEMM (width % 256 == 0 or width > 1024,
+    and a multiple of 32 for the dgrad); any other MLP width keeps the fp32 pre-activation path instead of failing."""
+    from audiossl_b200 import engine
+    assert engine.HALF_DGELU == engine.half_dgelu()  # default library: the switch alone
+    if engine.HALF_DGELU:
+        for width in (512, 768, 1536, 3072, 4096, 1056):
+            assert engine.half_dgelu(width), width
+        for width in (640, 1040, 1100, 96):
+            assert not engine.half_dgelu(width), width
+        import audiossl_b200
+        with audiossl_b200.precision("3xtf32"):
+            assert not engine.half_dgelu(3072)  # the validation build keeps fp32 everywhere
+
+
 def test_no_cpu_fallback():
     from audiossl_b200.models.atst import ATST
     from audiossl_b200.transforms import LogMelSpectrogram
