@@ -342,6 +342,11 @@ def run_torch_gpu(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def _half_stream():
+    from audiossl_b200 import engine
+    return bool(engine.half_dgelu())
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -634,7 +639,11 @@ def run_ours(args):
         "config": {"workload": "%s [%s], 16 kHz, 64 mel, %d crops, %d clips/GPU, DropPath 0.1, "
                                "mel+teacher fwd+student fwd+loss+bwd+AdamW+EMA" % (cfg["name"], args.config, ncrops, B),
                    "parallelism": "dp%d" % world, "l2": "inputs_exceed_l2 (tens of GB of activations per step)",
-                   "step_gflop_per_clip_algorithmic": step_gflop},
+                   "step_gflop_per_clip_algorithmic": step_gflop,
+                   "arithmetic": "TF32 tcgen05 products with fp32 accumulation (heads: 3xTF32), everything else fp32"
+                                 + ("; stored activations fp32 except the student MLP's gelu'(u), kept as fp16 = the "
+                                    "10-bit mantissa of the TF32 rounding its product gets anyway (DESIGN.md section 3)"
+                                    if _half_stream() else "")},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_val, "unit": "clips/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
         "e2e_augmented": None if ms_aug is None else {
