@@ -17,7 +17,9 @@ It restates, in plain numpy / fp32 torch-CPU, the algorithm of the reference
 * ``byol_loss``          - audiossl/models/atst/byol.py:24-41,42-53,57-78.
 * ``ema_update``         - audiossl/models/atst/atst.py:29-34.
 * ``hf_adamw_step``      - transformers 4.x ``AdamW`` (removed from the installed 5.5; restated
-                           from its published algorithm; PARITY UNPINNED for this one function).
+                           from its published algorithm; PARITY UNPINNED for this one function -
+                           its Adam half is cross-checked against torch.optim.Adam through the exact
+                           eps re-parametrisation in tests/test_oracle_golden.py).
 * ``cosine_scheduler_step`` / ``param_groups`` - audiossl/utils/common.py:29-39,41-68.
 
 Pinning: ``tests/golden/make_golden.py`` imports the unmodified reference from
