@@ -110,6 +110,42 @@ def test_fp16_side_stream_is_only_chosen_for_widths_the_pair_kernel_serves():
             assert not engine.half_dgelu(3072)  # the validation build keeps fp32 everywhere
 
 
+def test_built_library_sass_has_the_blackwell_paths_and_no_regressions():
+    """cuobjdump of the in-tree library (no GPU needed): tcgen05 / TMEM / TMA opcodes in every hot kernel, no register
+    spills in the per-class pair-GEMM instantiations, and no GPU-scope fence on the accumulator hand-back (the only
+    MEMBAR.ALL.GPU left in a pair GEMM are the two cluster barriers at kernel start and end)."""
+    import shutil
+    from audiossl_b200 import _lib
+    if shutil.which("cuobjdump") is None or not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("needs cuobjdump and the built library")
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], stdout=subprocess.PIPE, text=True, check=True).stdout
+    kernels, cur = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = kernels.setdefault(m.group(1), {})
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+        if m and cur is not None:
+            op = m.group(1)
+            for w in ("UTCHMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "STL", "MEMBAR.ALL.GPU"):
+                if op == w or op.startswith(w + "."):
+                    cur[w] = cur.get(w, 0) + 1
+    pair = {k: v for k, v in kernels.items() if "gemm2_tf32_kernel" in k}
+    assert len(pair) >= 9, sorted(pair)  # 3 layouts x plain, residual, GELU, 2 fp16 classes, 2 generic
+    for k, c in pair.items():
+        assert c.get("UTCHMMA", 0) > 0 and c.get("LDTM", 0) > 0 and c.get("UTMALDG", 0) > 0, k
+        assert c.get("MEMBAR.ALL.GPU", 0) <= 2, (k, c)
+        if not k.endswith("Li0EEEv14CUtensorMap_stS1_NS_10GemmParamsE"):  # every class but the run-time generic one
+            assert c.get("STL", 0) == 0, (k, c)
+    for name in ("attn_fwd_tc_kernel", "attn_bwd_tc_kernel"):
+        ks = [c for k, c in kernels.items() if name in k]
+        assert ks and all(c.get("UTCHMMA", 0) > 0 and c.get("LDTM", 0) > 0 and c.get("STTM", 0) > 0 and
+                          c.get("UTMALDG", 0) > 0 and c.get("UTMASTG", 0) > 0 for c in ks), name
+    mel = [c for k, c in kernels.items() if "mel_kernel" in k]
+    assert mel and mel[0].get("UBLKCP", 0) > 0
+
+
 def test_no_cpu_fallback():
     from audiossl_b200.models.atst import ATST
     from audiossl_b200.transforms import LogMelSpectrogram
